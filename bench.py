@@ -1,0 +1,340 @@
+#!/usr/bin/env python
+"""bench.py -- SHT pairs/s (alm2map + map2alm, IQU) at nside 2048 / lmax 4000 (BASELINE.json).
+
+One "step" = one pair = comm_map%Y() followed by comm_map%YtW() on an IQU object
+(commander3/src/comm_map_mod.f90:437-455, 546-564): four sharp_execute calls.
+
+  value : whole-job pairs/s with alm and map resident in HBM (CUDA events, max over ranks)
+  e2e   : the same pair through the reference-facing call with HOST buffers (pinned), so the
+          H2D copy of the inputs and the D2H copy of the outputs are inside the timed region
+  roofline     : dominant kernel (spin-2 Legendre) against the FP64-FMA peak measured live
+  cpu_baseline : the CPU restatement (oracle/sht_cpu.c, "port": libsharp2 itself is not
+                 available) on the box's host cores, on a bounded m-subset of the same workload
+
+N > 1 (torchrun): ONE transform pair distributed over N GPUs exactly as libsharp's MPI mode
+shards it (m's and ring pairs round-robin, commander3/src/comm_map_mod.f90:197-261) with an
+NCCL all-to-all of the phases -> strong scaling.
+
+--impl reference times the CPU path (all host threads) on the same config/metric.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "SHT pairs/sec (alm2map+map2alm, IQU) at nside 2048 lmax 4000"
+UNIT = "pairs/s"
+
+
+def ntriples(nside, lmax):
+    return (lmax + 1) * (lmax + 2) / 2 * 2 * nside
+
+
+def workload(args):
+    return {"workload": f"comm_map Y+YtW pair, IQU, nside={args.nside} lmax={args.lmax}, synthetic Gaussian alm",
+            "nside": args.nside, "lmax": args.lmax, "nmaps": 3,
+            "l2_policy": "inputs larger than L2 (alm 0.38 GB, map 1.2 GB, phases 1.6 GB per direction)",
+            "parallelism": "m-distributed alm / ring-distributed map, NCCL all-to-all"}
+
+
+# ------------------------------------------------------------------ CPU baseline / reference arm
+def cpu_pair_sample(nside, lmax, stride, nthreads=0):
+    """Times Y + YtW (spin 0 and spin 2) of the CPU restatement on the m-subset
+    m = 0, stride, 2*stride, ... with all rings.  The Legendre stage scales with the m-subset,
+    the per-ring FFT stage does not, so the two are timed separately inside the C code and the
+    full-workload time is estimated as  t_legendre / work_fraction + t_fft.
+    stride == 1 is the complete workload (no extrapolation).
+    Returns dict(seconds_full_est, frac, threads, simd, t_leg, t_fft)."""
+    import numpy as np
+    from oracle import sht_cpu as S
+    S.build()
+    # one-off FFT plan tables (not part of a transform; libsharp2 also plans once per geometry)
+    tiny = np.array([0], dtype=np.int32)
+    S.execute(S.Y, 0, nside, lmax, alm=np.zeros((1, lmax + 1)), ms=tiny, nthreads=nthreads, mlim_skip=True)
+    ms = np.arange(0, lmax + 1, stride, dtype=np.int32)
+    frac = float(sum(lmax + 1 - m for m in ms)) / ((lmax + 1) * (lmax + 2) / 2)
+    nalm = S.alm_count(lmax, ms)
+    rng = np.random.default_rng(9)
+    almT, almP = rng.standard_normal((1, nalm)), rng.standard_normal((2, nalm))
+    t_leg = t_fft = 0.0
+
+    def acc():
+        nonlocal t_leg, t_fft
+        a, b = S.last_times()
+        t_leg += a
+        t_fft += b
+    t0 = time.perf_counter()
+    mT = S.execute(S.Y, 0, nside, lmax, alm=almT, ms=ms, nthreads=nthreads, mlim_skip=True); acc()
+    mP = S.execute(S.Y, 2, nside, lmax, alm=almP, ms=ms, nthreads=nthreads, mlim_skip=True); acc()
+    S.execute(S.YtW, 0, nside, lmax, map=mT, ms=ms, nthreads=nthreads, mlim_skip=True); acc()
+    S.execute(S.YtW, 2, nside, lmax, map=mP, ms=ms, nthreads=nthreads, mlim_skip=True); acc()
+    wall = time.perf_counter() - t0
+    other = max(wall - t_leg - t_fft, 0.0)   # geometry setup, buffers
+    full = t_leg / frac + t_fft + other
+    return {"seconds_full_est": full, "frac": frac, "wall": wall, "t_leg": t_leg, "t_fft": t_fft,
+            "threads": S.lib().osht_max_threads() if nthreads == 0 else nthreads, "simd": S.lib().variant}
+
+
+def cpu_sample_text(r, stride):
+    if stride == 1:
+        return f"the complete workload, one pair, {r['wall']:.1f} s wall (Legendre {r['t_leg']:.1f} s, FFT {r['t_fft']:.1f} s)"
+    return (f"m = 0,{stride},{2 * stride},... = {100 * r['frac']:.1f}% of the (l,m) work with all rings, {r['wall']:.1f} s wall; "
+            f"full pair estimated as t_legendre/fraction + t_fft = {r['t_leg']:.2f}/{r['frac']:.4f} + {r['t_fft']:.2f} s")
+
+
+def run_reference(args):
+    """The reference arm: the CPU implementation of the path on all host threads.  libsharp2 is not
+    available (not under /root/reference, no network), so this is the oracle port."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    stride = args.cpu_stride if args.cpu_stride > 0 else 8
+    ests = []
+    r = None
+    for i in range(args.warmup + args.steps):
+        r = cpu_pair_sample(args.nside, args.lmax, stride)
+        if i >= args.warmup:
+            ests.append(r["seconds_full_est"])
+    mean_t = sum(ests) / len(ests)
+    value = 1.0 / mean_t
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * mean_t, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload(args),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": r["threads"], "kind": "port",
+                             "sample": "each step: " + cpu_sample_text(r, stride), "simd": r["simd"],
+                             "note": "oracle/sht_cpu.c (OpenMP restatement of the libsharp2 algorithm); libsharp2 "
+                                     "itself is not in /root/reference and cannot be built offline"},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------ clocks sampling
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            self.thr = threading.Thread(target=self._read, daemon=True)
+            self.thr.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.rows.append([x.strip() for x in ln.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        self.thr.join(timeout=2)
+        sm = sorted(int(r[1]) for r in self.rows if len(r) >= 9 and r[1].isdigit())
+        mx = [int(r[2]) for r in self.rows if len(r) >= 9 and r[2].isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) >= 9:
+                for nm, v in zip(names, r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------ GPU arm
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from commander_b200 import comm_map, comm_mapinfo, sharp
+    from commander_b200 import dist as cdist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    comm = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+        comm = cdist.init_from_torch(dev)
+    nside, lmax = args.nside, args.lmax
+    info = comm_mapinfo(comm, nside, lmax, 3, True)
+
+    # synthetic Gaussian alm: value depends on (l, m) only, so results are independent of N
+    g = torch.Generator(device=dev).manual_seed(9)
+    full = None
+    m = comm_map(info, device=dev)
+    l_t = torch.as_tensor(info.lm[0].astype(np.int64), device=dev)
+    m_t = torch.as_tensor(info.lm[1].astype(np.int64), device=dev)
+    key = (l_t * (l_t + 1) + m_t).double()
+    for c in range(3):
+        # cheap deterministic pseudo-Gaussian from a hash of the global index (Box-Muller)
+        u1 = torch.frac(torch.sin(key * 12.9898 + 78.233 * (c + 1)) * 43758.5453).abs().clamp_(1e-12, 1.0)
+        u2 = torch.frac(torch.sin(key * 39.3468 + 11.135 * (c + 1)) * 24634.6345).abs()
+        m.alm[c] = torch.sqrt(-2.0 * torch.log(u1)) * torch.cos(2 * np.pi * u2)
+    m.alm[1:3, l_t < 2] = 0.0
+    del g, full
+    alm_in = m.alm.clone()
+
+    def pair_dev():
+        m.Y()
+        m.YtW()
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # plan creation (coefficient tables, cuFFT plans, Bluestein filters) happens in the warm-up
+    for _ in range(max(args.warmup, 3)):
+        m.alm.copy_(alm_in)
+        pair_dev()
+    sync_all()
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    sharp.set_profiling(True)
+    sharp.last_legendre_ms()
+    n0 = sharp.launch_count()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    sync_all()
+    ev[0].record()
+    for _ in range(args.steps):
+        pair_dev()
+    ev[1].record()
+    sync_all()
+    launches = sharp.launch_count() - n0
+    ms_total = ev[0].elapsed_time(ev[1])
+    leg = sharp.last_legendre_ms()
+    sharp.set_profiling(False)
+    tmax = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    ms_per_step = float(tmax.item()) / args.steps
+    value = 1e3 / ms_per_step
+
+    # ---- end to end through the reference-facing call with pinned host buffers
+    h = comm_map(info)   # numpy host arrays, as the Fortran caller has them
+    pin_alm = torch.empty((3, info.nalm), dtype=torch.float64).pin_memory()
+    pin_map = torch.empty((3, info.np), dtype=torch.float64).pin_memory()
+    pin_alm.copy_(alm_in.cpu())
+    h.alm, h.map = pin_alm.numpy(), pin_map.numpy()
+
+    def pair_host():
+        h.Y()      # H2D alm, kernels, D2H map
+        h.YtW()    # H2D map, kernels, D2H alm
+
+    pair_host()
+    sync_all()
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    t0 = time.perf_counter()
+    ev2 = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    ev2[0].record()
+    for _ in range(e2e_steps):
+        pair_host()
+    ev2[1].record()
+    sync_all()
+    wall = (time.perf_counter() - t0) * 1e3
+    t_e2e = torch.tensor([max(ev2[0].elapsed_time(ev2[1]), 0.0), wall], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
+    e2e_ms = float(t_e2e[0].item()) / e2e_steps
+    clocks = sampler.stop() if rank == 0 else None
+    bytes_alm, bytes_map = 3 * info.nalm * 8, 3 * info.np * 8
+
+    # ---- roofline of the dominant kernel (spin-2 Legendre), FP64 pipe
+    fp64_peak = sharp.measure_fp64_tflops(4096, 5)
+    per = {}
+    for spin, direction, msv in leg:
+        per.setdefault((spin, direction), []).append(msv)
+    avg = {k: sum(v) / len(v) for k, v in per.items()}
+    share = sum(sum(v) for v in per.values()) / max(ms_total, 1e-9)
+    local_frac = float(sum(lmax + 1 - int(mm) for mm in info.ms)) / ((lmax + 1) * (lmax + 2) / 2)
+    flops2 = 28.0 * ntriples(nside, lmax) * local_frac   # nominal flops of one spin-2 launch on this rank
+    dom = max(((k, v) for k, v in avg.items() if k[0] == 2), key=lambda kv: kv[1], default=((2, 1), float("nan")))
+    achieved = flops2 / (dom[1] * 1e-3) / 1e12
+    kern = {f"spin{k[0]}_{'analysis' if k[1] else 'synthesis'}_ms": round(v, 4) for k, v in sorted(avg.items())}
+    kern["legendre_share_of_step"] = round(share, 4)
+    for k, v in sorted(avg.items()):
+        fl = (8.0 if k[0] == 0 else 28.0) * ntriples(nside, lmax) * local_frac
+        kern[f"spin{k[0]}_{'analysis' if k[1] else 'synthesis'}_tflops_nominal"] = round(fl / (v * 1e-3) / 1e12, 3)
+    roofline = {"bound": "fp64", "kernel": f"spin-2 Legendre {'analysis (anal2_kernel)' if dom[0][1] else 'synthesis (synth2_kernel)'}",
+                "achieved": round(achieved, 3), "peak": round(fp64_peak, 3), "unit": "TFLOP/s",
+                "frac": round(achieved / fp64_peak, 4), "traffic": None,
+                "peak_source": "measured live: cmdr_sht_measure_fp64_tflops DFMA probe (MEASURED_PEAKS.json has no FP64 entry)",
+                "flop_convention": "nominal 28 flops per (l,m,ring pair) for spin 2, 8 for spin 0 (SURVEY 8d); no work "
+                                   "subtracted for the m cut-off",
+                "kernels": kern}
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except OSError:
+        pass
+    if peaks.get("hbm_gbs"):
+        hbm_bytes = 2 * (bytes_alm + bytes_map + 2 * 32.0 * 3 * info.nm * 2 * nside)   # per pair, this rank
+        roofline["hbm_secondary"] = {"algorithmic_GB_per_pair": round(hbm_bytes / 1e9, 3),
+                                     "achieved_GBs": round(hbm_bytes / 1e9 / (ms_per_step * 1e-3), 1),
+                                     "peak_GBs_measured": peaks["hbm_gbs"]}
+
+    if rank == 0:
+        cpu = None
+        if not args.no_cpu_baseline:
+            st = args.cpu_stride if args.cpu_stride > 0 else 1
+            r = cpu_pair_sample(nside, lmax, st)
+            cpu = {"value": 1.0 / r["seconds_full_est"], "unit": UNIT, "cores": r["threads"], "kind": "port",
+                   "simd": r["simd"], "sample": cpu_sample_text(r, st)}
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": workload(args), "clocks": clocks, "gpu_launches": int(launches),
+                "gpu_launches_note": "kernels launched by rank 0 inside the timed region (cuFFT execs count 1 each)",
+                "e2e": {"value": 1e3 / e2e_ms, "unit": UNIT, "ms_per_step": e2e_ms, "steps": e2e_steps,
+                        "h2d_bytes_per_step": bytes_alm + bytes_map, "d2h_bytes_per_step": bytes_alm + bytes_map,
+                        "host_buffers": "pinned", "api": "comm_map.Y(); comm_map.YtW()  (4 sharp_execute calls)"},
+                "roofline": roofline, "cpu_baseline": cpu}
+        print(json.dumps(line))
+    if world > 1:
+        cdist.destroy(comm)
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--nside", type=int, default=2048)
+    ap.add_argument("--lmax", type=int, default=4000)
+    ap.add_argument("--cpu-stride", type=int, default=0,
+                    help="CPU sample: every stride-th m (0: full workload for cpu_baseline, 8 for --impl reference)")
+    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,484 @@
+// abi.cu -- the C ABI of libcmdr_sht: handle construction, device residency of the
+// geometry / alm descriptors, host<->device staging and the single-GPU execute paths.
+//
+// Drop-in for the libsharp2 entry points bound by commander3/src/sharp.f90:32-105
+// (SURVEY.md 8b).  Multi-GPU entry points live in dist.cu.
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "kernels.h"
+#include "legendre_core.cuh"
+
+namespace cmdr {
+
+void destroy_plans(sharp_geom_info *g);
+void forget_layout(const sharp_alm_info *a);
+
+static std::atomic<unsigned long long> g_launches{0};
+void count_launch(int n) { g_launches += (unsigned long long)n; }
+
+// ---------------------------------------------------------------- scratch arena
+struct ScratchBuf { void *ptr = nullptr; size_t bytes = 0; };
+static std::map<std::string, ScratchBuf> g_scratch;
+static std::mutex g_mu;
+
+void *scratch_get(const char *name, size_t bytes) {
+  int dev = 0;
+  CMDR_CUDA_CHECK(cudaGetDevice(&dev));
+  std::string key = std::string(name) + "@" + std::to_string(dev);
+  std::lock_guard<std::mutex> lk(g_mu);
+  ScratchBuf &b = g_scratch[key];
+  if (b.bytes < bytes) {
+    if (b.ptr) { CMDR_CUDA_CHECK(cudaDeviceSynchronize()); CMDR_CUDA_CHECK(cudaFree(b.ptr)); }
+    size_t want = bytes + bytes / 16 + 256;
+    CMDR_CUDA_CHECK(cudaMalloc(&b.ptr, want));
+    b.bytes = want;
+  }
+  return b.ptr;
+}
+
+static void scratch_release() {
+  std::lock_guard<std::mutex> lk(g_mu);
+  for (auto &kv : g_scratch) if (kv.second.ptr) cudaFree(kv.second.ptr);
+  g_scratch.clear();
+}
+
+template <typename T>
+static T *upload(const std::vector<T> &v) {  // (dist.cu has its own copy)
+  T *d = nullptr;
+  size_t n = v.size() ? v.size() : 1;
+  CMDR_CUDA_CHECK(cudaMalloc(&d, sizeof(T) * n));
+  if (v.size()) CMDR_CUDA_CHECK(cudaMemcpy(d, v.data(), sizeof(T) * v.size(), cudaMemcpyHostToDevice));
+  return d;
+}
+
+// ---------------------------------------------------------------- device residency
+void ensure_alm_device(sharp_alm_info *a) {
+  int dev = 0;
+  CMDR_CUDA_CHECK(cudaGetDevice(&dev));
+  if (a->device == dev) return;
+  if (a->device >= 0) { fprintf(stderr, "cmdr_sht: alm_info used on two devices\n"); abort(); }
+  a->device = dev;
+  a->d_mval = upload(a->mval);
+  a->d_mvstart = upload(a->mvstart);
+  std::vector<int> m2im(a->mmax + 2, -1);
+  for (int i = 0; i < a->nm; ++i) m2im[a->mval[i]] = i;
+  a->d_m2im = upload(m2im);
+  std::vector<double> K0, K2;
+  build_start_norms(a->mmax < 0 ? 0 : a->mmax, K0, K2);
+  a->d_K0 = upload(K0);
+  a->d_K2 = upload(K2);
+}
+
+void ensure_coef(sharp_alm_info *a, int spin) {
+  CoefDev &c = a->coef[spin ? 1 : 0];
+  if (c.ready) return;
+  std::vector<double> tab; std::vector<long long> ofs;
+  build_coef_table(a->lmax, spin, a->mval, tab, ofs);
+  c.tab = upload(tab);
+  c.ofs = upload(ofs);
+  c.ready = true;
+}
+
+void ensure_geom_device(sharp_geom_info *g) {
+  int dev = 0;
+  CMDR_CUDA_CHECK(cudaGetDevice(&dev));
+  if (g->device == dev) return;
+  if (g->device >= 0) { fprintf(stderr, "cmdr_sht: geom_info used on two devices\n"); abort(); }
+  g->device = dev;
+  std::vector<double> trig(4 * (size_t)g->npairs);
+  for (int p = 0; p < g->npairs; ++p) {
+    trig[4 * p] = g->cth[p]; trig[4 * p + 1] = g->sth[p]; trig[4 * p + 2] = g->sh[p]; trig[4 * p + 3] = g->ch[p];
+  }
+  g->d_trig = upload(trig);
+  g->d_wgt = upload(g->wgt);
+  g->d_nph = upload(g->nph);
+  g->d_shifted = upload(g->shifted);
+  g->d_ofsN = upload(g->ofsN);
+  g->d_ofsS = upload(g->ofsS);
+  std::vector<long long> zbase(g->npairs);
+  std::vector<int> zidx(g->npairs), znp(g->npairs), zlen(g->npairs), zblue(g->npairs);
+  for (const FftRegion &R : g->regions)
+    for (int i = 0; i < R.np; ++i) {
+      int p = R.first + i;
+      zbase[p] = R.base; zidx[p] = i; znp[p] = R.np; zlen[p] = R.len; zblue[p] = R.bluestein ? 1 : 0;
+    }
+  g->d_zbase = upload(zbase); g->d_zidx = upload(zidx); g->d_znp = upload(znp);
+  g->d_zlen = upload(zlen); g->d_zblue = upload(zblue);
+}
+
+// per-ring-pair m cut-off for (lmax, spin)
+const int *ensure_mlim(sharp_geom_info *g, int lmax, int spin) {
+  long long key = ((long long)lmax << 8) | spin;
+  auto it = g->mlim.find(key);
+  if (it != g->mlim.end()) return it->second;
+  std::vector<int> ml(g->npairs);
+  for (int p = 0; p < g->npairs; ++p) ml[p] = mlim_for_ring(lmax, spin, g->sth[p], g->cth[p]);
+  int *d = upload(ml);
+  g->mlim[key] = d;
+  return d;
+}
+
+// ---------------------------------------------------------------- geometry construction
+void ring_trig_ld(int nside, int north, long double &cth, long double &sth, long double &sh, long double &ch) {
+  long double ns = nside;
+  long double omc;   // 1 - cos(theta)
+  if (north < nside) omc = (long double)north * north / (3.0L * ns * ns);
+  else omc = 1.0L - (2.0L * ns - north) * 2.0L / (3.0L * ns);
+  cth = 1.0L - omc;
+  sth = sqrtl(omc * (2.0L - omc));
+  sh = sqrtl(0.5L * omc);
+  ch = sqrtl(1.0L - 0.5L * omc);
+}
+
+static int next_pow2(int v) { int m = 1; while (m < v) m <<= 1; return m; }
+
+}  // namespace cmdr
+
+using namespace cmdr;
+
+// =================================================================== ABI part 1
+extern "C" {
+
+void sharp_make_general_alm_info(int lmax, int nm, int stride, const int *mval, const ptrdiff_t *mvstart,
+                                 int flags, sharp_alm_info **out) {
+  if (stride != 1) { fprintf(stderr, "cmdr_sht: alm stride %d unsupported (only 1)\n", stride); abort(); }
+  sharp_alm_info *a = new sharp_alm_info;
+  a->lmax = lmax; a->nm = nm; a->stride = stride; a->flags = flags;
+  a->real_packed = (flags & SHARP_REAL_HARMONICS) != 0;
+  a->mval.assign(mval, mval + nm);
+  a->mvstart.resize(nm);
+  long long cnt = 0;
+  for (int i = 0; i < nm; ++i) {
+    a->mvstart[i] = (long long)mvstart[i];
+    int m = mval[i];
+    if (m < 0 || m > lmax) { fprintf(stderr, "cmdr_sht: bad m=%d\n", m); abort(); }
+    cnt += (long long)(lmax + 1 - m) * ((a->real_packed && m > 0) ? 2 : 1);
+    if (m > a->mmax) a->mmax = m;
+  }
+  a->nalm = cnt;
+  *out = a;
+}
+
+void sharp_make_mmajor_real_packed_alm_info(int lmax, int stride, int nm, const int *ms, sharp_alm_info **out) {
+  if (stride != 1) { fprintf(stderr, "cmdr_sht: alm stride %d unsupported (only 1)\n", stride); abort(); }
+  std::vector<int> mval(nm);
+  std::vector<ptrdiff_t> mvstart(nm);
+  long long idx = 0;
+  for (int i = 0; i < nm; ++i) {
+    int m = ms ? ms[i] : i;
+    int f = m == 0 ? 1 : 2;
+    mval[i] = m;
+    mvstart[i] = (ptrdiff_t)(idx - (long long)f * m);
+    idx += (long long)f * (lmax + 1 - m);
+  }
+  sharp_make_general_alm_info(lmax, nm, 1, mval.data(), mvstart.data(), SHARP_PACKED | SHARP_REAL_HARMONICS, out);
+}
+
+ptrdiff_t sharp_alm_count(const sharp_alm_info *self) { return (ptrdiff_t)self->nalm; }
+
+void sharp_destroy_alm_info(sharp_alm_info *a) {
+  if (!a) return;
+  if (a->device >= 0) {
+    forget_layout(a);
+    cudaFree(a->d_mval); cudaFree(a->d_mvstart); cudaFree(a->d_m2im); cudaFree(a->d_K0); cudaFree(a->d_K2);
+    for (int s = 0; s < 2; ++s) if (a->coef[s].ready) { cudaFree(a->coef[s].tab); cudaFree(a->coef[s].ofs); }
+  }
+  delete a;
+}
+
+void sharp_make_subset_healpix_geom_info(int nside, int stride, int nrings, const int *rings,
+                                         const double *weight, sharp_geom_info **out) {
+  if (stride != 1) { fprintf(stderr, "cmdr_sht: map stride %d unsupported (only 1)\n", stride); abort(); }
+  sharp_geom_info *g = new sharp_geom_info;
+  g->nside = nside; g->nrings = nrings;
+  const int nn = 2 * nside;
+  std::vector<long long> oN(nn + 1, -1), oS(nn + 1, -1);
+  long long ofs = 0;
+  g->ring.resize(nrings);
+  for (int i = 0; i < nrings; ++i) {
+    int ring = rings ? rings[i] : i + 1;
+    if (ring < 1 || ring > 4 * nside - 1) { fprintf(stderr, "cmdr_sht: bad ring %d\n", ring); abort(); }
+    g->ring[i] = ring;
+    int north = ring > nn ? 4 * nside - ring : ring;
+    int nph = north < nside ? 4 * north : 4 * nside;
+    if (ring == north) oN[north] = ofs; else oS[north] = ofs;
+    ofs += nph;
+  }
+  g->npix = ofs;
+  const double pixarea_w = 4.0 * M_PI / (12.0 * (double)nside * (double)nside);
+  for (int i = 1; i <= nn; ++i) {
+    if (oN[i] < 0 && oS[i] < 0) continue;
+    long double c, s, sh, ch;
+    ring_trig_ld(nside, i, c, s, sh, ch);
+    g->north.push_back(i);
+    g->cth.push_back((double)c); g->sth.push_back((double)s); g->sh.push_back((double)sh); g->ch.push_back((double)ch);
+    g->nph.push_back(i < nside ? 4 * i : 4 * nside);
+    g->shifted.push_back(i < nside ? 1 : (((i - nside) & 1) ? 0 : 1));
+    g->wgt.push_back(pixarea_w * (weight ? weight[i - 1] : 1.0));
+    g->ofsN.push_back(oN[i]); g->ofsS.push_back(oS[i]);
+  }
+  g->npairs = (int)g->north.size();
+  // FFT regions: polar-cap pairs grouped by Bluestein work length, then the belt
+  long long base = 0;
+  int p = 0;
+  while (p < g->npairs && g->north[p] < nside) {
+    int M = next_pow2(2 * g->nph[p] - 1);
+    FftRegion R; R.first = p; R.len = M; R.bluestein = true; R.base = base;
+    while (p < g->npairs && g->north[p] < nside && next_pow2(2 * g->nph[p] - 1) == M) ++p;
+    R.np = p - R.first;
+    base += (long long)R.np * R.len;
+    g->regions.push_back(R);
+  }
+  g->vlen_total = base;
+  if (p < g->npairs) {
+    FftRegion R; R.first = p; R.np = g->npairs - p; R.len = 4 * nside; R.bluestein = false; R.base = base;
+    base += (long long)R.np * R.len;
+    g->regions.push_back(R);
+  }
+  g->zlen_total = base;
+  *out = g;
+}
+
+void sharp_destroy_geom_info(sharp_geom_info *g) {
+  if (!g) return;
+  if (g->device >= 0) {
+    destroy_plans(g);
+    cudaFree(g->d_trig); cudaFree(g->d_wgt); cudaFree(g->d_nph); cudaFree(g->d_shifted);
+    cudaFree(g->d_ofsN); cudaFree(g->d_ofsS); cudaFree(g->d_zbase); cudaFree(g->d_zidx);
+    cudaFree(g->d_znp); cudaFree(g->d_zlen); cudaFree(g->d_zblue);
+    if (g->d_vtab) cudaFree(g->d_vtab);
+    for (auto &kv : g->mlim) cudaFree(kv.second);
+  }
+  delete g;
+}
+
+ptrdiff_t sharp_map_size(const sharp_geom_info *g) { return (ptrdiff_t)g->npix; }
+
+}  // extern "C"
+
+// =================================================================== execution
+namespace cmdr {
+
+thread_local int g_profiling = 0;
+static thread_local std::vector<double> g_prof;   // triples {spin, dir, ms}
+struct ProfEv { cudaEvent_t a, b; int spin, dir; };
+static thread_local std::vector<ProfEv> g_prof_pending;
+
+void prof_begin(int spin, int dir, cudaStream_t st) {
+  if (!g_profiling) return;
+  ProfEv e; e.spin = spin; e.dir = dir;
+  CMDR_CUDA_CHECK(cudaEventCreate(&e.a)); CMDR_CUDA_CHECK(cudaEventCreate(&e.b));
+  CMDR_CUDA_CHECK(cudaEventRecord(e.a, st));
+  g_prof_pending.push_back(e);
+}
+void prof_end(cudaStream_t st) {
+  if (!g_profiling) return;
+  CMDR_CUDA_CHECK(cudaEventRecord(g_prof_pending.back().b, st));
+}
+void prof_collect() {
+  for (auto &e : g_prof_pending) {
+    CMDR_CUDA_CHECK(cudaEventSynchronize(e.b));
+    float ms = 0;
+    CMDR_CUDA_CHECK(cudaEventElapsedTime(&ms, e.a, e.b));
+    g_prof.push_back(e.spin); g_prof.push_back(e.dir); g_prof.push_back(ms);
+    cudaEventDestroy(e.a); cudaEventDestroy(e.b);
+  }
+  g_prof_pending.clear();
+}
+
+bool is_device_ptr(const void *p) {
+  if (!p) return true;
+  cudaPointerAttributes at;
+  cudaError_t e = cudaPointerGetAttributes(&at, p);
+  if (e != cudaSuccess) { cudaGetLastError(); return false; }
+  return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
+}
+
+// Identity (single-rank) phase layout tables, cached per alm_info on the device.
+struct IdLayout { int *m2src = nullptr; int *zeros = nullptr; int *iota = nullptr; };
+static std::map<const sharp_alm_info *, IdLayout> g_idlayout;
+
+PhaseLayout single_layout(sharp_alm_info *a, int npairs, int ncomp_tot, int comp0) {
+  IdLayout &I = g_idlayout[a];
+  if (!I.zeros) {
+    std::vector<int> m2src(a->mmax + 2, -1), z(a->nm + 1, 0), io(a->nm + 1);
+    for (int i = 0; i < a->nm; ++i) m2src[a->mval[i]] = 0;
+    for (int i = 0; i <= a->nm; ++i) io[i] = i;
+    I.m2src = upload(m2src); I.zeros = upload(z); I.iota = upload(io);
+  }
+  PhaseLayout L;
+  L.NPL = npairs; L.NML = a->nm; L.ncomp_tot = ncomp_tot; L.comp0 = comp0;
+  L.mmax = a->mmax; L.m2src = I.m2src; L.m2im = a->d_m2im;
+  L.nm_total = a->nm; L.mlist = a->d_mval; L.mlist_src = I.zeros; L.mlist_im = I.iota;
+  return L;
+}
+
+void forget_layout(const sharp_alm_info *a) {
+  auto it = g_idlayout.find(a);
+  if (it == g_idlayout.end()) return;
+  cudaFree(it->second.m2src); cudaFree(it->second.zeros); cudaFree(it->second.iota);
+  g_idlayout.erase(it);
+}
+
+LegAlm make_legalm(sharp_alm_info *a, int spin) {
+  ensure_alm_device(a);
+  ensure_coef(a, spin);
+  LegAlm A;
+  A.lmax = a->lmax; A.nm = a->nm; A.real_packed = a->real_packed ? 1 : 0;
+  A.mval = a->d_mval; A.mvstart = a->d_mvstart;
+  A.coef = a->coef[spin ? 1 : 0].tab; A.cofs = a->coef[spin ? 1 : 0].ofs;
+  A.Kstart = spin ? a->d_K2 : a->d_K0;
+  return A;
+}
+
+// Single-GPU transform with device pointers.  `ph` holds ncomp_tot components; this call
+// handles components [comp0, comp0+ncomp) of it.
+static void run_single(int type, int spin, double *const *alm, double *const *map, sharp_geom_info *g,
+                       sharp_alm_info *a, int flags, cudaStream_t st) {
+  if (!(spin == 0 || spin == 2)) { fprintf(stderr, "cmdr_sht: spin %d unsupported (0 or 2)\n", spin); abort(); }
+  if (type < 0 || type > 3) { fprintf(stderr, "cmdr_sht: job type %d unsupported\n", type); abort(); }
+  if (flags & SHARP_NO_FFT) { fprintf(stderr, "cmdr_sht: SHARP_NO_FFT unsupported\n"); abort(); }
+  const int ncomp = spin == 0 ? 1 : 2;
+  const bool synth = (type == SHARP_Y || type == SHARP_WY);
+  const bool add = (flags & SHARP_ADD) != 0;
+  ensure_geom_device(g);
+  LegAlm A = make_legalm(a, spin);
+  if (g->npairs == 0 || a->nm == 0) {
+    if (!add) {
+      if (synth) { for (int c = 0; c < ncomp; ++c) if (g->npix) CMDR_CUDA_CHECK(cudaMemsetAsync(map[c], 0, sizeof(double) * g->npix, st)); }
+      else { for (int c = 0; c < ncomp; ++c) if (a->nalm) CMDR_CUDA_CHECK(cudaMemsetAsync(alm[c], 0, sizeof(double) * a->nalm * (a->real_packed ? 1 : 2), st)); }
+    }
+    return;
+  }
+  LegGeom G;
+  G.nslots = g->npairs; G.NPL = g->npairs; G.nowners = 1; G.NML = a->nm; G.ncomp_tot = ncomp; G.comp0 = 0;
+  G.trig = g->d_trig; G.mlim = ensure_mlim(g, a->lmax, spin);
+  PhaseLayout L = single_layout(a, g->npairs, ncomp, 0);
+  double4 *ph = static_cast<double4 *>(scratch_get("phase", sizeof(double4) * (size_t)ncomp * a->nm * g->npairs));
+  if (synth) {
+    prof_begin(spin, 0, st);
+    launch_legendre_synth(spin, G, A, alm, ph, st);
+    prof_end(st);
+    ringfft_synth(g, ncomp, L, ph, map, type == SHARP_WY, add, st);
+  } else {
+    ringfft_anal(g, ncomp, L, ph, map, type == SHARP_YtW, st);
+    if (!add)
+      for (int c = 0; c < ncomp; ++c)
+        CMDR_CUDA_CHECK(cudaMemsetAsync(alm[c], 0, sizeof(double) * a->nalm * (a->real_packed ? 1 : 2), st));
+    prof_begin(spin, 1, st);
+    launch_legendre_anal(spin, G, A, alm, ph, st);
+    prof_end(st);
+  }
+}
+
+// Host/device pointer marshalling shared by sharp_execute and the IQU entry point.
+Staged stage_in(const char *tag, double *const *ptrs, int n, long long count, bool copy_in, cudaStream_t st) {
+  Staged s;
+  s.dev.resize(n); s.host.resize(n);
+  bool dev = true;
+  for (int c = 0; c < n; ++c) dev = dev && is_device_ptr(ptrs[c]);
+  if (dev || count == 0) { for (int c = 0; c < n; ++c) s.dev[c] = ptrs[c]; return s; }
+  s.staged = true;
+  double *buf = static_cast<double *>(scratch_get(tag, sizeof(double) * (size_t)count * n));
+  for (int c = 0; c < n; ++c) {
+    s.host[c] = ptrs[c]; s.dev[c] = buf + (size_t)c * count;
+    if (copy_in) CMDR_CUDA_CHECK(cudaMemcpyAsync(s.dev[c], s.host[c], sizeof(double) * count, cudaMemcpyHostToDevice, st));
+  }
+  return s;
+}
+void stage_out(Staged &s, long long count, cudaStream_t st) {
+  if (!s.staged) return;
+  for (size_t c = 0; c < s.dev.size(); ++c)
+    CMDR_CUDA_CHECK(cudaMemcpyAsync(s.host[c], s.dev[c], sizeof(double) * count, cudaMemcpyDeviceToHost, st));
+}
+
+unsigned long long nominal_flops(const sharp_geom_info *g, const sharp_alm_info *a, int spin) {
+  // (l,m) count over the local m's times ring pairs (an unpaired ring counts half)
+  double nlm = 0;
+  for (int m : a->mval) nlm += a->lmax + 1 - m;
+  double pairs = 0;
+  for (int p = 0; p < g->npairs; ++p) pairs += (g->ofsN[p] >= 0 && g->ofsS[p] >= 0) ? 1.0 : 0.5;
+  return (unsigned long long)(nlm * pairs * (spin == 0 ? 8.0 : 28.0));
+}
+
+void execute_any(int type, int spin, void *alm_v, void *map_v, sharp_geom_info *g, sharp_alm_info *a,
+                 int flags, double *time, unsigned long long *opcnt, cudaStream_t st) {
+  auto t0 = std::chrono::steady_clock::now();
+  const int ncomp = spin == 0 ? 1 : 2;
+  const bool synth = (type == SHARP_Y || type == SHARP_WY);
+  const bool add = (flags & SHARP_ADD) != 0;
+  double *const *alm = static_cast<double *const *>(alm_v);
+  double *const *map = static_cast<double *const *>(map_v);
+  const long long nalm_d = a->nalm * (a->real_packed ? 1 : 2);
+  Staged sa = stage_in("stage_alm", alm, ncomp, nalm_d, synth || add, st);
+  Staged sm = stage_in("stage_map", map, ncomp, g->npix, !synth || add, st);
+  run_single(type, spin, sa.dev.data(), sm.dev.data(), g, a, flags, st);
+  if (synth) stage_out(sm, g->npix, st); else stage_out(sa, nalm_d, st);
+  if (sa.staged || sm.staged || time) CMDR_CUDA_CHECK(cudaStreamSynchronize(st));
+  if (time) *time = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  if (opcnt) *opcnt = nominal_flops(g, a, spin);
+}
+
+}  // namespace cmdr
+
+extern "C" {
+
+void sharp_execute(int type, int spin, void *alm, void *map, const sharp_geom_info *geom_info,
+                   const sharp_alm_info *alm_info, int flags, double *time, unsigned long long *opcnt) {
+  execute_any(type, spin, alm, map, const_cast<sharp_geom_info *>(geom_info),
+              const_cast<sharp_alm_info *>(alm_info), flags, time, opcnt, (cudaStream_t)0);
+}
+
+int cmdr_sht_version(void) { return 100; }
+
+void cmdr_sht_execute_dev(int type, int spin, double *const *alm, double *const *map,
+                          const sharp_geom_info *geom_info, const sharp_alm_info *alm_info, int flags,
+                          void *stream) {
+  run_single(type, spin, alm, map, const_cast<sharp_geom_info *>(geom_info),
+             const_cast<sharp_alm_info *>(alm_info), flags, (cudaStream_t)stream);
+}
+
+void cmdr_sht_execute_iqu(int type, double *const *alm3, double *const *map3, const sharp_geom_info *geom_T,
+                          const sharp_geom_info *geom_P, const sharp_alm_info *alm_info, int flags,
+                          void *stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  sharp_geom_info *gT = const_cast<sharp_geom_info *>(geom_T), *gP = const_cast<sharp_geom_info *>(geom_P);
+  sharp_alm_info *a = const_cast<sharp_alm_info *>(alm_info);
+  const bool synth = (type == SHARP_Y || type == SHARP_WY);
+  const bool add = (flags & SHARP_ADD) != 0;
+  const long long nalm_d = a->nalm * (a->real_packed ? 1 : 2);
+  Staged sa = stage_in("stage_alm", alm3, 3, nalm_d, synth || add, st);
+  Staged sm = stage_in("stage_map", map3, 3, gT->npix, !synth || add, st);
+  run_single(type, 0, sa.dev.data(), sm.dev.data(), gT, a, flags, st);
+  run_single(type, 2, sa.dev.data() + 1, sm.dev.data() + 1, gP, a, flags, st);
+  if (synth) stage_out(sm, gT->npix, st); else stage_out(sa, nalm_d, st);
+  if (sa.staged || sm.staged) CMDR_CUDA_CHECK(cudaStreamSynchronize(st));
+}
+
+unsigned long long cmdr_sht_launch_count(void) { return g_launches.load(); }
+void cmdr_sht_set_profiling(int on) { g_profiling = on; }
+int cmdr_sht_last_legendre_ms(double *entries3, int max) {
+  prof_collect();   // waits for the recorded events; call after synchronising the stream
+  int n = (int)g_prof.size() / 3;
+  if (n > max) n = max;
+  for (int i = 0; i < 3 * n; ++i) entries3[i] = g_prof[i];
+  g_prof.clear();
+  return n;
+}
+unsigned long long cmdr_sht_nominal_flops(const sharp_geom_info *g, const sharp_alm_info *a, int spin) {
+  return nominal_flops(g, a, spin);
+}
+void cmdr_sht_release_caches(void) { scratch_release(); }
+
+}  // extern "C"

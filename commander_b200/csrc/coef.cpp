@@ -1,0 +1,116 @@
+// coef.cpp -- host-side (long double) construction of the recurrence coefficient
+// tables and start-value normalisations used by the Legendre kernels.
+//
+// libsharp2 builds the equivalent tables in its Ylmgen setup, reached from
+// sharp_execute (commander3/src/sharp.f90:234).  Here they are computed once per
+// (alm_info, spin) in 80-bit arithmetic, rounded to FP64 and uploaded.
+//
+// spin 0:  x lam_l = b_{l+1} lam_{l+1} + b_l lam_{l-1},  b_l = sqrt((l^2-m^2)/(4l^2-1))
+//          (the recurrence of commander3/src/math_tools.f90:1003-1023)
+//          lam_l = g_l mu_l,  g_m = g_{m+1} = 1,  g_{l+1} = g_{l-1} b_l / b_{l+1}
+//          mu_{l+1} = A'_l x mu_l - mu_{l-1},      A'_l = g_l / (g_{l+1} b_{l+1})
+// spin s:  L_{l+1} = al_l (x +- C_l) L_l - be_l L_{l-1}   (Wigner d^l_{-m,+-s} times sqrt((2l+1)/4pi))
+//          al_l = sqrt((2l+3)/(2l+1)) (2l+1)(l+1)/D_{l+1},  D_l = sqrt((l^2-m^2)(l^2-s^2))
+//          be_l = sqrt((2l+3)/(2l-1)) (l+1) D_l / (l D_{l+1}),   C_l = m s / (l (l+1))
+//          g_{l0} = g_{l0+1} = 1, g_{l+1} = be_l g_{l-1};  A'_l = al_l g_l / g_{l+1},  C'_l = A'_l C_l
+#include <cmath>
+#include <cstdint>
+#include <thread>
+#include <vector>
+
+#include "sht_internal.h"
+
+namespace cmdr {
+
+static void fill_spin0(int lmax, int m, double *out /* {A', g} per l = m..lmax */) {
+  auto beta = [m](int l) -> long double {
+    return sqrtl(((long double)l * l - (long double)m * m) / (4.0L * l * l - 1.0L));
+  };
+  long double g_prev = 1.0L, g_cur = 1.0L;   // g_{l-1}, g_l
+  for (int l = m; l <= lmax; ++l) {
+    long double b1 = beta(l + 1);
+    long double g_next = (l == m) ? 1.0L : g_prev * beta(l) / b1;
+    long double A = g_cur / (g_next * b1);
+    out[2 * (l - m)] = (double)A;
+    out[2 * (l - m) + 1] = (double)g_cur;
+    g_prev = g_cur; g_cur = g_next;
+  }
+}
+
+static void fill_spins(int lmax, int m, int s, double *out /* {A', C', g, pad} per l = l0..lmax */) {
+  int l0 = m > s ? m : s;
+  auto D = [m, s](int l) -> long double {
+    return sqrtl(((long double)l * l - (long double)m * m) * ((long double)l * l - (long double)s * s));
+  };
+  long double g_prev = 1.0L, g_cur = 1.0L;
+  for (int l = l0; l <= lmax; ++l) {
+    long double l1 = l + 1.0L, D1 = D(l + 1);
+    long double al = sqrtl((2.0L * l + 3.0L) / (2.0L * l + 1.0L)) * (2.0L * l + 1.0L) * l1 / D1;
+    long double g_next;
+    if (l == l0) g_next = 1.0L;
+    else {
+      long double be = sqrtl((2.0L * l + 3.0L) / (2.0L * l - 1.0L)) * l1 * D(l) / (l * D1);
+      g_next = be * g_prev;
+    }
+    long double A = al * g_cur / g_next;
+    long double C = (long double)m * s / ((long double)l * l1);
+    double *o = out + 4 * (size_t)(l - l0);
+    o[0] = (double)A; o[1] = (double)(A * C); o[2] = (double)g_cur; o[3] = 0.0;
+    g_prev = g_cur; g_cur = g_next;
+  }
+}
+
+void build_coef_table(int lmax, int spin, const std::vector<int> &mval, std::vector<double> &tab,
+                      std::vector<long long> &ofs) {
+  const int nm = (int)mval.size();
+  const int per = spin == 0 ? 2 : 4;
+  ofs.assign(nm + 1, 0);
+  for (int i = 0; i < nm; ++i) {
+    int l0 = mval[i] > spin ? mval[i] : spin;
+    long long n = lmax >= l0 ? (lmax - l0 + 1) : 0;
+    ofs[i + 1] = ofs[i] + n * per;
+  }
+  tab.assign((size_t)ofs[nm] + 4, 0.0);
+  unsigned nt = std::thread::hardware_concurrency();
+  if (nt == 0) nt = 4;
+  if (nt > 32) nt = 32;
+  if ((int)nt > nm) nt = nm > 0 ? nm : 1;
+  std::vector<std::thread> th;
+  for (unsigned t = 0; t < nt; ++t) {
+    th.emplace_back([&, t]() {
+      for (int i = (int)t; i < nm; i += (int)nt) {
+        int m = mval[i];
+        int l0 = m > spin ? m : spin;
+        if (lmax < l0) continue;
+        if (spin == 0) fill_spin0(lmax, m, tab.data() + ofs[i]);
+        else fill_spins(lmax, m, spin, tab.data() + ofs[i]);
+      }
+    });
+  }
+  for (auto &t : th) t.join();
+}
+
+// K0[m] = (-1)^m sqrt((2m+1)/(4pi) prod_{k<=m} (2k-1)/(2k))
+// K2[m] : m>=2: (-1)^m sqrt((2m+1)/4pi) sqrt(prod_{k<=m}(2k-1)/(2k)) sqrt((m-1)m/((m+1)(m+2))) * 4
+//         m==0: sqrt(5/4pi) sqrt(6)/4 ; m==1: sqrt(5/4pi) * 2     (see legendre_core.cuh start_spin2)
+void build_start_norms(int mmax, std::vector<double> &K0, std::vector<double> &K2) {
+  K0.assign(mmax + 1, 0.0);
+  K2.assign(mmax + 1, 0.0);
+  const long double fourpi = 4.0L * acosl(-1.0L);
+  long double prod = 1.0L;   // prod_{k<=m} (2k-1)/(2k)
+  for (int m = 0; m <= mmax; ++m) {
+    if (m > 0) prod *= (2.0L * m - 1.0L) / (2.0L * m);
+    long double sg = (m & 1) ? -1.0L : 1.0L;
+    K0[m] = (double)(sg * sqrtl((2.0L * m + 1.0L) / fourpi * prod));
+    if (m >= 2) {
+      long double r = ((long double)(m - 1) * m) / ((long double)(m + 1) * (m + 2));
+      K2[m] = (double)(sg * sqrtl((2.0L * m + 1.0L) / fourpi * prod * r) * 4.0L);
+    } else if (m == 0) {
+      K2[m] = (double)(sqrtl(5.0L / fourpi) * sqrtl(6.0L) / 4.0L);
+    } else {
+      K2[m] = (double)(sqrtl(5.0L / fourpi) * 2.0L);
+    }
+  }
+}
+
+}  // namespace cmdr

@@ -1,0 +1,383 @@
+// dist.cu -- multi-GPU SHT: one process per GPU, libsharp-MPI layout.
+//
+// Replaces sharp_execute_mpi (reached through sharp_execute_mpi_fortran,
+// commander3/src/sharp.f90:96-104,226-232) where libsharp2 does: Allgather of the
+// per-rank m lists and ring-pair colatitudes, Legendre for local m over ALL ring pairs,
+// one MPI_Alltoallv of complex phases, FFT on local rings.  Layout of m's and rings per
+// rank is whatever the caller's handles say (comm_mapinfo uses round-robin,
+// commander3/src/comm_map_mod.f90:197-261); it is discovered with NCCL all-gathers.
+//
+// The exchange is an NCCL all-to-all (grouped ncclSend/ncclRecv over NVLink/NVSwitch).
+// The Legendre kernels write their output directly in the per-destination block layout
+// ([owner][comp][m][ring pair]) and the fold kernel reads the received blocks in place,
+// so there is no separate pack/unpack pass on either side.
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <cstring>
+#include <map>
+#include <tuple>
+
+#include "kernels.h"
+#include "legendre_core.cuh"
+
+namespace cmdr {
+
+#define CMDR_NCCL_CHECK(x)                                                                  \
+  do {                                                                                      \
+    ncclResult_t r_ = (x);                                                                  \
+    if (r_ != ncclSuccess) {                                                                \
+      fprintf(stderr, "cmdr_sht: NCCL error %s at %s:%d\n", nccl_api()->GetErrorString(r_), __FILE__, __LINE__); \
+      abort();                                                                              \
+    }                                                                                       \
+  } while (0)
+
+// NCCL is bound at first use with dlopen so that (a) loading this library never drags a
+// second libnccl into a process that already has one (PyTorch bundles its own), and (b) a
+// single-GPU Commander run needs no NCCL at all.  Order: an already-loaded libnccl.so.2,
+// $CMDR_SHT_NCCL_LIB, then the system libnccl.so.2.
+struct NcclApi {
+  ncclResult_t (*GetUniqueId)(ncclUniqueId *);
+  ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int);
+  ncclResult_t (*CommDestroy)(ncclComm_t);
+  ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t);
+  ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t);
+  ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t);
+  ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t);
+  ncclResult_t (*GroupStart)();
+  ncclResult_t (*GroupEnd)();
+  const char *(*GetErrorString)(ncclResult_t);
+};
+static NcclApi *nccl_api() {
+  static NcclApi api;
+  static bool ready = false;
+  if (ready) return &api;
+  void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
+  if (!h) { const char *e = getenv("CMDR_SHT_NCCL_LIB"); if (e && *e) h = dlopen(e, RTLD_NOW | RTLD_GLOBAL); }
+  if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) { fprintf(stderr, "cmdr_sht: cannot load libnccl.so.2 (%s)\n", dlerror()); abort(); }
+  auto need = [&](const char *name) {
+    void *s = dlsym(h, name);
+    if (!s) { fprintf(stderr, "cmdr_sht: libnccl lacks %s\n", name); abort(); }
+    return s;
+  };
+  api.GetUniqueId = reinterpret_cast<decltype(api.GetUniqueId)>(need("ncclGetUniqueId"));
+  api.CommInitRank = reinterpret_cast<decltype(api.CommInitRank)>(need("ncclCommInitRank"));
+  api.CommDestroy = reinterpret_cast<decltype(api.CommDestroy)>(need("ncclCommDestroy"));
+  api.AllGather = reinterpret_cast<decltype(api.AllGather)>(need("ncclAllGather"));
+  api.AllReduce = reinterpret_cast<decltype(api.AllReduce)>(need("ncclAllReduce"));
+  api.Send = reinterpret_cast<decltype(api.Send)>(need("ncclSend"));
+  api.Recv = reinterpret_cast<decltype(api.Recv)>(need("ncclRecv"));
+  api.GroupStart = reinterpret_cast<decltype(api.GroupStart)>(need("ncclGroupStart"));
+  api.GroupEnd = reinterpret_cast<decltype(api.GroupEnd)>(need("ncclGroupEnd"));
+  api.GetErrorString = reinterpret_cast<decltype(api.GetErrorString)>(need("ncclGetErrorString"));
+  ready = true;
+  return &api;
+}
+
+template <typename T>
+static T *upload_v(const std::vector<T> &v) {
+  T *d = nullptr;
+  size_t n = v.size() ? v.size() : 1;
+  CMDR_CUDA_CHECK(cudaMalloc(&d, sizeof(T) * n));
+  if (v.size()) CMDR_CUDA_CHECK(cudaMemcpy(d, v.data(), sizeof(T) * v.size(), cudaMemcpyHostToDevice));
+  return d;
+}
+
+struct DistPlan {
+  int NPL = 0, NML = 0, mmax = -1, nm_total = 0;
+  int nslots = 0;
+  double *d_trig = nullptr;                 // [nranks*NPL][4]
+  std::map<int, int *> d_mlim;              // per spin: [nranks*NPL]
+  std::vector<double> h_sth, h_cth;         // per slot (0 for empty)
+  std::vector<int> h_valid;
+  int *d_m2src = nullptr, *d_m2im = nullptr, *d_mlist = nullptr, *d_mlist_src = nullptr, *d_mlist_im = nullptr;
+};
+
+struct DistComm {
+  ncclComm_t nccl = nullptr;
+  int rank = 0, nranks = 1, device = 0;
+  std::map<std::tuple<const sharp_geom_info *, const sharp_alm_info *>, DistPlan *> plans;
+};
+
+static std::map<int, DistComm *> g_comms;
+
+static DistComm *find_comm(int comm) {
+  auto it = g_comms.find(comm);
+  return it == g_comms.end() ? nullptr : it->second;
+}
+
+// all-gather a vector of ints padded to `n` entries per rank
+static std::vector<int> allgather_ints(DistComm *C, const std::vector<int> &mine, int n, cudaStream_t st) {
+  std::vector<int> pad(n, -1);
+  std::copy(mine.begin(), mine.end(), pad.begin());
+  int *d_in = upload_v(pad), *d_out = nullptr;
+  CMDR_CUDA_CHECK(cudaMalloc(&d_out, sizeof(int) * (size_t)n * C->nranks));
+  CMDR_NCCL_CHECK(nccl_api()->AllGather(d_in, d_out, n, ncclInt32, C->nccl, st));
+  std::vector<int> out((size_t)n * C->nranks);
+  CMDR_CUDA_CHECK(cudaMemcpyAsync(out.data(), d_out, sizeof(int) * out.size(), cudaMemcpyDeviceToHost, st));
+  CMDR_CUDA_CHECK(cudaStreamSynchronize(st));
+  cudaFree(d_in); cudaFree(d_out);
+  return out;
+}
+
+static DistPlan *get_plan(DistComm *C, sharp_geom_info *g, sharp_alm_info *a, cudaStream_t st) {
+  auto key = std::make_tuple((const sharp_geom_info *)g, (const sharp_alm_info *)a);
+  auto it = C->plans.find(key);
+  if (it != C->plans.end()) return it->second;
+  DistPlan *P = new DistPlan;
+  const int R = C->nranks;
+  // sizes: {nm, npairs, nside, lmax}
+  std::vector<int> sz = allgather_ints(C, {a->nm, g->npairs, g->nside, a->lmax}, 4, st);
+  int NML = 1, NPL = 1;
+  for (int r = 0; r < R; ++r) {
+    if (sz[4 * r + 2] != g->nside || sz[4 * r + 3] != a->lmax) {
+      fprintf(stderr, "cmdr_sht: ranks disagree on nside/lmax\n"); abort();
+    }
+    NML = std::max(NML, sz[4 * r]); NPL = std::max(NPL, sz[4 * r + 1]);
+  }
+  P->NML = NML; P->NPL = NPL; P->nslots = R * NPL;
+  std::vector<int> all_m = allgather_ints(C, a->mval, NML, st);
+  std::vector<int> all_north = allgather_ints(C, g->north, NPL, st);
+  // global slot geometry
+  std::vector<double> trig(4 * (size_t)P->nslots, 0.0);
+  P->h_sth.assign(P->nslots, 0.0); P->h_cth.assign(P->nslots, 0.0); P->h_valid.assign(P->nslots, 0);
+  for (int r = 0; r < R; ++r)
+    for (int j = 0; j < sz[4 * r + 1]; ++j) {
+      int s = r * NPL + j;
+      long double c, sn, sh, ch;
+      ring_trig_ld(g->nside, all_north[(size_t)r * NPL + j], c, sn, sh, ch);
+      trig[4 * s] = (double)c; trig[4 * s + 1] = (double)sn; trig[4 * s + 2] = (double)sh; trig[4 * s + 3] = (double)ch;
+      P->h_sth[s] = (double)sn; P->h_cth[s] = (double)c; P->h_valid[s] = 1;
+    }
+  P->d_trig = upload_v(trig);
+  // global m tables
+  int mmax = -1;
+  for (int r = 0; r < R; ++r) for (int i = 0; i < sz[4 * r]; ++i) mmax = std::max(mmax, all_m[(size_t)r * NML + i]);
+  P->mmax = mmax;
+  std::vector<int> m2src(mmax + 2, -1), m2im(mmax + 2, -1), mlist, mlist_src, mlist_im;
+  for (int r = 0; r < R; ++r)
+    for (int i = 0; i < sz[4 * r]; ++i) {
+      int m = all_m[(size_t)r * NML + i];
+      if (m2src[m] >= 0) { fprintf(stderr, "cmdr_sht: m=%d owned by two ranks\n", m); abort(); }
+      m2src[m] = r; m2im[m] = i;
+      mlist.push_back(m); mlist_src.push_back(r); mlist_im.push_back(i);
+    }
+  P->nm_total = (int)mlist.size();
+  P->d_m2src = upload_v(m2src); P->d_m2im = upload_v(m2im);
+  P->d_mlist = upload_v(mlist); P->d_mlist_src = upload_v(mlist_src); P->d_mlist_im = upload_v(mlist_im);
+  C->plans[key] = P;
+  return P;
+}
+
+static const int *plan_mlim(DistPlan *P, int lmax, int spin) {
+  auto it = P->d_mlim.find(spin);
+  if (it != P->d_mlim.end()) return it->second;
+  std::vector<int> ml(P->nslots, -1);
+  for (int s = 0; s < P->nslots; ++s)
+    if (P->h_valid[s]) ml[s] = mlim_for_ring(lmax, spin, P->h_sth[s], P->h_cth[s]);
+  int *d = upload_v(ml);
+  P->d_mlim[spin] = d;
+  return d;
+}
+
+// all-to-all of equal-sized blocks (in doubles)
+static void alltoall_blocks(DistComm *C, const double *send, double *recv, size_t block, cudaStream_t st) {
+  CMDR_NCCL_CHECK(nccl_api()->GroupStart());
+  for (int r = 0; r < C->nranks; ++r) {
+    if (r == C->rank) continue;
+    CMDR_NCCL_CHECK(nccl_api()->Send(send + (size_t)r * block, block, ncclDouble, r, C->nccl, st));
+    CMDR_NCCL_CHECK(nccl_api()->Recv(recv + (size_t)r * block, block, ncclDouble, r, C->nccl, st));
+  }
+  CMDR_NCCL_CHECK(nccl_api()->GroupEnd());
+  CMDR_CUDA_CHECK(cudaMemcpyAsync(recv + (size_t)C->rank * block, send + (size_t)C->rank * block,
+                                  sizeof(double) * block, cudaMemcpyDeviceToDevice, st));
+  count_launch(1);
+}
+
+struct Part { int spin, comp0, ncomp; sharp_geom_info *g; double *const *alm; double *const *map; };
+
+// Distributed transform over `parts` (one part = one spin with its geometry); all parts
+// share one phase buffer of ncomp_tot components and one exchange.
+static void run_dist(DistComm *C, int type, const Part *parts, int nparts, int ncomp_tot, sharp_alm_info *a,
+                     int flags, cudaStream_t st) {
+  if (type < 0 || type > 3) { fprintf(stderr, "cmdr_sht: job type %d unsupported\n", type); abort(); }
+  const bool synth = (type == SHARP_Y || type == SHARP_WY);
+  const bool add = (flags & SHARP_ADD) != 0;
+  sharp_geom_info *g0 = parts[0].g;
+  for (int i = 0; i < nparts; ++i) {
+    ensure_geom_device(parts[i].g);
+    if (parts[i].g->north != g0->north) { fprintf(stderr, "cmdr_sht: parts use different ring sets\n"); abort(); }
+  }
+  ensure_alm_device(a);
+  DistPlan *P = get_plan(C, g0, a, st);
+  const size_t block = (size_t)ncomp_tot * P->NML * P->NPL * 4;   // doubles per peer block
+  double *bufA = static_cast<double *>(scratch_get("dist_phA", sizeof(double) * block * C->nranks));
+  double *bufB = static_cast<double *>(scratch_get("dist_phB", sizeof(double) * block * C->nranks));
+  PhaseLayout L;
+  L.NPL = P->NPL; L.NML = P->NML; L.ncomp_tot = ncomp_tot; L.mmax = P->mmax;
+  L.m2src = P->d_m2src; L.m2im = P->d_m2im; L.nm_total = P->nm_total;
+  L.mlist = P->d_mlist; L.mlist_src = P->d_mlist_src; L.mlist_im = P->d_mlist_im;
+  LegGeom G;
+  G.nslots = P->nslots; G.NPL = P->NPL; G.nowners = C->nranks; G.NML = P->NML; G.ncomp_tot = ncomp_tot;
+  G.trig = P->d_trig;
+  if (synth) {
+    // padded m rows are never written by the kernels: keep them defined
+    if (a->nm < P->NML) CMDR_CUDA_CHECK(cudaMemsetAsync(bufA, 0, sizeof(double) * block * C->nranks, st));
+    for (int i = 0; i < nparts; ++i) {
+      const Part &p = parts[i];
+      LegAlm A = make_legalm(a, p.spin);
+      G.comp0 = p.comp0; G.mlim = plan_mlim(P, a->lmax, p.spin);
+      prof_begin(p.spin, 0, st);
+      launch_legendre_synth(p.spin, G, A, p.alm, reinterpret_cast<double4 *>(bufA), st);
+      prof_end(st);
+    }
+    alltoall_blocks(C, bufA, bufB, block, st);
+    for (int i = 0; i < nparts; ++i) {
+      const Part &p = parts[i];
+      L.comp0 = p.comp0;
+      if (p.g->npairs == 0) continue;
+      ringfft_synth(p.g, p.ncomp, L, reinterpret_cast<double4 *>(bufB), p.map, type == SHARP_WY, add, st);
+    }
+  } else {
+    CMDR_CUDA_CHECK(cudaMemsetAsync(bufA, 0, sizeof(double) * block * C->nranks, st));
+    for (int i = 0; i < nparts; ++i) {
+      const Part &p = parts[i];
+      L.comp0 = p.comp0;
+      if (p.g->npairs == 0) continue;
+      ringfft_anal(p.g, p.ncomp, L, reinterpret_cast<double4 *>(bufA), p.map, type == SHARP_YtW, st);
+    }
+    alltoall_blocks(C, bufA, bufB, block, st);
+    for (int i = 0; i < nparts; ++i) {
+      const Part &p = parts[i];
+      LegAlm A = make_legalm(a, p.spin);
+      G.comp0 = p.comp0; G.mlim = plan_mlim(P, a->lmax, p.spin);
+      const size_t nd = (size_t)a->nalm * (a->real_packed ? 1 : 2);
+      if (!add && nd)
+        for (int c = 0; c < p.ncomp; ++c) CMDR_CUDA_CHECK(cudaMemsetAsync(p.alm[c], 0, sizeof(double) * nd, st));
+      prof_begin(p.spin, 1, st);
+      launch_legendre_anal(p.spin, G, A, p.alm, reinterpret_cast<const double4 *>(bufB), st);
+      prof_end(st);
+    }
+  }
+}
+
+static void execute_dist_any(DistComm *C, int type, int nparts, const int *spins, double *const *alm,
+                             double *const *map, sharp_geom_info *const *geoms, sharp_alm_info *a, int flags,
+                             cudaStream_t st) {
+  const bool synth = (type == SHARP_Y || type == SHARP_WY);
+  const bool add = (flags & SHARP_ADD) != 0;
+  int ncomp_tot = 0;
+  for (int i = 0; i < nparts; ++i) ncomp_tot += spins[i] == 0 ? 1 : 2;
+  const long long nalm_d = a->nalm * (a->real_packed ? 1 : 2);
+  Staged sa = stage_in("stage_alm", alm, ncomp_tot, nalm_d, synth || add, st);
+  Staged sm = stage_in("stage_map", map, ncomp_tot, geoms[0]->npix, !synth || add, st);
+  Part parts[4];
+  int c0 = 0;
+  for (int i = 0; i < nparts; ++i) {
+    int nc = spins[i] == 0 ? 1 : 2;
+    if (!(spins[i] == 0 || spins[i] == 2)) { fprintf(stderr, "cmdr_sht: spin %d unsupported\n", spins[i]); abort(); }
+    parts[i] = Part{spins[i], c0, nc, geoms[i], sa.dev.data() + c0, sm.dev.data() + c0};
+    c0 += nc;
+  }
+  run_dist(C, type, parts, nparts, ncomp_tot, a, flags, st);
+  if (synth) stage_out(sm, geoms[0]->npix, st); else stage_out(sa, nalm_d, st);
+  if (sa.staged || sm.staged) CMDR_CUDA_CHECK(cudaStreamSynchronize(st));
+}
+
+}  // namespace cmdr
+
+using namespace cmdr;
+
+extern "C" {
+
+void cmdr_sht_get_unique_id(void *id128) {
+  ncclUniqueId id;
+  CMDR_NCCL_CHECK(nccl_api()->GetUniqueId(&id));
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+  memcpy(id128, &id, sizeof(id));
+}
+
+int cmdr_sht_comm_register(int comm, int rank, int nranks, const void *id128) {
+  if (find_comm(comm)) return 0;
+  DistComm *C = new DistComm;
+  C->rank = rank; C->nranks = nranks;
+  CMDR_CUDA_CHECK(cudaGetDevice(&C->device));
+  if (nranks > 1) {
+    ncclUniqueId id;
+    memcpy(&id, id128, sizeof(id));
+    CMDR_NCCL_CHECK(nccl_api()->CommInitRank(&C->nccl, nranks, id, rank));
+  }
+  g_comms[comm] = C;
+  return 0;
+}
+
+void cmdr_sht_comm_destroy(int comm) {
+  DistComm *C = find_comm(comm);
+  if (!C) return;
+  for (auto &kv : C->plans) {
+    DistPlan *P = kv.second;
+    cudaFree(P->d_trig); cudaFree(P->d_m2src); cudaFree(P->d_m2im); cudaFree(P->d_mlist);
+    cudaFree(P->d_mlist_src); cudaFree(P->d_mlist_im);
+    for (auto &m : P->d_mlim) cudaFree(m.second);
+    delete P;
+  }
+  if (C->nccl) nccl_api()->CommDestroy(C->nccl);
+  g_comms.erase(comm);
+  delete C;
+}
+
+void cmdr_sht_execute_dist(int comm, int type, int spin, void *alm, void *map, const sharp_geom_info *geom_info,
+                           const sharp_alm_info *alm_info, int flags, void *stream) {
+  DistComm *C = find_comm(comm);
+  sharp_geom_info *g = const_cast<sharp_geom_info *>(geom_info);
+  sharp_alm_info *a = const_cast<sharp_alm_info *>(alm_info);
+  if (!C || C->nranks == 1) {
+    execute_any(type, spin, alm, map, g, a, flags, nullptr, nullptr, (cudaStream_t)stream);
+    return;
+  }
+  execute_dist_any(C, type, 1, &spin, static_cast<double *const *>(alm), static_cast<double *const *>(map), &g, a,
+                   flags, (cudaStream_t)stream);
+}
+
+void cmdr_sht_execute_iqu_dist(int comm, int type, double *const *alm3, double *const *map3,
+                               const sharp_geom_info *geom_T, const sharp_geom_info *geom_P,
+                               const sharp_alm_info *alm_info, int flags, void *stream) {
+  DistComm *C = find_comm(comm);
+  if (!C || C->nranks == 1) {
+    cmdr_sht_execute_iqu(type, alm3, map3, geom_T, geom_P, alm_info, flags, stream);
+    return;
+  }
+  int spins[2] = {0, 2};
+  sharp_geom_info *gs[2] = {const_cast<sharp_geom_info *>(geom_T), const_cast<sharp_geom_info *>(geom_P)};
+  execute_dist_any(C, type, 2, spins, alm3, map3, gs, const_cast<sharp_alm_info *>(alm_info), flags,
+                   (cudaStream_t)stream);
+}
+
+void cmdr_sht_allreduce_sum(int comm, double *dev_buf, int n, void *stream) {
+  DistComm *C = find_comm(comm);
+  if (!C || C->nranks == 1) return;
+  CMDR_NCCL_CHECK(nccl_api()->AllReduce(dev_buf, dev_buf, n, ncclDouble, ncclSum, C->nccl, (cudaStream_t)stream));
+  count_launch(1);
+}
+
+// commander3/src/sharp.f90:96-104.  `comm` is the MPI_Fint; the group must have been
+// registered (INTEGRATION.md shows the MPI_Bcast of the NCCL id the Fortran side adds).
+void sharp_execute_mpi_fortran(int comm, int type, int spin, void *alm, void *map,
+                               const sharp_geom_info *geom_info, const sharp_alm_info *alm_info, int flags,
+                               double *time, unsigned long long *opcnt) {
+  DistComm *C = find_comm(comm);
+  sharp_geom_info *g = const_cast<sharp_geom_info *>(geom_info);
+  sharp_alm_info *a = const_cast<sharp_alm_info *>(alm_info);
+  if (!C || C->nranks == 1) {
+    execute_any(type, spin, alm, map, g, a, flags, time, opcnt, (cudaStream_t)0);
+    return;
+  }
+  execute_dist_any(C, type, 1, &spin, static_cast<double *const *>(alm), static_cast<double *const *>(map), &g, a,
+                   flags, (cudaStream_t)0);
+  if (time || opcnt) CMDR_CUDA_CHECK(cudaStreamSynchronize(0));
+  if (time) *time = 0.0;
+  if (opcnt) *opcnt = cmdr_sht_nominal_flops(geom_info, alm_info, spin);
+}
+
+}  // extern "C"

@@ -1,0 +1,94 @@
+// kernels.h -- launcher interface between the ABI layer (abi.cu) and the CUDA stages.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
+#include "sht_internal.h"
+
+namespace cmdr {
+
+void count_launch(int n = 1);
+
+// Geometry as the Legendre stage sees it: `nslots` ring-pair slots laid out as
+// [owner][NPL]; slot -> trig (cth,sth,sh,ch) and per-slot m cut-off (-1 = empty slot).
+struct LegGeom {
+  int nslots = 0, NPL = 0, nowners = 1;
+  int NML = 0;                    // padded number of local m's (phase buffer row count per comp)
+  int ncomp_tot = 1, comp0 = 0;   // components in the phase buffer / first one written here
+  const double *trig = nullptr;   // nslots*4
+  const int *mlim = nullptr;      // nslots
+};
+
+// alm side of the Legendre stage (local m's of this rank)
+struct LegAlm {
+  int lmax = 0, nm = 0, real_packed = 1;
+  const int *mval = nullptr;
+  const long long *mvstart = nullptr;
+  const double *coef = nullptr;
+  const long long *cofs = nullptr;
+  const double *Kstart = nullptr;  // K0 (spin 0) or K2 (spin 2), indexed by m
+};
+
+// Phase buffer element: {north re, north im, south re, south im}.
+// Index: ((owner*ncomp_tot + comp0 + c)*NML + im)*NPL + local
+//
+// synthesis: alm (device, ncomp pointers) -> ph ; analysis: ph -> alm (atomic accumulate)
+void launch_legendre_synth(int spin, const LegGeom &g, const LegAlm &a, const double *const *alm,
+                           double4 *ph, cudaStream_t st);
+void launch_legendre_anal(int spin, const LegGeom &g, const LegAlm &a, double *const *alm,
+                          const double4 *ph, cudaStream_t st);
+
+// Ring-FFT stage on the LOCAL rings of `geom` (ringfft.cu).
+// The phase buffer on this side is indexed
+//   ((src*ncomp_tot + comp0 + c)*NML + im_src)*NPL + local_pair
+// with the (m -> src, im) lookup tables below (src = rank that owns m).
+struct PhaseLayout {
+  int NPL = 0, NML = 0, ncomp_tot = 1, comp0 = 0;
+  int mmax = -1;                 // largest m present anywhere
+  const int *m2src = nullptr;    // size mmax+1 (-1: m absent)
+  const int *m2im = nullptr;     // size mmax+1
+  int nm_total = 0;              // number of (src, im) entries (all ranks)
+  const int *mlist = nullptr;    // nm_total: m value
+  const int *mlist_src = nullptr, *mlist_im = nullptr;
+};
+
+void ringfft_synth(sharp_geom_info *geom, int ncomp, const PhaseLayout &L, const double4 *ph,
+                   double *const *map, bool weighted, bool add, cudaStream_t st);
+void ringfft_anal(sharp_geom_info *geom, int ncomp, const PhaseLayout &L, double4 *ph,
+                  const double *const *map, bool weighted, cudaStream_t st);
+
+// scratch memory arena and shared engine helpers (abi.cu)
+void *scratch_get(const char *name, size_t bytes);
+void ensure_alm_device(sharp_alm_info *a);
+void ensure_geom_device(sharp_geom_info *g);
+LegAlm make_legalm(sharp_alm_info *a, int spin);
+void ring_trig_ld(int nside, int north, long double &cth, long double &sth, long double &sh, long double &ch);
+bool is_device_ptr(const void *p);
+extern thread_local int g_profiling;
+void prof_begin(int spin, int dir, cudaStream_t st);
+void prof_end(cudaStream_t st);
+void prof_collect();
+struct Staged {
+  std::vector<double *> dev;
+  std::vector<double *> host;
+  bool staged = false;
+};
+Staged stage_in(const char *tag, double *const *ptrs, int n, long long count, bool copy_in, cudaStream_t st);
+void stage_out(Staged &s, long long count, cudaStream_t st);
+void execute_any(int type, int spin, void *alm_v, void *map_v, sharp_geom_info *g, sharp_alm_info *a,
+                 int flags, double *time, unsigned long long *opcnt, cudaStream_t st);
+
+}  // namespace cmdr
+
+#define CMDR_CUDA_CHECK(x)                                                                   \
+  do {                                                                                       \
+    cudaError_t e_ = (x);                                                                    \
+    if (e_ != cudaSuccess) {                                                                 \
+      fprintf(stderr, "cmdr_sht: CUDA error %s at %s:%d: %s\n", cudaGetErrorName(e_), __FILE__, \
+              __LINE__, cudaGetErrorString(e_));                                             \
+      abort();                                                                               \
+    }                                                                                        \
+  } while (0)

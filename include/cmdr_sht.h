@@ -1,0 +1,166 @@
+/* cmdr_sht.h -- C ABI of the B200-native SHT engine for Commander3.
+ *
+ * Part 1 is the drop-in boundary: exactly the symbols that Commander3's
+ * ISO_C_BINDING shim `commander3/src/sharp.f90` binds.  Linking
+ * Commander against libcmdr_sht.so instead of libsharp2 needs no Fortran change.
+ * Each entry point cites the reference interface it replaces.
+ *
+ * Part 2 is additive (device-resident pointers, fused IQU calls, multi-GPU
+ * bootstrap, counters).  Nothing in part 1 depends on part 2 being called.
+ *
+ * All data is FP64.  There is no CPU fallback: every execute call runs CUDA
+ * kernels on the current device and aborts with a message if that is impossible
+ * (libsharp2 has no error channel either; it aborts on internal assertions).
+ */
+#ifndef CMDR_SHT_H
+#define CMDR_SHT_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Opaque handles (commander3/src/sharp.f90:22-30 keeps them as type(c_ptr)). */
+typedef struct sharp_alm_info sharp_alm_info;
+typedef struct sharp_geom_info sharp_geom_info;
+
+/* Job types, commander3/src/sharp.f90:8-14 */
+enum { SHARP_YtW = 0, SHARP_Y = 1, SHARP_Yt = 2, SHARP_WY = 3, SHARP_ALM2MAP_DERIV1 = 4 };
+/* alm_info flags, commander3/src/sharp.f90:5 and libsharp2 sharp_almhelpers */
+enum { SHARP_PACKED = 1, SHARP_REAL_HARMONICS = 1 << 6 };
+/* job flags, commander3/src/sharp.f90:17-20 */
+enum { SHARP_DP = 1 << 4, SHARP_ADD = 1 << 5, SHARP_NO_FFT = 1 << 7 };
+
+/* ------------------------------------------------------------------ part 1 */
+
+/* commander3/src/sharp.f90:35-42 (declared by the reference, never called).
+ * Complex alm, entry (l,m) at alm[2*(mvstart[im] + stride*l) + {0,1}].  Only
+ * stride==1 is supported. */
+void sharp_make_general_alm_info(int lmax, int nm, int stride, const int *mval,
+                                 const ptrdiff_t *mvstart, int flags,
+                                 sharp_alm_info **alm_info);
+
+/* commander3/src/sharp.f90:44-50, called at :128,:131 from
+ * commander3/src/comm_map_mod.f90:264.  m-major real-packed layout: for each
+ * m in `ms` (NULL -> 0..nm-1) in order, m=0 stores lmax+1 reals, m>0 stores
+ * (lmax+1-m) pairs (alm[+m], alm[-m]) with a_lm = (alm[+m] + i alm[-m])/sqrt2. */
+void sharp_make_mmajor_real_packed_alm_info(int lmax, int stride, int nm, const int *ms,
+                                            sharp_alm_info **alm_info);
+
+/* commander3/src/sharp.f90:52-56 */
+ptrdiff_t sharp_alm_count(const sharp_alm_info *self);
+
+/* commander3/src/sharp.f90:58-61 */
+void sharp_destroy_alm_info(sharp_alm_info *info);
+
+/* commander3/src/sharp.f90:64-71, called at :158,:162 from
+ * commander3/src/comm_map_mod.f90:266-282.  `rings` are 1-based HEALPix ring
+ * numbers (NULL -> 1..nrings), stored in the map in the given order with
+ * stride `stride` (only 1 supported); `weight` has 2*nside entries indexed by
+ * northern-ring number - 1 (NULL -> 1.0); ring weight = 4 pi / npix * weight. */
+void sharp_make_subset_healpix_geom_info(int nside, int stride, int nrings, const int *rings,
+                                         const double *weight, sharp_geom_info **geom_info);
+
+/* commander3/src/sharp.f90:73-76 */
+void sharp_destroy_geom_info(sharp_geom_info *info);
+
+/* commander3/src/sharp.f90:78-82 */
+ptrdiff_t sharp_map_size(const sharp_geom_info *info);
+
+/* commander3/src/sharp.f90:86-94 (called at :234).  `alm` and `map` are arrays of
+ * pointers, one per component (spin 0: 1, spin>0: 2), each to a contiguous
+ * double array.  The pointers may be host memory (pageable or pinned; the
+ * Fortran case) or device memory (detected with cudaPointerGetAttributes).
+ * spin must be 0 or 2.  `time` (seconds) and `opcnt` (nominal flops) are
+ * optional outputs. */
+void sharp_execute(int type, int spin, void *alm, void *map, const sharp_geom_info *geom_info,
+                   const sharp_alm_info *alm_info, int flags, double *time,
+                   unsigned long long *opcnt);
+
+/* commander3/src/sharp.f90:96-104 (called at :227).  `comm` is an MPI_Fint.  This
+ * library does not link MPI: the communicator is looked up in the table filled by
+ * cmdr_sht_comm_register() (part 2); an unregistered comm of a 1-rank run falls
+ * through to sharp_execute.  See INTEGRATION.md for the MPI bootstrap stub. */
+void sharp_execute_mpi_fortran(int comm, int type, int spin, void *alm, void *map,
+                               const sharp_geom_info *geom_info, const sharp_alm_info *alm_info,
+                               int flags, double *time, unsigned long long *opcnt);
+
+/* ------------------------------------------------------------------ part 2 */
+
+int cmdr_sht_version(void);
+
+/* Device-resident variant of sharp_execute: all pointers are device pointers on
+ * the current device, work is enqueued on `stream` (a cudaStream_t; NULL = the
+ * legacy default stream) and the call returns without synchronising. */
+void cmdr_sht_execute_dev(int type, int spin, double *const *alm, double *const *map,
+                          const sharp_geom_info *geom_info, const sharp_alm_info *alm_info,
+                          int flags, void *stream);
+
+/* Fused IQU transform = what comm_map%Y / Yt / YtW / WY do with pol=.true.,
+ * nmaps=3 (commander3/src/comm_map_mod.f90:437-564): spin-0 on component 0 with
+ * geom_T and spin-2 on components 1,2 with geom_P, sharing one phase exchange.
+ * Pointers may be host or device as for sharp_execute; stream as above (host
+ * pointers force a synchronisation before returning). */
+void cmdr_sht_execute_iqu(int type, double *const *alm3, double *const *map3,
+                          const sharp_geom_info *geom_T, const sharp_geom_info *geom_P,
+                          const sharp_alm_info *alm_info, int flags, void *stream);
+
+/* ---- multi-GPU (one process per GPU), libsharp-MPI layout: m's and ring pairs
+ * round-robin per rank (commander3/src/comm_map_mod.f90:197-261), one
+ * all-to-all of phases per transform. */
+
+/* 128-byte NCCL unique id, created on rank 0 and broadcast by the host program
+ * (MPI_Bcast in Commander, torch.distributed in this repo's harness). */
+void cmdr_sht_get_unique_id(void *id128);
+
+/* Collective.  Binds this process (current CUDA device) as `rank` of `nranks`
+ * and registers the group under `comm` (the MPI_Fint the Fortran side passes, or
+ * any integer chosen by the harness).  Returns 0 on success. */
+int cmdr_sht_comm_register(int comm, int rank, int nranks, const void *id128);
+void cmdr_sht_comm_destroy(int comm);
+
+/* Collective distributed transform on a registered comm.  geometry/alm handles
+ * describe this rank's local rings and m's exactly as comm_mapinfo builds them.
+ * Every rank must pass the same nside/lmax and the round-robin layout. */
+void cmdr_sht_execute_dist(int comm, int type, int spin, void *alm, void *map,
+                           const sharp_geom_info *geom_info, const sharp_alm_info *alm_info,
+                           int flags, void *stream);
+void cmdr_sht_execute_iqu_dist(int comm, int type, double *const *alm3, double *const *map3,
+                               const sharp_geom_info *geom_T, const sharp_geom_info *geom_P,
+                               const sharp_alm_info *alm_info, int flags, void *stream);
+
+/* NCCL sum-allreduce of n doubles (device pointer) on the comm: the collective
+ * behind mpi_dot_product (commander3/src/comm_utils.f90:599-614). */
+void cmdr_sht_allreduce_sum(int comm, double *dev_buf, int n, void *stream);
+
+/* ---- introspection for benchmarks/tests */
+
+/* Number of CUDA kernels this library has launched since load (cuFFT execs
+ * count as one each). */
+unsigned long long cmdr_sht_launch_count(void);
+
+/* Event timing of the Legendre kernels of the most recent execute on this
+ * thread: returns the number of entries written (<= max).  Each entry is
+ * {spin, direction(0 synth,1 analysis), milliseconds}.  Only filled when
+ * cmdr_sht_set_profiling(1) was called (adds event records to the stream). */
+void cmdr_sht_set_profiling(int on);
+int cmdr_sht_last_legendre_ms(double *entries3, int max);
+
+/* Nominal flop count of one transform direction (SURVEY.md 8d convention:
+ * 8 flops per (l,m,ring pair) for spin 0, 28 for spin 2, FMA = 2). */
+unsigned long long cmdr_sht_nominal_flops(const sharp_geom_info *geom_info,
+                                          const sharp_alm_info *alm_info, int spin);
+
+/* FP64 FMA throughput of the current device in TFLOP/s (best of `reps` launches of a
+ * register-only DFMA probe, `iters` x 64 FMAs per thread): the roofline denominator for the
+ * Legendre kernels, which MEASURED_PEAKS.json does not carry. */
+double cmdr_sht_measure_fp64_tflops(int iters, int reps);
+
+/* Frees cached device buffers, cuFFT plans and coefficient tables. */
+void cmdr_sht_release_caches(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CMDR_SHT_H */

@@ -39,7 +39,6 @@
 #include <omp.h>
 #endif
 
-#define NV 8              /* ring pairs per vector block */
 #define SCL 800           /* rescaling granularity in bits (libsharp: 2^+-800) */
 #define TBITS 100         /* values below 2^-TBITS are not accumulated */
 
@@ -320,32 +319,48 @@ static void coefs(int lmax, int m, int s, double *A, double *B, double *C) {
   }
 }
 
+/* Vector blocks: NV0 ring pairs per block for spin 0, NV2 for spin 2 (several SIMD
+ * registers per array so that the dependent recurrence chains overlap). */
+#define NV0 32
+#define NV2 16
+#define NVMAX 32
+
 /* --- spin 0 synthesis: outN = sum_l a_l lam_l ; outS = sum_l (-1)^(l+m) a_l lam_l */
 static void leg_synth0(int lmax, int m, const double *A, const double *B,
                        const double *ar, const double *ai, int nb,
                        const double *cth, const double *lam0, const int *scale0,
                        double *oNr, double *oNi, double *oSr, double *oSi) {
-  double x[NV], l1[NV], l2[NV], per[NV], pei[NV], por[NV], poi[NV], cf[NV];
-  int sc[NV];
-  for (int v = 0; v < NV; ++v) {
+  double x[NV0], l1[NV0], l2[NV0], per[NV0], pei[NV0], por[NV0], poi[NV0], cf[NV0];
+  int sc[NV0];
+  for (int v = 0; v < NV0; ++v) {
     int u = v < nb ? v : nb - 1;
     x[v] = cth[u]; l2[v] = lam0[u]; l1[v] = 0; sc[v] = scale0[u];
     per[v] = pei[v] = por[v] = poi[v] = 0;
   }
   int l = m, nact = 0;
-  for (int v = 0; v < NV; ++v) nact += (sc[v] == 0);
-  /* careful phase */
-  while (l <= lmax && nact < NV) {
+  for (int v = 0; v < NV0; ++v) nact += (sc[v] == 0);
+  /* careful phase: some rings still carry a scale factor */
+  while (l <= lmax && nact < NV0) {
+    double a_r = ar[l], a_i = ai[l], Al = A[l], Bl = B[l], mx = 0;
     if (nact > 0) {
-      for (int v = 0; v < NV; ++v) cf[v] = sc[v] == 0 ? l2[v] : 0.0;
-      if ((l - m) & 1) for (int v = 0; v < NV; ++v) { por[v] += cf[v] * ar[l]; poi[v] += cf[v] * ai[l]; }
-      else             for (int v = 0; v < NV; ++v) { per[v] += cf[v] * ar[l]; pei[v] += cf[v] * ai[l]; }
+      for (int v = 0; v < NV0; ++v) cf[v] = sc[v] == 0 ? l2[v] : 0.0;
+      if ((l - m) & 1) {
+#pragma omp simd
+        for (int v = 0; v < NV0; ++v) { por[v] += cf[v] * a_r; poi[v] += cf[v] * a_i; }
+      } else {
+#pragma omp simd
+        for (int v = 0; v < NV0; ++v) { per[v] += cf[v] * a_r; pei[v] += cf[v] * a_i; }
+      }
     }
-    for (int v = 0; v < NV; ++v) {
-      double t = x[v] * A[l] * l2[v] - B[l] * l1[v];
+#pragma omp simd reduction(max:mx)
+    for (int v = 0; v < NV0; ++v) {
+      double t = x[v] * Al * l2[v] - Bl * l1[v];
       l1[v] = l2[v]; l2[v] = t;
-      if (sc[v] < 0 && fabs(t) >= BIG) { l1[v] *= SMALL; l2[v] *= SMALL; if (++sc[v] == 0) ++nact; }
+      mx = fmax(mx, fabs(t));
     }
+    if (mx >= BIG)
+      for (int v = 0; v < NV0; ++v)
+        if (sc[v] < 0 && fabs(l2[v]) >= BIG) { l1[v] *= SMALL; l2[v] *= SMALL; if (++sc[v] == 0) ++nact; }
     ++l;
   }
   /* fast phase, all active */
@@ -353,13 +368,13 @@ static void leg_synth0(int lmax, int m, const double *A, const double *B,
     double a_r = ar[l], a_i = ai[l], Al = A[l], Bl = B[l];
     if ((l - m) & 1) {
 #pragma omp simd
-      for (int v = 0; v < NV; ++v) { por[v] += l2[v] * a_r; poi[v] += l2[v] * a_i; }
+      for (int v = 0; v < NV0; ++v) { por[v] += l2[v] * a_r; poi[v] += l2[v] * a_i; }
     } else {
 #pragma omp simd
-      for (int v = 0; v < NV; ++v) { per[v] += l2[v] * a_r; pei[v] += l2[v] * a_i; }
+      for (int v = 0; v < NV0; ++v) { per[v] += l2[v] * a_r; pei[v] += l2[v] * a_i; }
     }
 #pragma omp simd
-    for (int v = 0; v < NV; ++v) {
+    for (int v = 0; v < NV0; ++v) {
       double t = x[v] * Al * l2[v] - Bl * l1[v];
       l1[v] = l2[v]; l2[v] = t;
     }
@@ -375,9 +390,9 @@ static void leg_anal0(int lmax, int m, const double *A, const double *B,
                       double *ar, double *ai, int nb,
                       const double *cth, const double *lam0, const int *scale0,
                       const double *qNr, const double *qNi, const double *qSr, const double *qSi) {
-  double x[NV], l1[NV], l2[NV], er[NV], ei[NV], odr[NV], odi[NV];
-  int sc[NV];
-  for (int v = 0; v < NV; ++v) {
+  double x[NV0], l1[NV0], l2[NV0], er[NV0], ei[NV0], odr[NV0], odi[NV0], cf[NV0];
+  int sc[NV0];
+  for (int v = 0; v < NV0; ++v) {
     int u = v < nb ? v : nb - 1;
     double z = v < nb ? 1.0 : 0.0;
     x[v] = cth[u]; l2[v] = lam0[u]; l1[v] = 0; sc[v] = scale0[u];
@@ -385,29 +400,36 @@ static void leg_anal0(int lmax, int m, const double *A, const double *B,
     odr[v] = z * (qNr[u] - qSr[u]); odi[v] = z * (qNi[u] - qSi[u]);
   }
   int l = m, nact = 0;
-  for (int v = 0; v < NV; ++v) nact += (sc[v] == 0);
-  while (l <= lmax && nact < NV) {
+  for (int v = 0; v < NV0; ++v) nact += (sc[v] == 0);
+  while (l <= lmax && nact < NV0) {
+    double Al = A[l], Bl = B[l], mx = 0;
     if (nact > 0) {
       double sr = 0, si = 0;
       const double *pr = ((l - m) & 1) ? odr : er, *pi = ((l - m) & 1) ? odi : ei;
-      for (int v = 0; v < NV; ++v) if (sc[v] == 0) { sr += l2[v] * pr[v]; si += l2[v] * pi[v]; }
+      for (int v = 0; v < NV0; ++v) cf[v] = sc[v] == 0 ? l2[v] : 0.0;
+#pragma omp simd reduction(+:sr,si)
+      for (int v = 0; v < NV0; ++v) { sr += cf[v] * pr[v]; si += cf[v] * pi[v]; }
       ar[l] += sr; ai[l] += si;
     }
-    for (int v = 0; v < NV; ++v) {
-      double t = x[v] * A[l] * l2[v] - B[l] * l1[v];
+#pragma omp simd reduction(max:mx)
+    for (int v = 0; v < NV0; ++v) {
+      double t = x[v] * Al * l2[v] - Bl * l1[v];
       l1[v] = l2[v]; l2[v] = t;
-      if (sc[v] < 0 && fabs(t) >= BIG) { l1[v] *= SMALL; l2[v] *= SMALL; if (++sc[v] == 0) ++nact; }
+      mx = fmax(mx, fabs(t));
     }
+    if (mx >= BIG)
+      for (int v = 0; v < NV0; ++v)
+        if (sc[v] < 0 && fabs(l2[v]) >= BIG) { l1[v] *= SMALL; l2[v] *= SMALL; if (++sc[v] == 0) ++nact; }
     ++l;
   }
   for (; l <= lmax; ++l) {
     const double *pr = ((l - m) & 1) ? odr : er, *pi = ((l - m) & 1) ? odi : ei;
     double sr = 0, si = 0, Al = A[l], Bl = B[l];
 #pragma omp simd reduction(+:sr,si)
-    for (int v = 0; v < NV; ++v) { sr += l2[v] * pr[v]; si += l2[v] * pi[v]; }
+    for (int v = 0; v < NV0; ++v) { sr += l2[v] * pr[v]; si += l2[v] * pi[v]; }
     ar[l] += sr; ai[l] += si;
 #pragma omp simd
-    for (int v = 0; v < NV; ++v) {
+    for (int v = 0; v < NV0; ++v) {
       double t = x[v] * Al * l2[v] - Bl * l1[v];
       l1[v] = l2[v]; l2[v] = t;
     }
@@ -422,50 +444,60 @@ static void leg_synths(int lmax, int m, int s, const double *A, const double *B,
                        int nb, const double *cth, const double *P0, const double *M0, const int *scale0,
                        double *QNr, double *QNi, double *UNr, double *UNi,
                        double *QSr, double *QSi, double *USr, double *USi) {
-  double x[NV], p1[NV], p2[NV], m1[NV], m2[NV];
-  double a1r[NV], a1i[NV], a2r[NV], a2i[NV], a3r[NV], a3i[NV], a4r[NV], a4i[NV];
-  int sc[NV];
+  double x[NV2], p1[NV2], p2[NV2], m1[NV2], m2[NV2], cf[NV2];
+  double a1r[NV2], a1i[NV2], a2r[NV2], a2i[NV2], a3r[NV2], a3i[NV2], a4r[NV2], a4i[NV2];
+  int sc[NV2];
   int l0 = m > s ? m : s;
-  for (int v = 0; v < NV; ++v) {
+  for (int v = 0; v < NV2; ++v) {
     int u = v < nb ? v : nb - 1;
     x[v] = cth[u]; p2[v] = P0[u]; m2[v] = M0[u]; p1[v] = m1[v] = 0; sc[v] = scale0[u];
     a1r[v] = a1i[v] = a2r[v] = a2i[v] = a3r[v] = a3i[v] = a4r[v] = a4i[v] = 0;
   }
   int nact = 0;
-  for (int v = 0; v < NV; ++v) nact += (sc[v] == 0);
+  for (int v = 0; v < NV2; ++v) nact += (sc[v] == 0);
   for (int l = l0; l <= lmax; ++l) {
-    double sg = ((l + m + s) & 1) ? -1.0 : 1.0;
-    double Al = A[l], Bl = B[l], Cl = C[l];
-    if (nact == NV) {
+    const double sg = ((l + m + s) & 1) ? -1.0 : 1.0;
+    const double Al = A[l], Bl = B[l], Cl = C[l];
+    const double c_pr = cpr[l], c_pi = cpi[l], c_mr = cmr[l], c_mi = cmi[l];
+    if (nact == NV2) {
 #pragma omp simd
-      for (int v = 0; v < NV; ++v) {
+      for (int v = 0; v < NV2; ++v) {
         double P = p2[v], M = m2[v], sP = sg * P, sM = sg * M;
-        a1r[v] += cpr[l] * P;  a1i[v] += cpi[l] * P;
-        a2r[v] += cmr[l] * M;  a2i[v] += cmi[l] * M;
-        a3r[v] += cpr[l] * sM; a3i[v] += cpi[l] * sM;
-        a4r[v] += cmr[l] * sP; a4i[v] += cmi[l] * sP;
+        a1r[v] += c_pr * P;  a1i[v] += c_pi * P;
+        a2r[v] += c_mr * M;  a2i[v] += c_mi * M;
+        a3r[v] += c_pr * sM; a3i[v] += c_pi * sM;
+        a4r[v] += c_mr * sP; a4i[v] += c_mi * sP;
         double tp = Al * (x[v] + Cl) * P - Bl * p1[v];
         double tm = Al * (x[v] - Cl) * M - Bl * m1[v];
         p1[v] = P; p2[v] = tp; m1[v] = M; m2[v] = tm;
       }
     } else {
-      for (int v = 0; v < NV; ++v) {
-        double P = p2[v], M = m2[v];
-        if (sc[v] == 0) {
-          double sP = sg * P, sM = sg * M;
-          a1r[v] += cpr[l] * P;  a1i[v] += cpi[l] * P;
-          a2r[v] += cmr[l] * M;  a2i[v] += cmi[l] * M;
-          a3r[v] += cpr[l] * sM; a3i[v] += cpi[l] * sM;
-          a4r[v] += cmr[l] * sP; a4i[v] += cmi[l] * sP;
+      double mx = 0;
+      if (nact > 0) {
+        for (int v = 0; v < NV2; ++v) cf[v] = sc[v] == 0 ? 1.0 : 0.0;
+#pragma omp simd
+        for (int v = 0; v < NV2; ++v) {
+          double P = cf[v] * p2[v], M = cf[v] * m2[v], sP = sg * P, sM = sg * M;
+          a1r[v] += c_pr * P;  a1i[v] += c_pi * P;
+          a2r[v] += c_mr * M;  a2i[v] += c_mi * M;
+          a3r[v] += c_pr * sM; a3i[v] += c_pi * sM;
+          a4r[v] += c_mr * sP; a4i[v] += c_mi * sP;
         }
+      }
+#pragma omp simd reduction(max:mx)
+      for (int v = 0; v < NV2; ++v) {
+        double P = p2[v], M = m2[v];
         double tp = Al * (x[v] + Cl) * P - Bl * p1[v];
         double tm = Al * (x[v] - Cl) * M - Bl * m1[v];
         p1[v] = P; p2[v] = tp; m1[v] = M; m2[v] = tm;
-        if (sc[v] < 0 && (fabs(tp) >= BIG || fabs(tm) >= BIG)) {
-          p1[v] *= SMALL; p2[v] *= SMALL; m1[v] *= SMALL; m2[v] *= SMALL;
-          if (++sc[v] == 0) ++nact;
-        }
+        mx = fmax(mx, fmax(fabs(tp), fabs(tm)));
       }
+      if (mx >= BIG)
+        for (int v = 0; v < NV2; ++v)
+          if (sc[v] < 0 && (fabs(p2[v]) >= BIG || fabs(m2[v]) >= BIG)) {
+            p1[v] *= SMALL; p2[v] *= SMALL; m1[v] *= SMALL; m2[v] *= SMALL;
+            if (++sc[v] == 0) ++nact;
+          }
     }
   }
   for (int v = 0; v < nb; ++v) {
@@ -484,11 +516,11 @@ static void leg_anals(int lmax, int m, int s, const double *A, const double *B, 
                       int nb, const double *cth, const double *P0, const double *M0, const int *scale0,
                       const double *QNr, const double *QNi, const double *UNr, const double *UNi,
                       const double *QSr, const double *QSi, const double *USr, const double *USi) {
-  double x[NV], p1[NV], p2[NV], m1[NV], m2[NV];
-  double zpNr[NV], zpNi[NV], zmNr[NV], zmNi[NV], zpSr[NV], zpSi[NV], zmSr[NV], zmSi[NV];
-  int sc[NV];
+  double x[NV2], p1[NV2], p2[NV2], m1[NV2], m2[NV2], cf[NV2];
+  double zpNr[NV2], zpNi[NV2], zmNr[NV2], zmNi[NV2], zpSr[NV2], zpSi[NV2], zmSr[NV2], zmSi[NV2];
+  int sc[NV2];
   int l0 = m > s ? m : s;
-  for (int v = 0; v < NV; ++v) {
+  for (int v = 0; v < NV2; ++v) {
     int u = v < nb ? v : nb - 1;
     double z = v < nb ? 1.0 : 0.0;
     x[v] = cth[u]; p2[v] = P0[u]; m2[v] = M0[u]; p1[v] = m1[v] = 0; sc[v] = scale0[u];
@@ -497,22 +529,47 @@ static void leg_anals(int lmax, int m, int s, const double *A, const double *B, 
     zpSr[v] = z * (QSr[u] - USi[u]); zpSi[v] = z * (QSi[u] + USr[u]);
     zmSr[v] = z * (QSr[u] + USi[u]); zmSi[v] = z * (QSi[u] - USr[u]);
   }
+  int nact = 0;
+  for (int v = 0; v < NV2; ++v) nact += (sc[v] == 0);
   for (int l = l0; l <= lmax; ++l) {
-    double sg = ((l + m + s) & 1) ? -1.0 : 1.0;
-    double Al = A[l], Bl = B[l], Cl = C[l];
+    const double sg = ((l + m + s) & 1) ? -1.0 : 1.0;
+    const double Al = A[l], Bl = B[l], Cl = C[l];
     double s1r = 0, s1i = 0, s2r = 0, s2i = 0;
-    for (int v = 0; v < NV; ++v) {
-      double P = p2[v], M = m2[v];
-      if (sc[v] == 0) {
-        s1r += P * zpNr[v] + sg * M * zpSr[v]; s1i += P * zpNi[v] + sg * M * zpSi[v];
-        s2r += M * zmNr[v] + sg * P * zmSr[v]; s2i += M * zmNi[v] + sg * P * zmSi[v];
+    if (nact == NV2) {
+#pragma omp simd reduction(+:s1r,s1i,s2r,s2i)
+      for (int v = 0; v < NV2; ++v) {
+        double P = p2[v], M = m2[v], sP = sg * P, sM = sg * M;
+        s1r += P * zpNr[v] + sM * zpSr[v]; s1i += P * zpNi[v] + sM * zpSi[v];
+        s2r += M * zmNr[v] + sP * zmSr[v]; s2i += M * zmNi[v] + sP * zmSi[v];
+        double tp = Al * (x[v] + Cl) * P - Bl * p1[v];
+        double tm = Al * (x[v] - Cl) * M - Bl * m1[v];
+        p1[v] = P; p2[v] = tp; m1[v] = M; m2[v] = tm;
       }
-      double tp = Al * (x[v] + Cl) * P - Bl * p1[v];
-      double tm = Al * (x[v] - Cl) * M - Bl * m1[v];
-      p1[v] = P; p2[v] = tp; m1[v] = M; m2[v] = tm;
-      if (sc[v] < 0 && (fabs(tp) >= BIG || fabs(tm) >= BIG)) {
-        p1[v] *= SMALL; p2[v] *= SMALL; m1[v] *= SMALL; m2[v] *= SMALL; ++sc[v];
+    } else {
+      double mx = 0;
+      if (nact > 0) {
+        for (int v = 0; v < NV2; ++v) cf[v] = sc[v] == 0 ? 1.0 : 0.0;
+#pragma omp simd reduction(+:s1r,s1i,s2r,s2i)
+        for (int v = 0; v < NV2; ++v) {
+          double P = cf[v] * p2[v], M = cf[v] * m2[v], sP = sg * P, sM = sg * M;
+          s1r += P * zpNr[v] + sM * zpSr[v]; s1i += P * zpNi[v] + sM * zpSi[v];
+          s2r += M * zmNr[v] + sP * zmSr[v]; s2i += M * zmNi[v] + sP * zmSi[v];
+        }
       }
+#pragma omp simd reduction(max:mx)
+      for (int v = 0; v < NV2; ++v) {
+        double P = p2[v], M = m2[v];
+        double tp = Al * (x[v] + Cl) * P - Bl * p1[v];
+        double tm = Al * (x[v] - Cl) * M - Bl * m1[v];
+        p1[v] = P; p2[v] = tp; m1[v] = M; m2[v] = tm;
+        mx = fmax(mx, fmax(fabs(tp), fabs(tm)));
+      }
+      if (mx >= BIG)
+        for (int v = 0; v < NV2; ++v)
+          if (sc[v] < 0 && (fabs(p2[v]) >= BIG || fabs(m2[v]) >= BIG)) {
+            p1[v] *= SMALL; p2[v] *= SMALL; m1[v] *= SMALL; m2[v] *= SMALL;
+            if (++sc[v] == 0) ++nact;
+          }
     }
     Er[l] += -0.5 * (s1r + s2r); Ei[l] += -0.5 * (s1i + s2i);
     Br[l] += -0.5 * (s1i - s2i); Bi[l] += 0.5 * (s1r - s2r);
@@ -521,6 +578,15 @@ static void leg_anals(int lmax, int m, int s, const double *A, const double *B, 
 
 /* ------------------------------------------------------------------ driver */
 static int g_mlim_skip = 0;
+static double g_t_leg = 0, g_t_fft = 0;   /* wall seconds of the last osht_execute: Legendre, FFT */
+void osht_last_times(double *t2) { t2[0] = g_t_leg; t2[1] = g_t_fft; }
+static double wall(void) {
+#ifdef _OPENMP
+  return omp_get_wtime();
+#else
+  return 0.0;
+#endif
+}
 void osht_set_mlim_skip(int on) { g_mlim_skip = on; }
 int osht_max_threads(void) {
 #ifdef _OPENMP
@@ -576,6 +642,7 @@ int osht_execute(int type, int spin, int nside, int lmax,
 #endif
   const double rt2 = sqrt(2.0), irt2 = 1.0 / rt2;
 
+  double t_a = wall();
   /* ---------------- analysis: rings -> phases */
   if (!synth) {
 #pragma omp parallel
@@ -610,6 +677,7 @@ int osht_execute(int type, int spin, int nside, int lmax,
     }
   }
 
+  double t_b = wall();
   /* ---------------- Legendre over m */
 #pragma omp parallel
   {
@@ -619,7 +687,7 @@ int osht_execute(int type, int spin, int nside, int lmax,
     double *c1 = c0 + (lmax + 2), *c2 = c1 + (lmax + 2), *c3 = c2 + (lmax + 2);
     double *lam0 = malloc(sizeof(double) * (npairs + 1)), *lamM = malloc(sizeof(double) * (npairs + 1));
     int *sc0 = malloc(sizeof(int) * (npairs + 1));
-    double bufs[16][NV];
+    double bufs[16][NVMAX];
 #pragma omp for schedule(dynamic, 1)
     for (int im = 0; im < nm; ++im) {
       int m = ms[im];
@@ -637,8 +705,8 @@ int osht_execute(int type, int spin, int nside, int lmax,
             if (m == 0) { c0[l] = a[l]; c1[l] = 0; }
             else { c0[l] = nrm * a[2*(l-m)]; c1[l] = nrm * a[2*(l-m)+1]; }
           }
-          for (int p = pfirst; p < npairs; p += NV) {
-            int nb = npairs - p < NV ? npairs - p : NV;
+          for (int p = pfirst; p < npairs; p += NV0) {
+            int nb = npairs - p < NV0 ? npairs - p : NV0;
             leg_synth0(lmax, m, A, B, c0, c1, nb, P->cth + p, lam0 + p, sc0 + p,
                        bufs[0], bufs[1], bufs[2], bufs[3]);
             for (int v = 0; v < nb; ++v) {
@@ -648,8 +716,8 @@ int osht_execute(int type, int spin, int nside, int lmax,
           }
         } else {
           for (int l = m; l <= lmax; ++l) c0[l] = c1[l] = 0;
-          for (int p = pfirst; p < npairs; p += NV) {
-            int nb = npairs - p < NV ? npairs - p : NV;
+          for (int p = pfirst; p < npairs; p += NV0) {
+            int nb = npairs - p < NV0 ? npairs - p : NV0;
             for (int v = 0; v < nb; ++v) {
               bufs[0][v] = ph[PH(0,p+v,0,im)]; bufs[1][v] = ph[PH(0,p+v,0,im)+1];
               bufs[2][v] = ph[PH(0,p+v,1,im)]; bufs[3][v] = ph[PH(0,p+v,1,im)+1];
@@ -680,9 +748,9 @@ int osht_execute(int type, int spin, int nside, int lmax,
           }
           for (int p = 0; p < pfirst; ++p)
             for (int c = 0; c < 2; ++c) for (int h = 0; h < 2; ++h) ph[PH(c,p,h,im)] = ph[PH(c,p,h,im)+1] = 0;
-          for (int p = pfirst; p < npairs; p += NV) {
-            int nb = npairs - p < NV ? npairs - p : NV;
-            if (l0 > lmax) { for (int k = 0; k < 8; ++k) for (int v = 0; v < NV; ++v) bufs[k][v] = 0; }
+          for (int p = pfirst; p < npairs; p += NV2) {
+            int nb = npairs - p < NV2 ? npairs - p : NV2;
+            if (l0 > lmax) { for (int k = 0; k < 8; ++k) for (int v = 0; v < NVMAX; ++v) bufs[k][v] = 0; }
             else leg_synths(lmax, m, spin, A, B, C, c0, c1, c2, c3, nb, P->cth + p, lam0 + p, lamM + p, sc0 + p,
                             bufs[0], bufs[1], bufs[2], bufs[3], bufs[4], bufs[5], bufs[6], bufs[7]);
             for (int v = 0; v < nb; ++v) {
@@ -695,8 +763,8 @@ int osht_execute(int type, int spin, int nside, int lmax,
         } else {
           for (int l = 0; l <= lmax; ++l) c0[l] = c1[l] = c2[l] = c3[l] = 0;
           if (l0 <= lmax)
-          for (int p = pfirst; p < npairs; p += NV) {
-            int nb = npairs - p < NV ? npairs - p : NV;
+          for (int p = pfirst; p < npairs; p += NV2) {
+            int nb = npairs - p < NV2 ? npairs - p : NV2;
             for (int v = 0; v < nb; ++v) {
               bufs[0][v] = ph[PH(0,p+v,0,im)]; bufs[1][v] = ph[PH(0,p+v,0,im)+1];
               bufs[2][v] = ph[PH(1,p+v,0,im)]; bufs[3][v] = ph[PH(1,p+v,0,im)+1];
@@ -723,6 +791,7 @@ int osht_execute(int type, int spin, int nside, int lmax,
     free(A); free(B); free(C); free(c0); free(lam0); free(lamM); free(sc0);
   }
 
+  double t_c = wall();
   /* ---------------- synthesis: phases -> rings */
   if (synth) {
 #pragma omp parallel
@@ -758,6 +827,8 @@ int osht_execute(int type, int spin, int nside, int lmax,
       free(z); free(work);
     }
   }
+  double t_d = wall();
+  g_t_leg = t_c - t_b; g_t_fft = (t_b - t_a) + (t_d - t_c);
   free(ph); free(ms); free(mstart); free_pairs(P);
   return 0;
 }

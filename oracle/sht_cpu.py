@@ -47,6 +47,7 @@ def lib():
         L.osht_alm_count.argtypes = [C.c_int, C.c_int, C.c_void_p]
         L.osht_set_mlim_skip.argtypes = [C.c_int]
         L.osht_max_threads.restype = C.c_int
+        L.osht_last_times.argtypes = [C.c_void_p]
         L.variant = v
         _lib = L
     return _lib
@@ -103,3 +104,10 @@ def execute(job, spin, nside, lmax, alm=None, map=None, rings=None, ms=None, wei
     if rc != 0:
         raise RuntimeError(f"osht_execute failed rc={rc}")
     return map if synth else alm
+
+
+def last_times():
+    """(legendre seconds, fft seconds) of the most recent execute()."""
+    t = (C.c_double * 2)()
+    lib().osht_last_times(t)
+    return float(t[0]), float(t[1])

@@ -1,0 +1,129 @@
+"""CPU tests of the host-side logic: the C ABI library loads and exports every symbol the
+header declares (no compute calls without a GPU), descriptor arithmetic, the comm_mapinfo
+layout mirror, and a host emulation of the device Legendre math."""
+import ctypes as C
+import math
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from oracle import sht_def as D
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_abi_exports_every_declared_symbol(shtlib):
+    hdr = open(os.path.join(ROOT, "include", "cmdr_sht.h")).read()
+    declared = set(re.findall(r"\b((?:sharp|cmdr_sht)_[a-z0-9_]+)\s*\(", hdr))
+    declared -= {"sharp_alm_info", "sharp_geom_info"}
+    assert len(declared) >= 23
+    L = shtlib.lib()
+    for sym in sorted(declared):
+        assert hasattr(L, sym), f"libcmdr_sht.so does not export {sym}"
+    assert set(shtlib.ABI_SYMBOLS) == declared
+    assert L.cmdr_sht_version() >= 100
+
+
+def test_library_is_sm100a_only():
+    lib = os.path.join(ROOT, "commander_b200", "lib", "libcmdr_sht.so")
+    if not os.path.exists(lib):
+        pytest.skip("library not built")
+    out = subprocess.run(["cuobjdump", "-lelf", lib], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_\d+a?", out))
+    assert archs == {"sm_100a"}, archs
+
+
+def test_descriptor_counts(shtlib):
+    sharp = shtlib
+    for lmax, ms in ((0, None), (5, None), (12, [0, 3, 6, 9, 12]), (12, [1, 4, 7, 10]), (7, [])):
+        ai = sharp.sharp_make_mmajor_real_packed_alm_info(lmax, ms=ms)
+        assert ai.n_local == D.alm_count(lmax, range(lmax + 1) if ms is None else ms)
+        sharp.sharp_destroy_alm_info(ai)
+    for nside, rings in ((1, None), (2, None), (8, None), (8, [1, 31, 16]), (4, D.mapinfo_rings(4, 2, 5)), (4, [])):
+        gi = sharp.sharp_make_healpix_geom_info(nside, rings=rings)
+        assert gi.n_local == D.map_size(nside, range(1, 4 * nside) if rings is None else rings)
+        sharp.sharp_destroy_geom_info(gi)
+
+
+def test_comm_mapinfo_layout_matches_reference_rules(shtlib):
+    """commander3/src/comm_map_mod.f90:193-261, 1213-1262."""
+    from commander_b200.comm_map import comm_mapinfo
+
+    class FakeComm:
+        handle = None
+
+        def __init__(self, rank, size):
+            self.rank, self.size = rank, size
+    nside, lmax, P = 8, 21, 3
+    seen_pix, seen_lm = [], set()
+    for r in range(P):
+        info = comm_mapinfo(FakeComm(r, P), nside, lmax, 3, True)
+        assert list(info.rings) == D.mapinfo_rings(nside, r, P)
+        assert list(info.ms) == D.mapinfo_ms(lmax, r, P)
+        assert info.np == D.map_size(nside, info.rings) and info.nalm == D.alm_count(lmax, info.ms)
+        assert np.all(np.diff(info.pix) > 0)
+        seen_pix.append(info.pix)
+        idx = D.alm_index(lmax, info.ms)
+        for i, (l, m) in enumerate(idx):
+            assert info.i2lm(i) == (l, m) and info.lm2i(l, m) == i
+            seen_lm.add((l, m))
+        assert info.lm2i(lmax + 1, 0) == -1 and info.lm2i(3, 4) == -1
+        other_m = (r + 1) % P
+        assert info.lm2i(max(other_m, 1) + P * 0 + (0 if other_m else P), other_m if other_m else 0) in (-1, info.lm2i(P, 0))
+        li, mi = info.lm[0], info.lm[1]
+        assert np.array_equal(info.lm2i_vec(li, mi), np.arange(info.nalm))
+        info.dealloc()
+    assert np.array_equal(np.sort(np.concatenate(seen_pix)), np.arange(12 * nside ** 2))
+    assert len(seen_lm) == (lmax + 1) ** 2
+
+
+@pytest.fixture(scope="module")
+def emul():
+    src = os.path.join(ROOT, "tests", "host_emul", "emul_legendre.cpp")
+    coef = os.path.join(ROOT, "commander_b200", "csrc", "coef.cpp")
+    out = os.path.join(ROOT, "tests", "host_emul", "_build")
+    os.makedirs(out, exist_ok=True)
+    so = os.path.join(out, "libemul.so")
+    if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(coef)):
+        subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-o", so, src, coef, "-lpthread"])
+    L = C.CDLL(so)
+    L.emul_lambda.argtypes = [C.c_int] * 5 + [C.c_void_p, C.c_void_p]
+
+    def run(spin, lmax, m, nside, north):
+        P = np.zeros(lmax + 1); M = np.zeros(lmax + 1)
+        L.emul_lambda(spin, lmax, m, nside, north, P.ctypes.data, M.ctypes.data)
+        return P, M
+    return run
+
+
+def test_device_recurrence_math_spin0(emul):
+    """The product's g-scaled recurrence + 2^512 scale bookkeeping (legendre_core.cuh, coef.cpp),
+    executed on the host, against the reference's recurrence (math_tools.f90:926-1028)."""
+    for nside, lmax in ((64, 200), (256, 700)):
+        for m in (0, 1, 2, 3, 17, 100, 199, lmax):
+            for north in (1, 2, nside // 2, nside, nside + 1, 2 * nside - 1, 2 * nside):
+                cth, sth, *_ = D.healpix_ring(nside, north)
+                ref = D.comp_normalised_Plm(lmax, m, math.atan2(sth, cth))
+                P, _ = emul(0, lmax, m, nside, north)
+                # values below 2^-128 are (deliberately) flushed to zero by the product
+                assert np.max(np.abs(P - ref)) <= 2e-12 * max(np.max(np.abs(ref)), 1e-30) + 1e-36
+
+
+def test_device_recurrence_math_spin2(emul):
+    import mpmath as mp
+    mp.mp.dps = 400
+    nside, lmax = 32, 150
+    for m in (0, 1, 2, 3, 40, 120, 150):
+        for north in (1, 3, 20, 32, 50, 64):
+            cth, sth, *_ = D.healpix_ring(nside, north)
+            P, M = emul(2, lmax, m, nside, north)
+            for l in (max(m, 2), max(m, 2) + 1, max(m, 2) + 7, 100, 149, 150):
+                if l > lmax or l < max(m, 2):
+                    continue
+                rp, rm = float(D.slam(l, m, 2, cth, sth)), float(D.slam(l, m, -2, cth, sth))
+                sc = max(abs(rp), abs(rm))
+                assert abs(P[l] - rp) <= 1e-11 * sc + 1e-36 and abs(M[l] - rm) <= 1e-11 * sc + 1e-36
