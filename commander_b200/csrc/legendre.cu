@@ -23,7 +23,7 @@
 
 namespace cmdr {
 
-constexpr int TL = 64;     // l per shared-memory tile
+constexpr int TL = 128;    // l per shared-memory tile (== NT: every thread stages one entry)
 constexpr int NT = 128;    // threads per CTA
 constexpr unsigned FULL = 0xffffffffu;
 constexpr double SCALE_DOWN = 7.458340731200207e-155;   // 2^-512
@@ -46,7 +46,9 @@ struct KParams {
 
 struct __align__(16) TileS0 { double A, ar, ai, pad; };
 struct __align__(16) TileS2 { double A, C, cpr, cpi, cmr, cmi; };
-struct __align__(16) TileA2 { double A, C; };
+struct __align__(16) TileA0 { double A, g; };
+struct __align__(16) TileA2 { double A, C, g, pad; };
+static_assert(TL == NT, "tile staging assumes one entry per thread");
 
 __device__ __forceinline__ size_t ph_index(const KParams &p, int comp, int im, int slot) {
   int owner = slot / p.NPL, local = slot - owner * p.NPL;
@@ -83,7 +85,7 @@ __device__ __forceinline__ void synth0_group(const TileS0 *t, const double (&x)[
 
 template <int R>
 __global__ void __launch_bounds__(NT) synth0_kernel(KParams p) {
-  __shared__ TileS0 tile[TL];
+  __shared__ TileS0 tile[2][TL];
   const int im = blockIdx.y, m = p.mval[im];
   const int tid = threadIdx.x;
   const int chunk0 = blockIdx.x * (NT * R);
@@ -115,35 +117,44 @@ __global__ void __launch_bounds__(NT) synth0_kernel(KParams p) {
   const double *a = p.alm0;
   const long long mvs = p.mvstart[im];
   const double nrm = (p.real_packed && m > 0) ? 0.70710678118654752440 : 1.0;
-  for (int lt = m; lt <= p.lmax; lt += TL) {
-    __syncthreads();
-    if (tid < TL) {
-      int l = lt + tid;
-      TileS0 e{0.0, 0.0, 0.0, 0.0};
-      if (l <= p.lmax) {
-        double2 c = reinterpret_cast<const double2 *>(coef)[l - m];   // {A', g}
-        double gs = c.y * nrm;
-        e.A = c.x;
-        if (p.real_packed) {
-          if (m == 0) { e.ar = gs * a[mvs + l]; }
-          else { e.ar = gs * a[mvs + 2 * (long long)l]; e.ai = gs * a[mvs + 2 * (long long)l + 1]; }
-        } else {
-          e.ar = gs * a[2 * (mvs + l)];
-          e.ai = m == 0 ? 0.0 : gs * a[2 * (mvs + l) + 1];
-        }
+  // Tiles are double buffered: the next tile's global loads are issued before the current
+  // tile is consumed and land in shared memory afterwards -> one barrier per tile and the
+  // global latency is hidden behind the FP64 work.
+  auto load_entry = [&](int l) {
+    TileS0 e{0.0, 0.0, 0.0, 0.0};
+    if (l <= p.lmax) {
+      double2 c = reinterpret_cast<const double2 *>(coef)[l - m];   // {A', g}
+      double gs = c.y * nrm;
+      e.A = c.x;
+      if (p.real_packed) {
+        if (m == 0) { e.ar = gs * a[mvs + l]; }
+        else { e.ar = gs * a[mvs + 2 * (long long)l]; e.ai = gs * a[mvs + 2 * (long long)l + 1]; }
+      } else {
+        e.ar = gs * a[2 * (mvs + l)];
+        e.ai = m == 0 ? 0.0 : gs * a[2 * (mvs + l) + 1];
       }
-      tile[tid] = e;
     }
-    __syncthreads();
+    return e;
+  };
+  tile[0][tid] = load_entry(m + tid);
+  __syncthreads();
+  int buf = 0;
+  for (int lt = m; lt <= p.lmax; lt += TL, buf ^= 1) {
+    const bool more = lt + TL <= p.lmax;
+    TileS0 nxt;
+    if (more) nxt = load_entry(lt + TL + tid);
+    const int ngroups = min(TL, p.lmax - lt + 8) / 8;
 #pragma unroll 1
-    for (int g = 0; g < TL / 8; ++g) {
+    for (int g = 0; g < ngroups; ++g) {
       bool all_on = true, none_on = true;
 #pragma unroll
       for (int r = 0; r < R; ++r) { all_on &= (k[r] == 0); none_on &= (k[r] < 0); }
-      if (__all_sync(FULL, all_on)) synth0_group<2, R>(tile + 8 * g, x, cur, prev, per, pei, por, poi, k);
-      else if (__all_sync(FULL, none_on)) synth0_group<0, R>(tile + 8 * g, x, cur, prev, per, pei, por, poi, k);
-      else synth0_group<1, R>(tile + 8 * g, x, cur, prev, per, pei, por, poi, k);
+      if (__all_sync(FULL, all_on)) synth0_group<2, R>(tile[buf] + 8 * g, x, cur, prev, per, pei, por, poi, k);
+      else if (__all_sync(FULL, none_on)) synth0_group<0, R>(tile[buf] + 8 * g, x, cur, prev, per, pei, por, poi, k);
+      else synth0_group<1, R>(tile[buf] + 8 * g, x, cur, prev, per, pei, por, poi, k);
     }
+    if (more) tile[buf ^ 1][tid] = nxt;
+    __syncthreads();
   }
 #pragma unroll
   for (int r = 0; r < R; ++r)
@@ -196,7 +207,7 @@ __device__ __forceinline__ void synth2_group(const TileS2 *t, const double (&x)[
 
 template <int R>
 __global__ void __launch_bounds__(NT) synth2_kernel(KParams p) {
-  __shared__ TileS2 tile[TL];
+  __shared__ TileS2 tile[2][TL];
   const int im = blockIdx.y, m = p.mval[im];
   const int tid = threadIdx.x;
   const int chunk0 = blockIdx.x * (NT * R);
@@ -233,41 +244,47 @@ __global__ void __launch_bounds__(NT) synth2_kernel(KParams p) {
   const double *aE = p.alm0, *aB = p.alm1;
   const long long mvs = p.mvstart[im];
   const double nrm = (p.real_packed && m > 0) ? 0.70710678118654752440 : 1.0;
-  for (int lt = l0; lt <= p.lmax; lt += TL) {
-    __syncthreads();
-    if (tid < TL) {
-      int l = lt + tid;
-      TileS2 e{0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-      if (l <= p.lmax) {
-        double4 c = reinterpret_cast<const double4 *>(coef)[l - l0];   // {A', C', g, 0}
-        double gs = c.z * nrm;
-        e.A = c.x; e.C = c.y;
-        double er, ei = 0.0, br, bi = 0.0;
-        if (p.real_packed) {
-          if (m == 0) { er = aE[mvs + l]; br = aB[mvs + l]; }
-          else {
-            er = aE[mvs + 2 * (long long)l]; ei = aE[mvs + 2 * (long long)l + 1];
-            br = aB[mvs + 2 * (long long)l]; bi = aB[mvs + 2 * (long long)l + 1];
-          }
-        } else {
-          er = aE[2 * (mvs + l)]; br = aB[2 * (mvs + l)];
-          if (m > 0) { ei = aE[2 * (mvs + l) + 1]; bi = aB[2 * (mvs + l) + 1]; }
+  auto load_entry = [&](int l) {
+    TileS2 e{0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    if (l <= p.lmax) {
+      double4 c = reinterpret_cast<const double4 *>(coef)[l - l0];   // {A', C', g, 0}
+      double gs = c.z * nrm;
+      e.A = c.x; e.C = c.y;
+      double er, ei = 0.0, br, bi = 0.0;
+      if (p.real_packed) {
+        if (m == 0) { er = aE[mvs + l]; br = aB[mvs + l]; }
+        else {
+          er = aE[mvs + 2 * (long long)l]; ei = aE[mvs + 2 * (long long)l + 1];
+          br = aB[mvs + 2 * (long long)l]; bi = aB[mvs + 2 * (long long)l + 1];
         }
-        e.cpr = -gs * (er - bi); e.cpi = -gs * (ei + br);
-        e.cmr = -gs * (er + bi); e.cmi = -gs * (ei - br);
+      } else {
+        er = aE[2 * (mvs + l)]; br = aB[2 * (mvs + l)];
+        if (m > 0) { ei = aE[2 * (mvs + l) + 1]; bi = aB[2 * (mvs + l) + 1]; }
       }
-      tile[tid] = e;
+      e.cpr = -gs * (er - bi); e.cpi = -gs * (ei + br);
+      e.cmr = -gs * (er + bi); e.cmi = -gs * (ei - br);
     }
-    __syncthreads();
+    return e;
+  };
+  tile[0][tid] = load_entry(l0 + tid);
+  __syncthreads();
+  int buf = 0;
+  for (int lt = l0; lt <= p.lmax; lt += TL, buf ^= 1) {
+    const bool more = lt + TL <= p.lmax;
+    TileS2 nxt;
+    if (more) nxt = load_entry(lt + TL + tid);
+    const int ngroups = min(TL, p.lmax - lt + 8) / 8;
 #pragma unroll 1
-    for (int g = 0; g < TL / 8; ++g) {
+    for (int g = 0; g < ngroups; ++g) {
       bool all_on = true, none_on = true;
 #pragma unroll
       for (int r = 0; r < R; ++r) { all_on &= (k[r] == 0); none_on &= (k[r] < 0); }
-      if (__all_sync(FULL, all_on)) synth2_group<2, R>(tile + 8 * g, x, P, Pp, M, Mp, a, k);
-      else if (__all_sync(FULL, none_on)) synth2_group<0, R>(tile + 8 * g, x, P, Pp, M, Mp, a, k);
-      else synth2_group<1, R>(tile + 8 * g, x, P, Pp, M, Mp, a, k);
+      if (__all_sync(FULL, all_on)) synth2_group<2, R>(tile[buf] + 8 * g, x, P, Pp, M, Mp, a, k);
+      else if (__all_sync(FULL, none_on)) synth2_group<0, R>(tile[buf] + 8 * g, x, P, Pp, M, Mp, a, k);
+      else synth2_group<1, R>(tile[buf] + 8 * g, x, P, Pp, M, Mp, a, k);
     }
+    if (more) tile[buf ^ 1][tid] = nxt;
+    __syncthreads();
   }
   // sg_l = (-1)^(l+m+2) = sg0 * (-1)^(l-l0)
   const double sg0 = ((l0 + m) & 1) ? -0.5 : 0.5;
@@ -339,13 +356,13 @@ __device__ __forceinline__ void warp_reduce_scatter4(double (&v)[4], int lane) {
 // spin-0 analysis:  a_l = sum_rings mu_l * (l-m even ? qN+qS : qN-qS)
 // ------------------------------------------------------------------------------------
 template <int MODE, int R>
-__device__ __forceinline__ void anal0_group(const double *tA, const double (&x)[R], double (&cur)[R],
+__device__ __forceinline__ void anal0_group(const TileA0 *tA, const double (&x)[R], double (&cur)[R],
                                             double (&prev)[R], const double (&sr)[R], const double (&si)[R],
                                             const double (&dr)[R], const double (&di)[R], int (&k)[R],
                                             double (&accr)[8], double (&acci)[8]) {
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    const double A = tA[j];
+    const double A = tA[j].A;
     double ar = 0.0, ai = 0.0;
 #pragma unroll
     for (int r = 0; r < R; ++r) {
@@ -368,8 +385,8 @@ __device__ __forceinline__ void anal0_group(const double *tA, const double (&x)[
 
 template <int R>
 __global__ void __launch_bounds__(NT) anal0_kernel(KParams p) {
-  __shared__ double tileA[TL];
-  __shared__ double red[NT / 32][TL][2];
+  __shared__ TileA0 tile[2][TL];
+  __shared__ double red[2][NT / 32][TL][2];
   const int im = blockIdx.y, m = p.mval[im];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int chunk0 = blockIdx.x * (NT * R);
@@ -397,38 +414,47 @@ __global__ void __launch_bounds__(NT) anal0_kernel(KParams p) {
   const double *coef = p.coef + p.cofs[im];
   const long long mvs = p.mvstart[im];
   const double nrm = (p.real_packed && m > 0) ? 0.70710678118654752440 : 1.0;
-  for (int lt = m; lt <= p.lmax; lt += TL) {
-    __syncthreads();
-    if (tid < TL) {
-      int l = lt + tid;
-      tileA[tid] = l <= p.lmax ? coef[2 * (l - m)] : 0.0;
-    }
-    __syncthreads();
+  auto load_entry = [&](int l) {
+    TileA0 e{0.0, 0.0};
+    if (l <= p.lmax) { double2 c = reinterpret_cast<const double2 *>(coef)[l - m]; e.A = c.x; e.g = c.y; }
+    return e;
+  };
+  tile[0][tid] = load_entry(m + tid);
+  __syncthreads();
+  int buf = 0;
+  for (int lt = m; lt <= p.lmax; lt += TL, buf ^= 1) {
+    const bool more = lt + TL <= p.lmax;
+    TileA0 nxt;
+    if (more) nxt = load_entry(lt + TL + tid);
+    const int ngroups = min(TL, p.lmax - lt + 8) / 8;
 #pragma unroll 1
-    for (int g = 0; g < TL / 8; ++g) {
+    for (int g = 0; g < ngroups; ++g) {
       bool all_on = true, none_on = true;
 #pragma unroll
       for (int r = 0; r < R; ++r) { all_on &= (k[r] == 0); none_on &= (k[r] < 0); }
       double accr[8], acci[8];
       const bool w_none = __all_sync(FULL, none_on);
-      if (__all_sync(FULL, all_on)) anal0_group<2, R>(tileA + 8 * g, x, cur, prev, sr, si, dr, di, k, accr, acci);
-      else if (w_none) anal0_group<0, R>(tileA + 8 * g, x, cur, prev, sr, si, dr, di, k, accr, acci);
-      else anal0_group<1, R>(tileA + 8 * g, x, cur, prev, sr, si, dr, di, k, accr, acci);
+      if (__all_sync(FULL, all_on)) anal0_group<2, R>(tile[buf] + 8 * g, x, cur, prev, sr, si, dr, di, k, accr, acci);
+      else if (w_none) anal0_group<0, R>(tile[buf] + 8 * g, x, cur, prev, sr, si, dr, di, k, accr, acci);
+      else anal0_group<1, R>(tile[buf] + 8 * g, x, cur, prev, sr, si, dr, di, k, accr, acci);
       if (!w_none) { warp_reduce_scatter8(accr, lane); warp_reduce_scatter8(acci, lane); }
       if ((lane & 3) == 0) {
         int j = (lane >> 2) & 7;
-        red[warp][8 * g + j][0] = w_none ? 0.0 : accr[0];
-        red[warp][8 * g + j][1] = w_none ? 0.0 : acci[0];
+        red[buf][warp][8 * g + j][0] = w_none ? 0.0 : accr[0];
+        red[buf][warp][8 * g + j][1] = w_none ? 0.0 : acci[0];
       }
     }
+    if (more) tile[buf ^ 1][tid] = nxt;
     __syncthreads();
-    if (tid < TL) {
+    // cross-warp sum of this tile (one l per thread); red[buf]/tile[buf] are rewritten only
+    // after the next barrier
+    {
       int l = lt + tid;
       if (l <= p.lmax) {
         double re = 0.0, im_ = 0.0;
 #pragma unroll
-        for (int w = 0; w < NT / 32; ++w) { re += red[w][tid][0]; im_ += red[w][tid][1]; }
-        double gs = coef[2 * (l - m) + 1] * nrm;
+        for (int w = 0; w < NT / 32; ++w) { re += red[buf][w][tid][0]; im_ += red[buf][w][tid][1]; }
+        double gs = tile[buf][tid].g * nrm;
         double *a = p.alm0;
         if (p.real_packed) {
           if (m == 0) atomicAdd(&a[mvs + l], gs * re);
@@ -488,8 +514,8 @@ __device__ __forceinline__ void anal2_group(const TileA2 *t, const double (&x)[R
 
 template <int R>
 __global__ void __launch_bounds__(NT) anal2_kernel(KParams p) {
-  __shared__ TileA2 tile[TL];
-  __shared__ double red[NT / 32][TL][4];
+  __shared__ TileA2 tile[2][TL];
+  __shared__ double red[2][NT / 32][TL][4];
   const int im = blockIdx.y, m = p.mval[im];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int chunk0 = blockIdx.x * (NT * R);
@@ -524,25 +550,29 @@ __global__ void __launch_bounds__(NT) anal2_kernel(KParams p) {
   const double *coef = p.coef + p.cofs[im];
   const long long mvs = p.mvstart[im];
   const double nrm = (p.real_packed && m > 0) ? 0.70710678118654752440 : 1.0;
-  for (int lt = l0; lt <= p.lmax; lt += TL) {
-    __syncthreads();
-    if (tid < TL) {
-      int l = lt + tid;
-      TileA2 e{0.0, 0.0};
-      if (l <= p.lmax) { double2 c = reinterpret_cast<const double2 *>(coef)[2 * (l - l0)]; e.A = c.x; e.C = c.y; }
-      tile[tid] = e;
-    }
-    __syncthreads();
+  auto load_entry = [&](int l) {
+    TileA2 e{0.0, 0.0, 0.0, 0.0};
+    if (l <= p.lmax) { double4 c = reinterpret_cast<const double4 *>(coef)[l - l0]; e.A = c.x; e.C = c.y; e.g = c.z; }
+    return e;
+  };
+  tile[0][tid] = load_entry(l0 + tid);
+  __syncthreads();
+  int buf = 0;
+  for (int lt = l0; lt <= p.lmax; lt += TL, buf ^= 1) {
+    const bool more = lt + TL <= p.lmax;
+    TileA2 nxt;
+    if (more) nxt = load_entry(lt + TL + tid);
+    const int ngroups = min(TL, p.lmax - lt + 4) / 4;
 #pragma unroll 1
-    for (int g = 0; g < TL / 4; ++g) {
+    for (int g = 0; g < ngroups; ++g) {
       bool all_on = true, none_on = true;
 #pragma unroll
       for (int r = 0; r < R; ++r) { all_on &= (k[r] == 0); none_on &= (k[r] < 0); }
       double acc[4][4];
       const bool w_none = __all_sync(FULL, none_on);
-      if (__all_sync(FULL, all_on)) anal2_group<2, R>(tile + 4 * g, x, P, Pp, M, Mp, z, k, acc);
-      else if (w_none) anal2_group<0, R>(tile + 4 * g, x, P, Pp, M, Mp, z, k, acc);
-      else anal2_group<1, R>(tile + 4 * g, x, P, Pp, M, Mp, z, k, acc);
+      if (__all_sync(FULL, all_on)) anal2_group<2, R>(tile[buf] + 4 * g, x, P, Pp, M, Mp, z, k, acc);
+      else if (w_none) anal2_group<0, R>(tile[buf] + 4 * g, x, P, Pp, M, Mp, z, k, acc);
+      else anal2_group<1, R>(tile[buf] + 4 * g, x, P, Pp, M, Mp, z, k, acc);
       if (!w_none) {
 #pragma unroll
         for (int v = 0; v < 4; ++v) warp_reduce_scatter4(acc[v], lane);
@@ -550,19 +580,20 @@ __global__ void __launch_bounds__(NT) anal2_kernel(KParams p) {
       if ((lane & 7) == 0) {
         int j = (lane >> 3) & 3;
 #pragma unroll
-        for (int v = 0; v < 4; ++v) red[warp][4 * g + j][v] = w_none ? 0.0 : acc[v][0];
+        for (int v = 0; v < 4; ++v) red[buf][warp][4 * g + j][v] = w_none ? 0.0 : acc[v][0];
       }
     }
+    if (more) tile[buf ^ 1][tid] = nxt;
     __syncthreads();
-    if (tid < TL) {
+    {
       int l = lt + tid;
       if (l <= p.lmax) {
         double s[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
         for (int w = 0; w < NT / 32; ++w)
 #pragma unroll
-          for (int v = 0; v < 4; ++v) s[v] += red[w][tid][v];
-        double gs = coef[4 * (l - l0) + 2] * nrm;
+          for (int v = 0; v < 4; ++v) s[v] += red[buf][w][tid][v];
+        double gs = tile[buf][tid].g * nrm;
         double Er = -0.5 * gs * (s[0] + s[2]), Ei = -0.5 * gs * (s[1] + s[3]);
         double Br = -0.5 * gs * (s[1] - s[3]), Bi = 0.5 * gs * (s[0] - s[2]);
         double *aE = p.alm0, *aB = p.alm1;
@@ -584,7 +615,12 @@ __global__ void __launch_bounds__(NT) anal2_kernel(KParams p) {
 // ------------------------------------------------------------------------------------
 // launchers
 // ------------------------------------------------------------------------------------
-constexpr int R_S0 = 4, R_S2 = 2, R_A0 = 4, R_A2 = 2;
+// Ring pairs per thread (register blocking).  Defaults were picked from the sweep recorded in
+// profiles/; CMDR_SHT_R_S0 / _S2 / _A0 / _A2 override them for tuning runs.
+static int env_int(const char *name, int dflt) {
+  const char *e = getenv(name);
+  return (e && *e) ? atoi(e) : dflt;
+}
 
 static KParams make_params(const LegGeom &g, const LegAlm &a, double *alm0, double *alm1, double4 *ph) {
   KParams p;
@@ -596,16 +632,31 @@ static KParams make_params(const LegGeom &g, const LegAlm &a, double *alm0, doub
   return p;
 }
 
+template <int R, typename K>
+static void launch_r(K kernel, const KParams &p, int nslots, int nm, cudaStream_t st) {
+  dim3 grid((nslots + NT * R - 1) / (NT * R), nm);
+  kernel<<<grid, NT, 0, st>>>(p);
+}
+
 void launch_legendre_synth(int spin, const LegGeom &g, const LegAlm &a, const double *const *alm,
                            double4 *ph, cudaStream_t st) {
   if (a.nm == 0 || g.nslots == 0) return;
   KParams p = make_params(g, a, const_cast<double *>(alm[0]), spin ? const_cast<double *>(alm[1]) : nullptr, ph);
+  static const int r0 = env_int("CMDR_SHT_R_S0", 4), r2 = env_int("CMDR_SHT_R_S2", 2);
   if (spin == 0) {
-    dim3 grid((g.nslots + NT * R_S0 - 1) / (NT * R_S0), a.nm);
-    synth0_kernel<R_S0><<<grid, NT, 0, st>>>(p);
+    switch (r0) {
+      case 2: launch_r<2>(synth0_kernel<2>, p, g.nslots, a.nm, st); break;
+      case 6: launch_r<6>(synth0_kernel<6>, p, g.nslots, a.nm, st); break;
+      case 8: launch_r<8>(synth0_kernel<8>, p, g.nslots, a.nm, st); break;
+      default: launch_r<4>(synth0_kernel<4>, p, g.nslots, a.nm, st); break;
+    }
   } else {
-    dim3 grid((g.nslots + NT * R_S2 - 1) / (NT * R_S2), a.nm);
-    synth2_kernel<R_S2><<<grid, NT, 0, st>>>(p);
+    switch (r2) {
+      case 1: launch_r<1>(synth2_kernel<1>, p, g.nslots, a.nm, st); break;
+      case 3: launch_r<3>(synth2_kernel<3>, p, g.nslots, a.nm, st); break;
+      case 4: launch_r<4>(synth2_kernel<4>, p, g.nslots, a.nm, st); break;
+      default: launch_r<2>(synth2_kernel<2>, p, g.nslots, a.nm, st); break;
+    }
   }
   count_launch();
   CMDR_CUDA_CHECK(cudaGetLastError());
@@ -615,12 +666,20 @@ void launch_legendre_anal(int spin, const LegGeom &g, const LegAlm &a, double *c
                           const double4 *ph, cudaStream_t st) {
   if (a.nm == 0 || g.nslots == 0) return;
   KParams p = make_params(g, a, alm[0], spin ? alm[1] : nullptr, const_cast<double4 *>(ph));
+  static const int r0 = env_int("CMDR_SHT_R_A0", 4), r2 = env_int("CMDR_SHT_R_A2", 4);
   if (spin == 0) {
-    dim3 grid((g.nslots + NT * R_A0 - 1) / (NT * R_A0), a.nm);
-    anal0_kernel<R_A0><<<grid, NT, 0, st>>>(p);
+    switch (r0) {
+      case 2: launch_r<2>(anal0_kernel<2>, p, g.nslots, a.nm, st); break;
+      case 6: launch_r<6>(anal0_kernel<6>, p, g.nslots, a.nm, st); break;
+      case 8: launch_r<8>(anal0_kernel<8>, p, g.nslots, a.nm, st); break;
+      default: launch_r<4>(anal0_kernel<4>, p, g.nslots, a.nm, st); break;
+    }
   } else {
-    dim3 grid((g.nslots + NT * R_A2 - 1) / (NT * R_A2), a.nm);
-    anal2_kernel<R_A2><<<grid, NT, 0, st>>>(p);
+    switch (r2) {
+      case 3: launch_r<3>(anal2_kernel<3>, p, g.nslots, a.nm, st); break;
+      case 2: launch_r<2>(anal2_kernel<2>, p, g.nslots, a.nm, st); break;
+      default: launch_r<4>(anal2_kernel<4>, p, g.nslots, a.nm, st); break;
+    }
   }
   count_launch();
   CMDR_CUDA_CHECK(cudaGetLastError());

@@ -20,7 +20,61 @@ __global__ void __launch_bounds__(256) dfma_probe_kernel(double *out, int iters,
   if (s == 123.456) out[0] = s;   // never true; keeps the chains alive
 }
 
+// mode 0: DMMA (mma.sync m8n8k4 f64) only; mode 1: DMMA and DFMA interleaved 1:4 (same FMA count each);
+// used once to decide whether a tensor-core Legendre variant could pay off.
+__global__ void __launch_bounds__(256) dmma_probe_kernel(double *out, int iters, int mode, double a, double b) {
+  double c0 = threadIdx.x * 1e-3, c1 = c0 + 1, c2 = c0 + 2, c3 = c0 + 3, c4 = c0 + 4, c5 = c0 + 5, c6 = c0 + 6, c7 = c0 + 7;
+  double x0 = c0, x1 = c1, x2 = c2, x3 = c3, x4 = c4, x5 = c5, x6 = c6, x7 = c7;
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+      asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c2), "+d"(c3) : "d"(a), "d"(b));
+      asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c4), "+d"(c5) : "d"(a), "d"(b));
+      asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c6), "+d"(c7) : "d"(a), "d"(b));
+      if (mode == 1) {   // 4 DMMA = 1024 FMA per warp ; 32 warp-DFMA = 1024 FMA per warp
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+          x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+          x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+        }
+      }
+    }
+  }
+  double s = c0 + c1 + c2 + c3 + c4 + c5 + c6 + c7 + x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+  if (s == 123.456) out[0] = s;
+}
+
 }  // namespace cmdr
+
+extern "C" double cmdr_sht_measure_dmma_tflops(int iters, int reps, int mode) {
+  using namespace cmdr;
+  int dev = 0, sms = 0;
+  CMDR_CUDA_CHECK(cudaGetDevice(&dev));
+  CMDR_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  double *out = static_cast<double *>(scratch_get("probe", 64));
+  const int blocks = sms * 8, threads = 256;
+  cudaEvent_t a, b;
+  CMDR_CUDA_CHECK(cudaEventCreate(&a)); CMDR_CUDA_CHECK(cudaEventCreate(&b));
+  dmma_probe_kernel<<<blocks, threads>>>(out, iters, mode, 0.999999, 1e-9);
+  CMDR_CUDA_CHECK(cudaDeviceSynchronize());
+  double best = 0.0;
+  for (int r = 0; r < reps; ++r) {
+    CMDR_CUDA_CHECK(cudaEventRecord(a));
+    dmma_probe_kernel<<<blocks, threads>>>(out, iters, mode, 0.999999, 1e-9);
+    CMDR_CUDA_CHECK(cudaEventRecord(b));
+    CMDR_CUDA_CHECK(cudaEventSynchronize(b));
+    float ms = 0;
+    CMDR_CUDA_CHECK(cudaEventElapsedTime(&ms, a, b));
+    // per thread per iter: 8*4 DMMA * 256 FMA / 32 lanes = 256 FMA (+ 256 DFMA in mode 1)
+    double fma_per_thread = 256.0 * iters * (mode == 1 ? 2.0 : 1.0);
+    double tf = 2.0 * fma_per_thread * blocks * threads / (ms * 1e-3) / 1e12;
+    if (tf > best) best = tf;
+    count_launch();
+  }
+  cudaEventDestroy(a); cudaEventDestroy(b);
+  return best;
+}
 
 extern "C" double cmdr_sht_measure_fp64_tflops(int iters, int reps) {
   using namespace cmdr;
