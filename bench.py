@@ -54,6 +54,8 @@ def cpu_pair_sample(nside, lmax, stride, nthreads=0):
     import numpy as np
     from oracle import sht_cpu as S
     S.build()
+    if nthreads == 0:   # torchrun exports OMP_NUM_THREADS=1; the CPU arm uses every core it may run on
+        nthreads = len(os.sched_getaffinity(0))
     # one-off FFT plan tables (not part of a transform; libsharp2 also plans once per geometry)
     tiny = np.array([0], dtype=np.int32)
     S.execute(S.Y, 0, nside, lmax, alm=np.zeros((1, lmax + 1)), ms=tiny, nthreads=nthreads, mlim_skip=True)
@@ -78,7 +80,7 @@ def cpu_pair_sample(nside, lmax, stride, nthreads=0):
     other = max(wall - t_leg - t_fft, 0.0)   # geometry setup, buffers
     full = t_leg / frac + t_fft + other
     return {"seconds_full_est": full, "frac": frac, "wall": wall, "t_leg": t_leg, "t_fft": t_fft,
-            "threads": S.lib().osht_max_threads() if nthreads == 0 else nthreads, "simd": S.lib().variant}
+            "threads": nthreads, "simd": S.lib().variant}
 
 
 def cpu_sample_text(r, stride):
@@ -297,7 +299,7 @@ def run_ours(args):
 
     if rank == 0:
         cpu = None
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:   # contract: rank 0 at N=1 only
             st = args.cpu_stride if args.cpu_stride > 0 else 1
             r = cpu_pair_sample(nside, lmax, st)
             cpu = {"value": 1.0 / r["seconds_full_est"], "unit": UNIT, "cores": r["threads"], "kind": "port",

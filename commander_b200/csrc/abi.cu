@@ -143,6 +143,63 @@ void ring_trig_ld(int nside, int north, long double &cth, long double &sth, long
 
 static int next_pow2(int v) { int m = 1; while (m < v) m <<= 1; return m; }
 
+
+// FFT regions: polar-cap pairs grouped by Bluestein work length, then the belt
+static void build_regions(sharp_geom_info *g) {
+  const int nside = g->nside;
+  g->regions.clear();
+  long long base = 0;
+  int p = 0;
+  while (p < g->npairs && g->north[p] < nside) {
+    int M = next_pow2(2 * g->nph[p] - 1);
+    FftRegion R; R.first = p; R.len = M; R.bluestein = true; R.base = base;
+    while (p < g->npairs && g->north[p] < nside && next_pow2(2 * g->nph[p] - 1) == M) ++p;
+    R.np = p - R.first;
+    base += (long long)R.np * R.len;
+    g->regions.push_back(R);
+  }
+  g->vlen_total = base;
+  if (p < g->npairs) {
+    FftRegion R; R.first = p; R.np = g->npairs - p; R.len = 4 * nside; R.bluestein = false; R.base = base;
+    base += (long long)R.np * R.len;
+    g->regions.push_back(R);
+  }
+  g->zlen_total = base;
+}
+
+// Sub-geometry over parent pairs [a, b): same pixel offsets, own FFT regions / plans.
+static sharp_geom_info *make_subgeom(const sharp_geom_info *g, int a, int b) {
+  sharp_geom_info *s = new sharp_geom_info;
+  s->nside = g->nside; s->nrings = 0; s->npix = g->npix; s->pair0 = a; s->npairs = b - a;
+  auto cut = [&](auto &dst, const auto &src) { dst.assign(src.begin() + a, src.begin() + b); };
+  cut(s->north, g->north); cut(s->cth, g->cth); cut(s->sth, g->sth); cut(s->sh, g->sh); cut(s->ch, g->ch);
+  cut(s->wgt, g->wgt); cut(s->nph, g->nph); cut(s->shifted, g->shifted); cut(s->ofsN, g->ofsN); cut(s->ofsS, g->ofsS);
+  build_regions(s);
+  return s;
+}
+
+// Splits the pairs into chunks of roughly equal pixel count whose north rings (ascending) and
+// south rings (descending) are each contiguous in the map, so that a chunk is two plain
+// memory ranges per component.  Leaves g->subs empty when the ring list does not allow that.
+void ensure_subgeoms(sharp_geom_info *g, int nchunks) {
+  if (g->subs_built) return;
+  g->subs_built = true;
+  const int np = g->npairs;
+  if (np < 1024) return;
+  for (int p = 0; p < np; ++p) {
+    if (g->ofsN[p] < 0) return;
+    if (g->ofsS[p] < 0 && p != np - 1) return;
+    if (p + 1 < np && g->ofsN[p + 1] != g->ofsN[p] + g->nph[p]) return;
+    if (p + 1 < np && g->ofsS[p + 1] >= 0 && g->ofsS[p] != g->ofsS[p + 1] + g->nph[p + 1]) return;
+  }
+  // chunk = a multiple of 512 ring pairs: the Legendre CTAs cover 256 or 512 pair slots, so
+  // any other boundary would leave lanes idle in every CTA row of the chunk
+  const int unit = 512;
+  int per = ((np + nchunks - 1) / nchunks + unit - 1) / unit * unit;
+  if (per >= np) return;
+  for (int a = 0; a < np; a += per) g->subs.push_back(make_subgeom(g, a, std::min(np, a + per)));
+}
+
 }  // namespace cmdr
 
 using namespace cmdr;
@@ -229,29 +286,14 @@ void sharp_make_subset_healpix_geom_info(int nside, int stride, int nrings, cons
     g->ofsN.push_back(oN[i]); g->ofsS.push_back(oS[i]);
   }
   g->npairs = (int)g->north.size();
-  // FFT regions: polar-cap pairs grouped by Bluestein work length, then the belt
-  long long base = 0;
-  int p = 0;
-  while (p < g->npairs && g->north[p] < nside) {
-    int M = next_pow2(2 * g->nph[p] - 1);
-    FftRegion R; R.first = p; R.len = M; R.bluestein = true; R.base = base;
-    while (p < g->npairs && g->north[p] < nside && next_pow2(2 * g->nph[p] - 1) == M) ++p;
-    R.np = p - R.first;
-    base += (long long)R.np * R.len;
-    g->regions.push_back(R);
-  }
-  g->vlen_total = base;
-  if (p < g->npairs) {
-    FftRegion R; R.first = p; R.np = g->npairs - p; R.len = 4 * nside; R.bluestein = false; R.base = base;
-    base += (long long)R.np * R.len;
-    g->regions.push_back(R);
-  }
-  g->zlen_total = base;
+  build_regions(g);
   *out = g;
 }
 
 void sharp_destroy_geom_info(sharp_geom_info *g) {
   if (!g) return;
+  for (sharp_geom_info *sub : g->subs) sharp_destroy_geom_info(sub);
+  g->subs.clear();
   if (g->device >= 0) {
     destroy_plans(g);
     cudaFree(g->d_trig); cudaFree(g->d_wgt); cudaFree(g->d_nph); cudaFree(g->d_shifted);
@@ -403,6 +445,130 @@ void stage_out(Staged &s, long long count, cudaStream_t st) {
     CMDR_CUDA_CHECK(cudaMemcpyAsync(s.host[c], s.dev[c], sizeof(double) * count, cudaMemcpyDeviceToHost, st));
 }
 
+// ---------------------------------------------------------------- pipelined host path
+// With pinned host buffers the transform is cut into ring-pair chunks so that PCIe copies of
+// one chunk overlap the kernels of the next (synthesis: Legendre+FFT of chunk c+1 while the
+// map rows of chunk c go D2H; analysis: H2D of chunk c+1 while chunk c is transformed and
+// accumulated into the a_lm).  Pageable buffers (the plain Fortran case) take the simple
+// staged path above; registering the arrays once with cudaHostRegister enables this one.
+static bool is_pinned_host(const void *p) {
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return at.type == cudaMemoryTypeHost;
+}
+
+static cudaStream_t copy_stream() {
+  static std::map<int, cudaStream_t> cs;
+  int dev = 0;
+  CMDR_CUDA_CHECK(cudaGetDevice(&dev));
+  auto it = cs.find(dev);
+  if (it != cs.end()) return it->second;
+  cudaStream_t s;
+  CMDR_CUDA_CHECK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+  cs[dev] = s;
+  return s;
+}
+
+static cudaEvent_t pooled_event(size_t i) {
+  static std::vector<cudaEvent_t> pool;
+  while (pool.size() <= i) {
+    cudaEvent_t e;
+    CMDR_CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    pool.push_back(e);
+  }
+  return pool[i];
+}
+
+// pixel ranges [begin, end) of a sub-geometry's northern and southern rows
+static void sub_ranges(const sharp_geom_info *s, long long &nb, long long &ne, long long &sb, long long &se) {
+  const int n = s->npairs;
+  nb = s->ofsN[0]; ne = s->ofsN[n - 1] + s->nph[n - 1];
+  int last = n - 1;
+  while (last >= 0 && s->ofsS[last] < 0) --last;
+  if (last < 0) { sb = se = 0; return; }
+  sb = s->ofsS[last]; se = s->ofsS[0] + s->nph[0];
+}
+
+static bool try_pipelined(int type, int spin, double *const *alm, double *const *map, sharp_geom_info *g,
+                          sharp_alm_info *a, int flags, cudaStream_t st) {
+  static const bool disabled = getenv("CMDR_SHT_NO_PIPELINE") != nullptr;
+  const int ncomp = spin == 0 ? 1 : 2;
+  if (disabled || (flags & SHARP_ADD) || g->npix < (1 << 21) || a->nm == 0 || !(spin == 0 || spin == 2)) return false;
+  if (type < 0 || type > 3) return false;
+  for (int c = 0; c < ncomp; ++c) if (!is_pinned_host(alm[c]) || !is_pinned_host(map[c])) return false;
+  static const int nchunks = getenv("CMDR_SHT_CHUNKS") ? atoi(getenv("CMDR_SHT_CHUNKS")) : 8;
+  ensure_subgeoms(g, nchunks);
+  if (g->subs.empty()) return false;
+  const bool synth = (type == SHARP_Y || type == SHARP_WY);
+  ensure_geom_device(g);
+  LegAlm A = make_legalm(a, spin);
+  const long long nalm_d = a->nalm * (a->real_packed ? 1 : 2);
+  double *alm_buf = static_cast<double *>(scratch_get("stage_alm", sizeof(double) * (size_t)nalm_d * ncomp));
+  double *map_buf = static_cast<double *>(scratch_get("stage_map", sizeof(double) * (size_t)g->npix * ncomp));
+  double4 *ph = static_cast<double4 *>(scratch_get("phase", sizeof(double4) * (size_t)ncomp * a->nm * g->npairs));
+  long long maxz = 0;
+  for (sharp_geom_info *sub : g->subs) { ensure_geom_device(sub); maxz = std::max(maxz, sub->zlen_total); }
+  scratch_get("fftbuf", sizeof(double2) * (size_t)maxz * ncomp);
+  double *alm_dev[2], *map_dev[2];
+  for (int c = 0; c < ncomp; ++c) { alm_dev[c] = alm_buf + (size_t)c * nalm_d; map_dev[c] = map_buf + (size_t)c * g->npix; }
+  LegGeom G;
+  G.nslots = g->npairs; G.NPL = g->npairs; G.nowners = 1; G.NML = a->nm; G.ncomp_tot = ncomp; G.comp0 = 0;
+  G.trig = g->d_trig; G.mlim = ensure_mlim(g, a->lmax, spin);
+  PhaseLayout L = single_layout(a, g->npairs, ncomp, 0);
+  cudaStream_t cs = copy_stream();
+  const int ns = (int)g->subs.size();
+  if (synth) {
+    for (int c = 0; c < ncomp; ++c)
+      CMDR_CUDA_CHECK(cudaMemcpyAsync(alm_dev[c], alm[c], sizeof(double) * nalm_d, cudaMemcpyHostToDevice, st));
+    for (int i = ns - 1; i >= 0; --i) {          // belt (large rows) first, polar caps last
+      sharp_geom_info *sub = g->subs[i];
+      G.slot_begin = sub->pair0; G.slot_end = sub->pair0 + sub->npairs;
+      launch_legendre_synth(spin, G, A, alm_dev, ph, st);
+      L.pair0 = sub->pair0;
+      ringfft_synth(sub, ncomp, L, ph, map_dev, type == SHARP_WY, false, st);
+      cudaEvent_t e = pooled_event(i);
+      CMDR_CUDA_CHECK(cudaEventRecord(e, st));
+      CMDR_CUDA_CHECK(cudaStreamWaitEvent(cs, e, 0));
+      long long nb, ne, sb, se;
+      sub_ranges(sub, nb, ne, sb, se);
+      for (int c = 0; c < ncomp; ++c) {
+        CMDR_CUDA_CHECK(cudaMemcpyAsync(map[c] + nb, map_dev[c] + nb, sizeof(double) * (ne - nb), cudaMemcpyDeviceToHost, cs));
+        if (se > sb)
+          CMDR_CUDA_CHECK(cudaMemcpyAsync(map[c] + sb, map_dev[c] + sb, sizeof(double) * (se - sb), cudaMemcpyDeviceToHost, cs));
+      }
+    }
+    CMDR_CUDA_CHECK(cudaStreamSynchronize(cs));
+    CMDR_CUDA_CHECK(cudaStreamSynchronize(st));
+  } else {
+    // the copy stream must not overwrite staging rows an earlier call on `st` still reads
+    cudaEvent_t e0 = pooled_event(ns);
+    CMDR_CUDA_CHECK(cudaEventRecord(e0, st));
+    CMDR_CUDA_CHECK(cudaStreamWaitEvent(cs, e0, 0));
+    for (int c = 0; c < ncomp; ++c) CMDR_CUDA_CHECK(cudaMemsetAsync(alm_dev[c], 0, sizeof(double) * nalm_d, st));
+    for (int i = 0; i < ns; ++i) {               // small polar chunks first so compute starts early
+      sharp_geom_info *sub = g->subs[i];
+      long long nb, ne, sb, se;
+      sub_ranges(sub, nb, ne, sb, se);
+      for (int c = 0; c < ncomp; ++c) {
+        CMDR_CUDA_CHECK(cudaMemcpyAsync(map_dev[c] + nb, map[c] + nb, sizeof(double) * (ne - nb), cudaMemcpyHostToDevice, cs));
+        if (se > sb)
+          CMDR_CUDA_CHECK(cudaMemcpyAsync(map_dev[c] + sb, map[c] + sb, sizeof(double) * (se - sb), cudaMemcpyHostToDevice, cs));
+      }
+      cudaEvent_t e = pooled_event(i);
+      CMDR_CUDA_CHECK(cudaEventRecord(e, cs));
+      CMDR_CUDA_CHECK(cudaStreamWaitEvent(st, e, 0));
+      L.pair0 = sub->pair0;
+      ringfft_anal(sub, ncomp, L, ph, map_dev, type == SHARP_YtW, st);
+      G.slot_begin = sub->pair0; G.slot_end = sub->pair0 + sub->npairs;
+      launch_legendre_anal(spin, G, A, alm_dev, ph, st);
+    }
+    for (int c = 0; c < ncomp; ++c)
+      CMDR_CUDA_CHECK(cudaMemcpyAsync(alm[c], alm_dev[c], sizeof(double) * nalm_d, cudaMemcpyDeviceToHost, st));
+    CMDR_CUDA_CHECK(cudaStreamSynchronize(st));
+  }
+  return true;
+}
+
 unsigned long long nominal_flops(const sharp_geom_info *g, const sharp_alm_info *a, int spin) {
   // (l,m) count over the local m's times ring pairs (an unpaired ring counts half)
   double nlm = 0;
@@ -421,11 +587,13 @@ void execute_any(int type, int spin, void *alm_v, void *map_v, sharp_geom_info *
   double *const *alm = static_cast<double *const *>(alm_v);
   double *const *map = static_cast<double *const *>(map_v);
   const long long nalm_d = a->nalm * (a->real_packed ? 1 : 2);
-  Staged sa = stage_in("stage_alm", alm, ncomp, nalm_d, synth || add, st);
-  Staged sm = stage_in("stage_map", map, ncomp, g->npix, !synth || add, st);
-  run_single(type, spin, sa.dev.data(), sm.dev.data(), g, a, flags, st);
-  if (synth) stage_out(sm, g->npix, st); else stage_out(sa, nalm_d, st);
-  if (sa.staged || sm.staged || time) CMDR_CUDA_CHECK(cudaStreamSynchronize(st));
+  if (!try_pipelined(type, spin, alm, map, g, a, flags, st)) {
+    Staged sa = stage_in("stage_alm", alm, ncomp, nalm_d, synth || add, st);
+    Staged sm = stage_in("stage_map", map, ncomp, g->npix, !synth || add, st);
+    run_single(type, spin, sa.dev.data(), sm.dev.data(), g, a, flags, st);
+    if (synth) stage_out(sm, g->npix, st); else stage_out(sa, nalm_d, st);
+    if (sa.staged || sm.staged || time) CMDR_CUDA_CHECK(cudaStreamSynchronize(st));
+  }
   if (time) *time = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
   if (opcnt) *opcnt = nominal_flops(g, a, spin);
 }

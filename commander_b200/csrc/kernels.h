@@ -16,6 +16,7 @@ void count_launch(int n = 1);
 // [owner][NPL]; slot -> trig (cth,sth,sh,ch) and per-slot m cut-off (-1 = empty slot).
 struct LegGeom {
   int nslots = 0, NPL = 0, nowners = 1;
+  int slot_begin = 0, slot_end = -1;   // sub-range of slots to process (-1: all)
   int NML = 0;                    // padded number of local m's (phase buffer row count per comp)
   int ncomp_tot = 1, comp0 = 0;   // components in the phase buffer / first one written here
   const double *trig = nullptr;   // nslots*4
@@ -47,6 +48,7 @@ void launch_legendre_anal(int spin, const LegGeom &g, const LegAlm &a, double *c
 // with the (m -> src, im) lookup tables below (src = rank that owns m).
 struct PhaseLayout {
   int NPL = 0, NML = 0, ncomp_tot = 1, comp0 = 0;
+  int pair0 = 0;                 // phase-buffer index of this geometry's first ring pair
   int mmax = -1;                 // largest m present anywhere
   const int *m2src = nullptr;    // size mmax+1 (-1: m absent)
   const int *m2im = nullptr;     // size mmax+1

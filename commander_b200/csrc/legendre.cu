@@ -33,6 +33,7 @@ static_assert(SCALE_BITS == 512, "SCALE_DOWN must equal 2^-SCALE_BITS");
 struct KParams {
   int lmax, nm, real_packed;
   int nslots, NPL, NML, ncomp_tot, comp0;
+  int slot_begin;   // first slot handled by this launch (nslots = one past the last)
   const int *mval;
   const long long *mvstart;
   const double *coef;
@@ -88,7 +89,7 @@ __global__ void __launch_bounds__(NT) synth0_kernel(KParams p) {
   __shared__ TileS0 tile[2][TL];
   const int im = blockIdx.y, m = p.mval[im];
   const int tid = threadIdx.x;
-  const int chunk0 = blockIdx.x * (NT * R);
+  const int chunk0 = p.slot_begin + blockIdx.x * (NT * R);
   double x[R], cur[R], prev[R], per[R], pei[R], por[R], poi[R];
   int k[R], slot[R];
   bool any = false;
@@ -210,7 +211,7 @@ __global__ void __launch_bounds__(NT) synth2_kernel(KParams p) {
   __shared__ TileS2 tile[2][TL];
   const int im = blockIdx.y, m = p.mval[im];
   const int tid = threadIdx.x;
-  const int chunk0 = blockIdx.x * (NT * R);
+  const int chunk0 = p.slot_begin + blockIdx.x * (NT * R);
   const int l0 = max(m, 2);
   double x[R], P[R], Pp[R], M[R], Mp[R], a[R][8];
   int k[R], slot[R];
@@ -389,7 +390,7 @@ __global__ void __launch_bounds__(NT) anal0_kernel(KParams p) {
   __shared__ double red[2][NT / 32][TL][2];
   const int im = blockIdx.y, m = p.mval[im];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int chunk0 = blockIdx.x * (NT * R);
+  const int chunk0 = p.slot_begin + blockIdx.x * (NT * R);
   double x[R], cur[R], prev[R], sr[R], si[R], dr[R], di[R];
   int k[R];
   bool any = false;
@@ -518,7 +519,7 @@ __global__ void __launch_bounds__(NT) anal2_kernel(KParams p) {
   __shared__ double red[2][NT / 32][TL][4];
   const int im = blockIdx.y, m = p.mval[im];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int chunk0 = blockIdx.x * (NT * R);
+  const int chunk0 = p.slot_begin + blockIdx.x * (NT * R);
   const int l0 = max(m, 2);
   if (l0 > p.lmax) return;
   double x[R], P[R], Pp[R], M[R], Mp[R], z[R][8];
@@ -625,7 +626,7 @@ static int env_int(const char *name, int dflt) {
 static KParams make_params(const LegGeom &g, const LegAlm &a, double *alm0, double *alm1, double4 *ph) {
   KParams p;
   p.lmax = a.lmax; p.nm = a.nm; p.real_packed = a.real_packed;
-  p.nslots = g.nslots; p.NPL = g.NPL; p.NML = g.NML; p.ncomp_tot = g.ncomp_tot; p.comp0 = g.comp0;
+  p.slot_begin = g.slot_begin; p.nslots = g.slot_end >= 0 ? g.slot_end : g.nslots; p.NPL = g.NPL; p.NML = g.NML; p.ncomp_tot = g.ncomp_tot; p.comp0 = g.comp0;
   p.mval = a.mval; p.mvstart = a.mvstart; p.coef = a.coef; p.cofs = a.cofs; p.Kstart = a.Kstart;
   p.trig = g.trig; p.mlim = g.mlim;
   p.alm0 = alm0; p.alm1 = alm1; p.ph = ph;
@@ -633,8 +634,10 @@ static KParams make_params(const LegGeom &g, const LegAlm &a, double *alm0, doub
 }
 
 template <int R, typename K>
-static void launch_r(K kernel, const KParams &p, int nslots, int nm, cudaStream_t st) {
-  dim3 grid((nslots + NT * R - 1) / (NT * R), nm);
+static void launch_r(K kernel, const KParams &p, int /*nslots*/, int nm, cudaStream_t st) {
+  const int n = p.nslots - p.slot_begin;
+  if (n <= 0) return;
+  dim3 grid((n + NT * R - 1) / (NT * R), nm);
   kernel<<<grid, NT, 0, st>>>(p);
 }
 

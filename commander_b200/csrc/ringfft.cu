@@ -71,7 +71,7 @@ __global__ void __launch_bounds__(256) fold_kernel(FParams p) {
       for (int m = k; m <= L.mmax; m += n) {          // m == k (mod n): X_k += p_m
         int src = L.m2src[m];
         if (src < 0) continue;
-        double4 q = p.ph[((size_t)(src * L.ncomp_tot + L.comp0 + c) * L.NML + L.m2im[m]) * L.NPL + pair];
+        double4 q = p.ph[((size_t)(src * L.ncomp_tot + L.comp0 + c) * L.NML + L.m2im[m]) * L.NPL + L.pair0 + pair];
         double2 e = shifted ? expipi(m, n) : make_double2(1.0, 0.0);
         double2 pn = cmul(make_double2(q.x, q.y), e), ps = cmul(make_double2(q.z, q.w), e);
         if (m == 0) { acc.x += pn.x; acc.y += ps.x; }
@@ -82,7 +82,7 @@ __global__ void __launch_bounds__(256) fold_kernel(FParams p) {
       for (int m = start; m <= L.mmax; m += n) {      // m == -k (mod n): X_k += conj p_m
         int src = L.m2src[m];
         if (src < 0) continue;
-        double4 q = p.ph[((size_t)(src * L.ncomp_tot + L.comp0 + c) * L.NML + L.m2im[m]) * L.NPL + pair];
+        double4 q = p.ph[((size_t)(src * L.ncomp_tot + L.comp0 + c) * L.NML + L.m2im[m]) * L.NPL + L.pair0 + pair];
         double2 e = shifted ? expipi(m, n) : make_double2(1.0, 0.0);
         double2 pn = cmul(make_double2(q.x, q.y), e), ps = cmul(make_double2(q.z, q.w), e);
         acc.x += pn.x + ps.y; acc.y += -pn.y + ps.x;
@@ -176,7 +176,7 @@ __global__ void __launch_bounds__(256) unfold_kernel(FParams p) {
     double2 f = make_double2(cm, 0.0);
     if (shifted) { double2 t = expipi(m, n); f = make_double2(cm * t.x, -cm * t.y); }
     xn = cmul(xn, f); xs = cmul(xs, f);
-    p.ph[((size_t)(L.mlist_src[e] * L.ncomp_tot + L.comp0 + c) * L.NML + L.mlist_im[e]) * L.NPL + pair] =
+    p.ph[((size_t)(L.mlist_src[e] * L.ncomp_tot + L.comp0 + c) * L.NML + L.mlist_im[e]) * L.NPL + L.pair0 + pair] =
         make_double4(xn.x, xn.y, xs.x, xs.y);
   }
 }

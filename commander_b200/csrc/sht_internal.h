@@ -72,4 +72,8 @@ struct sharp_geom_info {
   std::map<long long, int> plans;   // key (region<<8 | ncomp) -> cufftHandle
   std::map<long long, int *> mlim;  // key (lmax<<8 | spin) -> device int[npairs]
   int device = -1;
+  // ring-pair sub-ranges used to pipeline host<->device copies with compute (abi.cu)
+  int pair0 = 0;                       // first parent pair (sub-geometries only)
+  bool subs_built = false;
+  std::vector<sharp_geom_info *> subs; // empty when the ring list is not chunkable
 };

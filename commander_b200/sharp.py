@@ -219,8 +219,8 @@ def set_profiling(on: bool) -> None:
 
 
 def last_legendre_ms():
-    buf = (C.c_double * 48)()
-    n = lib().cmdr_sht_last_legendre_ms(buf, 16)
+    buf = (C.c_double * (3 * 4096))()
+    n = lib().cmdr_sht_last_legendre_ms(buf, 4096)
     return [(int(buf[3 * i]), int(buf[3 * i + 1]), float(buf[3 * i + 2])) for i in range(n)]
 
 

@@ -1,0 +1,80 @@
+"""torchrun worker: distributed transforms on N GPUs vs the single-GPU result and the CPU oracle.
+Launched by tests/test_gpu_dist.py (or by hand:
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tests/dist_check.py)."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    import torch
+    import torch.distributed as dist
+    from commander_b200 import comm_map, comm_mapinfo, sharp
+    from commander_b200 import dist as cdist
+    from oracle import sht_cpu as S
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    rank, world = dist.get_rank(), dist.get_world_size()
+    comm = cdist.init_from_torch(dev)
+    worst = 0.0
+    for nside, lmax in ((16, 40), (64, 150), (128, 383)):
+        info = comm_mapinfo(comm, nside, lmax, 3, True)
+        # global inputs from a fixed seed, identical on all ranks
+        rng = np.random.default_rng(1234 + nside)
+        nalm_g, npix_g = (lmax + 1) ** 2, 12 * nside ** 2
+        alm_g = rng.standard_normal((3, nalm_g))
+        map_g = rng.standard_normal((3, npix_g))
+        w = rng.uniform(0.9, 1.1, (2, 2 * nside))
+        infow = comm_mapinfo(comm, nside, lmax, 3, True, weights=w)
+        # global real-packed index of my local alm slots (m-major over all m)
+        mstart = np.zeros(lmax + 2, dtype=np.int64)
+        for m in range(lmax + 1):
+            mstart[m + 1] = mstart[m] + (lmax + 1 - m) * (1 if m == 0 else 2)
+        l, mm = infow.lm[0].astype(np.int64), infow.lm[1].astype(np.int64)
+        am = np.abs(mm)
+        gidx = mstart[am] + np.where(am == 0, l, 2 * (l - am) + (mm < 0))
+        # oracle on the full sphere
+        refY = np.concatenate([S.execute(S.Y, 0, nside, lmax, alm=alm_g[0:1]), S.execute(S.Y, 2, nside, lmax, alm=alm_g[1:3])])
+        refA = np.concatenate([S.execute(S.YtW, 0, nside, lmax, map=map_g[0:1], weight=w[0]),
+                               S.execute(S.YtW, 2, nside, lmax, map=map_g[1:3], weight=w[1])])
+        for fused in (False, True):
+            for device in (None, dev):
+                m = comm_map(infow, device=device)
+                if device is None:
+                    m.alm[:] = alm_g[:, gidx]
+                else:
+                    m.alm.copy_(torch.as_tensor(alm_g[:, gidx], device=dev))
+                (m.Y_iqu if fused else m.Y)()
+                out = m.map if device is None else m.map.cpu().numpy()
+                e1 = np.linalg.norm(out - refY[:, infow.pix]) / np.linalg.norm(refY[:, infow.pix])
+                if device is None:
+                    m.map[:] = map_g[:, infow.pix]
+                else:
+                    m.map.copy_(torch.as_tensor(map_g[:, infow.pix], device=dev))
+                (m.YtW_iqu if fused else m.YtW)()
+                out = m.alm if device is None else m.alm.cpu().numpy()
+                e2 = np.linalg.norm(out - refA[:, gidx]) / np.linalg.norm(refA[:, gidx])
+                worst = max(worst, e1, e2)
+                assert e1 <= 1e-10 and e2 <= 1e-10, (nside, lmax, fused, device, e1, e2)
+        infow.dealloc()
+    # CG dot-product all-reduce
+    t = torch.full((3,), float(rank + 1), dtype=torch.float64, device=dev)
+    comm.allreduce_sum_(t)
+    torch.cuda.synchronize()
+    assert float(t[0]) == world * (world + 1) / 2
+    tw = torch.tensor([worst], dtype=torch.float64, device=dev)
+    dist.all_reduce(tw, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        print(f"DIST_CHECK_OK world={world} worst_rel_l2={float(tw):.3e}")
+    cdist.destroy(comm)
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
