@@ -414,7 +414,9 @@ __global__ void __launch_bounds__(NT) anal0_kernel(KParams p) {
   if (!__syncthreads_or(any)) return;
   const double *coef = p.coef + p.cofs[im];
   const long long mvs = p.mvstart[im];
-  const double nrm = (p.real_packed && m > 0) ? 0.70710678118654752440 : 1.0;
+  // real-packed: orthonormal real basis (sqrt2 both ways).  complex a_lm: the phases carry the
+  // factor 2 of the m>0 terms, so the adjoint needs 1/2 to return sum conj(Y) x as libsharp2 does
+  const double nrm = m > 0 ? (p.real_packed ? 0.70710678118654752440 : 0.5) : 1.0;
   auto load_entry = [&](int l) {
     TileA0 e{0.0, 0.0};
     if (l <= p.lmax) { double2 c = reinterpret_cast<const double2 *>(coef)[l - m]; e.A = c.x; e.g = c.y; }
@@ -550,7 +552,9 @@ __global__ void __launch_bounds__(NT) anal2_kernel(KParams p) {
   if (!__syncthreads_or(any)) return;
   const double *coef = p.coef + p.cofs[im];
   const long long mvs = p.mvstart[im];
-  const double nrm = (p.real_packed && m > 0) ? 0.70710678118654752440 : 1.0;
+  // real-packed: orthonormal real basis (sqrt2 both ways).  complex a_lm: the phases carry the
+  // factor 2 of the m>0 terms, so the adjoint needs 1/2 to return sum conj(Y) x as libsharp2 does
+  const double nrm = m > 0 ? (p.real_packed ? 0.70710678118654752440 : 0.5) : 1.0;
   auto load_entry = [&](int l) {
     TileA2 e{0.0, 0.0, 0.0, 0.0};
     if (l <= p.lmax) { double4 c = reinterpret_cast<const double4 *>(coef)[l - l0]; e.A = c.x; e.C = c.y; e.g = c.z; }

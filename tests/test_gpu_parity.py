@@ -191,3 +191,173 @@ def test_pinned_host_pipelined_path(shtlib, cpu_oracle, spin):
     assert rel(alm_p.numpy(), ref) <= TOL
     sharp.sharp_destroy_alm_info(ai)
     sharp.sharp_destroy_geom_info(gi)
+
+
+def test_general_complex_alm_info(shtlib, cpu_oracle):
+    """sharp_make_general_alm_info (commander3/src/sharp.f90:35-42; declared by the reference, never
+    called): complex a_lm, m-major, against the real-packed result."""
+    import ctypes as C
+    sharp, S = shtlib, cpu_oracle
+    nside, lmax = 16, 33
+    L = sharp.lib()
+    mval = np.arange(lmax + 1, dtype=np.int32)
+    mvstart = np.zeros(lmax + 1, dtype=np.int64)
+    idx = 0
+    for m in range(lmax + 1):
+        mvstart[m] = idx - m
+        idx += lmax + 1 - m
+    h = C.c_void_p()
+    L.sharp_make_general_alm_info(lmax, lmax + 1, 1, mval.ctypes.data, mvstart.ctypes.data, 0, C.byref(h))
+    assert L.sharp_alm_count(h) == idx
+    gi = sharp.sharp_make_healpix_geom_info(nside)
+    rng = np.random.default_rng(17)
+    a = rng.standard_normal(idx) + 1j * rng.standard_normal(idx)
+    a[: lmax + 1] = a[: lmax + 1].real          # m = 0 is real
+    buf = np.ascontiguousarray(a).view(np.float64).copy()
+    out = np.zeros(gi.n_local)
+    ap = (C.c_void_p * 1)(buf.ctypes.data); mp = (C.c_void_p * 1)(out.ctypes.data)
+    L.sharp_execute(sharp.SHARP_Y, 0, ap, mp, gi.handle, h, sharp.SHARP_DP, None, None)
+    # the same field in the real-packed basis: alm[+m] = sqrt2 Re a, alm[-m] = sqrt2 Im a
+    packed = []
+    for m in range(lmax + 1):
+        blk = a[mvstart[m] + m: mvstart[m] + lmax + 1]
+        packed.append(blk.real if m == 0 else np.sqrt(2.0) * np.stack([blk.real, blk.imag], axis=1).ravel())
+    ref = S.execute(S.Y, 0, nside, lmax, alm=np.concatenate(packed)[None, :])
+    assert rel(out[None, :], ref) <= TOL
+    back = np.zeros(2 * idx)
+    bp = (C.c_void_p * 1)(back.ctypes.data)
+    L.sharp_execute(sharp.SHARP_Yt, 0, bp, mp, gi.handle, h, sharp.SHARP_DP, None, None)
+    refa = S.execute(S.Yt, 0, nside, lmax, map=out[None, :])[0]
+    got = back.view(np.complex128)
+    o = 0
+    for m in range(lmax + 1):
+        n = lmax + 1 - m
+        blk = got[mvstart[m] + m: mvstart[m] + lmax + 1]
+        if m == 0:
+            assert np.linalg.norm(blk.real - refa[o:o + n]) <= TOL * np.linalg.norm(refa[o:o + n]); o += n
+        else:
+            r = refa[o:o + 2 * n].reshape(n, 2) / np.sqrt(2.0)
+            assert np.linalg.norm(blk.real - r[:, 0]) + np.linalg.norm(blk.imag - r[:, 1]) <= 10 * TOL * np.linalg.norm(r); o += 2 * n
+    L.sharp_destroy_alm_info(h)
+    sharp.sharp_destroy_geom_info(gi)
+
+
+@pytest.mark.parametrize("path", ["dense_n4_l9.npz", "dense_n2_l7.npz", "dense_n4_l8_rank1of3.npz"])
+def test_golden_vectors(shtlib, path):
+    """Committed fixtures from the definitional oracle (tests/golden/make_golden.py)."""
+    import os
+    sharp = shtlib
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", path))
+    nside, lmax = int(g["nside"]), int(g["lmax"])
+    ai = sharp.sharp_make_mmajor_real_packed_alm_info(lmax, ms=g["ms"])
+    gi = sharp.sharp_make_healpix_geom_info(nside, rings=g["rings"], weight=g["weight"])
+    for spin in (0, 2):
+        nc = 1 if spin == 0 else 2
+        alm, mp = np.ascontiguousarray(g[f"s{spin}_alm"]), np.ascontiguousarray(g[f"s{spin}_map"])
+        for job, key in ((sharp.SHARP_Y, "Y"), (sharp.SHARP_WY, "WY")):
+            out = np.zeros((nc, gi.n_local))
+            sharp.sharp_execute(job, spin, nc, alm.copy(), ai, out, gi)
+            assert rel(out, g[f"s{spin}_{key}"]) <= 1e-12
+        for job, key in ((sharp.SHARP_Yt, "Yt"), (sharp.SHARP_YtW, "YtW")):
+            out = np.zeros((nc, ai.n_local))
+            sharp.sharp_execute(job, spin, nc, out, ai, mp.copy(), gi)
+            assert rel(out, g[f"s{spin}_{key}"]) <= 1e-12
+
+
+@pytest.mark.parametrize("nside,lmax", [(1024, 2048), (2048, 4000)])
+def test_full_size_properties(shtlib, nside, lmax):
+    """BASELINE.json configs[1] and [3] sizes, where the oracle is too slow for a full comparison:
+    size-independent properties -- linearity, adjointness <Y a, x> = <a, Yt x>, WY = w Y, YtW = Yt w,
+    the approximate inverse YtW Y ~ 1 (HEALPix quadrature, ~1e-3), and oracle parity on one m-column."""
+    import torch
+    from commander_b200 import comm_map, comm_mapinfo
+    rng = np.random.default_rng(3)
+    w = rng.uniform(0.95, 1.05, (2, 2 * nside))
+    info = comm_mapinfo(None, nside, lmax, 3, True, weights=w)
+    dev = "cuda"
+    g = torch.Generator(device=dev).manual_seed(4)
+    a, b = comm_map(info, device=dev), comm_map(info, device=dev)
+    l = torch.as_tensor(info.lm[0].astype(np.int64), device=dev)
+    cl = 1.0 / (l * (l + 1) + 1.0).double().sqrt()     # red spectrum exercises the dynamic range
+    a.alm.normal_(generator=g); a.alm.mul_(cl); a.alm[1:3, l < 2] = 0
+    b.alm.normal_(generator=g); b.alm.mul_(cl); b.alm[1:3, l < 2] = 0
+    a0, b0 = a.alm.clone(), b.alm.clone()
+    a.Y(); b.Y()
+    c = comm_map(info, device=dev)
+    c.alm.copy_(2.0 * a0 - 3.0 * b0)
+    c.Y()
+    lin = float((c.map - (2.0 * a.map - 3.0 * b.map)).norm() / c.map.norm())
+    assert lin <= 1e-13, lin
+    # adjointness
+    x = comm_map(info, device=dev)
+    x.map.normal_(generator=g)
+    xm = x.map.clone()
+    x.Yt()
+    lhs, rhs = float((a.map * xm).sum()), float((a0 * x.alm).sum())
+    assert abs(lhs - rhs) <= 1e-12 * float(a.map.norm() * xm.norm())
+    # WY = diag(w) Y ; YtW = Yt diag(w)
+    d = comm_map(info, device=dev)
+    d.alm.copy_(a0); d.WY()
+    ringw = 4 * np.pi / (12 * nside ** 2) * w[:, np.minimum(info.rings, 4 * nside - info.rings) - 1]
+    counts = np.where(np.minimum(info.rings, 4 * nside - info.rings) < nside, 4 * np.minimum(info.rings, 4 * nside - info.rings), 4 * nside)
+    wT = torch.as_tensor(np.repeat(ringw[0], counts), device=dev)
+    wP = torch.as_tensor(np.repeat(ringw[1], counts), device=dev)
+    assert float((d.map[0] - wT * a.map[0]).norm() / d.map[0].norm()) <= 1e-14
+    assert float((d.map[1:] - wP * a.map[1:]).norm() / d.map[1:].norm()) <= 1e-14
+    e = comm_map(info, device=dev)
+    e.map[0] = xm[0] * wT; e.map[1:] = xm[1:] * wP
+    e.Yt()
+    f = comm_map(info, device=dev)
+    f.map.copy_(xm); f.YtW()
+    assert float((f.alm - e.alm).norm() / e.alm.norm()) <= 1e-13
+    # approximate inverse
+    a.YtW()
+    rt = float((a.alm - a0).norm() / a0.norm())
+    assert rt < 0.1, rt
+
+
+def test_full_size_m_column_vs_oracle(shtlib, cpu_oracle):
+    """nside 2048 / lmax 4000: a_lm restricted to a few m (incl. the largest) against the oracle on
+    every ring -- exercises the deep-underflow starts and the m cut-off at the target size."""
+    sharp, S = shtlib, cpu_oracle
+    nside, lmax = 2048, 4000
+    ms = np.array([0, 1, 2, 777, 2048, 3100, 3999, 4000], dtype=np.int32)
+    ai = sharp.sharp_make_mmajor_real_packed_alm_info(lmax, ms=ms)
+    gi = sharp.sharp_make_healpix_geom_info(nside)
+    rng = np.random.default_rng(8)
+    for spin in (0, 2):
+        nc = 1 if spin == 0 else 2
+        alm = rng.standard_normal((nc, ai.n_local))
+        out = np.zeros((nc, gi.n_local))
+        sharp.sharp_execute(sharp.SHARP_Y, spin, nc, alm, ai, out, gi)
+        ref = S.execute(S.Y, spin, nside, lmax, alm=alm, ms=ms)
+        assert rel(out, ref) <= TOL, rel(out, ref)
+        back = np.zeros((nc, ai.n_local))
+        sharp.sharp_execute(sharp.SHARP_Yt, spin, nc, back, ai, ref, gi)
+        refb = S.execute(S.Yt, spin, nside, lmax, map=ref, ms=ms)
+        assert rel(back, refb) <= TOL, rel(back, refb)
+    sharp.sharp_destroy_alm_info(ai)
+    sharp.sharp_destroy_geom_info(gi)
+
+
+def test_config5_band_batch(shtlib, cpu_oracle):
+    """BASELINE.json configs[4] shape (nside 512, lmax 1500, IQU) on 3 of the 30 bands: every band
+    through Y/YtW on shared handles; band 0 checked against the oracle."""
+    import torch
+    from commander_b200 import comm_map, comm_mapinfo
+    S = cpu_oracle
+    nside, lmax = 512, 1500
+    info = comm_mapinfo(None, nside, lmax, 3, True)
+    maps = []
+    for band in range(3):
+        m = comm_map(info, device="cuda")
+        g = torch.Generator(device="cuda").manual_seed(100 + band)
+        m.alm.normal_(generator=g)
+        m.Y()
+        maps.append(m)
+    a0 = maps[0].alm.cpu().numpy()
+    refT = S.execute(S.Y, 0, nside, lmax, alm=a0[0:1])
+    refP = S.execute(S.Y, 2, nside, lmax, alm=a0[1:3])
+    out = maps[0].map.cpu().numpy()
+    assert rel(out[0:1], refT) <= TOL and rel(out[1:3], refP) <= TOL
+    assert float((maps[1].map - maps[0].map).norm()) > 0
