@@ -261,6 +261,7 @@ def run_ours(args):
         dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
     e2e_ms = float(t_e2e[0].item()) / e2e_steps
     clocks = sampler.stop() if rank == 0 else None
+    cg = run_cg_metric(args, comm, dev, world) if not args.no_cg else None
     bytes_alm, bytes_map = 3 * info.nalm * 8, 3 * info.np * 8
 
     # ---- roofline of the dominant kernel (spin-2 Legendre), FP64 pipe
@@ -312,11 +313,49 @@ def run_ours(args):
                 "e2e": {"value": 1e3 / e2e_ms, "unit": UNIT, "ms_per_step": e2e_ms, "steps": e2e_steps,
                         "h2d_bytes_per_step": bytes_alm + bytes_map, "d2h_bytes_per_step": bytes_alm + bytes_map,
                         "host_buffers": "pinned", "api": "comm_map.Y(); comm_map.YtW()  (4 sharp_execute calls)"},
-                "roofline": roofline, "cpu_baseline": cpu}
+                "roofline": roofline, "cpu_baseline": cpu, "cg": cg}
         print(json.dumps(line))
     if world > 1:
         cdist.destroy(comm)
         dist.destroy_process_group()
+
+
+def run_cg_metric(args, comm, dev, world):
+    """Second half of BASELINE.json's metric: CR CG iterations/s on configs[2] (nside 1024, lmax 2000,
+    IQU, diagonal N^-1 + Gaussian beam, CMB only), criterion fixed_iter as shipped
+    (parameter_files/param_BP8.1_v1.txt:40-47), all vectors device resident."""
+    import numpy as np
+    import torch
+    from commander_b200 import comm_mapinfo
+    from commander_b200.comm_cr import cr_cmb_system, gaussian_beam, solve_cr_eqn_by_CG
+    nside, lmax, iters = 1024, 2000, 10
+    info = comm_mapinfo(comm, nside, lmax, 3, True)
+    l = np.arange(lmax + 1, dtype=np.float64)
+    Cl = np.stack([1.0 / (l * (l + 1) + 1.0)] * 3, axis=1)
+    g = torch.Generator(device=dev).manual_seed(5 + (comm.rank if comm else 0))
+    pix = torch.as_tensor(info.pix, device=dev).double()
+    z = 1.0 - 2.0 * (pix + 0.5) / (12 * nside ** 2)            # ~cos(theta) of the pixel in ring order
+    sigma0 = float(np.sqrt(Cl[1000, 0] * 12 * nside ** 2 / (4 * np.pi)))
+    siN = (1.0 / (sigma0 * (1.0 + 0.5 * (1.0 - z * z)))).expand(3, -1).contiguous()
+    sysm = cr_cmb_system(info, siN, gaussian_beam(lmax, 10.0), Cl)
+    data = torch.empty((3, info.np), dtype=torch.float64, device=dev).normal_(generator=g) / siN
+    b = sysm.computeRHS(data)
+    solve_cr_eqn_by_CG(sysm, b, maxiter=2, cg_conv_crit="fixed_iter")       # warm-up / plans
+    torch.cuda.synchronize()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    ev[0].record()
+    x, it, hist = solve_cr_eqn_by_CG(sysm, b, maxiter=iters, cg_conv_crit="fixed_iter")
+    ev[1].record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([ev[0].elapsed_time(ev[1])], dtype=torch.float64, device=dev)
+    if world > 1:
+        import torch.distributed as dist
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms.item())
+    return {"metric": "CR CG iters/sec", "value": (iters + 1) / (ms * 1e-3), "unit": "iter/s",
+            "config": f"nside={nside} lmax={lmax} IQU, 1 band, CMB only, diagonal N^-1, 10' Gaussian beam, diagonal preconditioner, "
+                      f"fixed_iter x{iters} (+1 initial A.x), device-resident vectors",
+            "ms_per_iter": ms / (iters + 1), "residual_drop": hist[-1] / hist[0]}
 
 
 def main():
@@ -331,6 +370,7 @@ def main():
                     help="CPU sample: every stride-th m (0: full workload for cpu_baseline, 8 for --impl reference)")
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-cg", action="store_true", help="skip the secondary CG iters/s measurement")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -23,7 +23,8 @@
 
 namespace cmdr {
 
-constexpr int TL = 128;    // l per shared-memory tile (== NT: every thread stages one entry)
+constexpr int TL = 128;    // l per shared-memory tile, analysis kernels (one entry per thread)
+constexpr int TLS = 256;   // l per tile, synthesis kernels (TLS / NT entries per thread)
 constexpr int NT = 128;    // threads per CTA
 constexpr unsigned FULL = 0xffffffffu;
 constexpr double SCALE_DOWN = 7.458340731200207e-155;   // 2^-512
@@ -86,7 +87,7 @@ __device__ __forceinline__ void synth0_group(const TileS0 *t, const double (&x)[
 
 template <int R>
 __global__ void __launch_bounds__(NT) synth0_kernel(KParams p) {
-  __shared__ TileS0 tile[2][TL];
+  __shared__ TileS0 tile[2][TLS];
   const int im = blockIdx.y, m = p.mval[im];
   const int tid = threadIdx.x;
   const int chunk0 = p.slot_begin + blockIdx.x * (NT * R);
@@ -137,14 +138,18 @@ __global__ void __launch_bounds__(NT) synth0_kernel(KParams p) {
     }
     return e;
   };
-  tile[0][tid] = load_entry(m + tid);
+#pragma unroll
+  for (int q = 0; q < TLS / NT; ++q) tile[0][tid + q * NT] = load_entry(m + tid + q * NT);
   __syncthreads();
   int buf = 0;
-  for (int lt = m; lt <= p.lmax; lt += TL, buf ^= 1) {
-    const bool more = lt + TL <= p.lmax;
-    TileS0 nxt;
-    if (more) nxt = load_entry(lt + TL + tid);
-    const int ngroups = min(TL, p.lmax - lt + 8) / 8;
+  for (int lt = m; lt <= p.lmax; lt += TLS, buf ^= 1) {
+    const bool more = lt + TLS <= p.lmax;
+    TileS0 nxt[TLS / NT];
+    if (more) {
+#pragma unroll
+      for (int q = 0; q < TLS / NT; ++q) nxt[q] = load_entry(lt + TLS + tid + q * NT);
+    }
+    const int ngroups = min(TLS, p.lmax - lt + 8) / 8;
 #pragma unroll 1
     for (int g = 0; g < ngroups; ++g) {
       bool all_on = true, none_on = true;
@@ -154,7 +159,10 @@ __global__ void __launch_bounds__(NT) synth0_kernel(KParams p) {
       else if (__all_sync(FULL, none_on)) synth0_group<0, R>(tile[buf] + 8 * g, x, cur, prev, per, pei, por, poi, k);
       else synth0_group<1, R>(tile[buf] + 8 * g, x, cur, prev, per, pei, por, poi, k);
     }
-    if (more) tile[buf ^ 1][tid] = nxt;
+    if (more) {
+#pragma unroll
+      for (int q = 0; q < TLS / NT; ++q) tile[buf ^ 1][tid + q * NT] = nxt[q];
+    }
     __syncthreads();
   }
 #pragma unroll
@@ -208,7 +216,7 @@ __device__ __forceinline__ void synth2_group(const TileS2 *t, const double (&x)[
 
 template <int R>
 __global__ void __launch_bounds__(NT) synth2_kernel(KParams p) {
-  __shared__ TileS2 tile[2][TL];
+  __shared__ TileS2 tile[2][TLS];
   const int im = blockIdx.y, m = p.mval[im];
   const int tid = threadIdx.x;
   const int chunk0 = p.slot_begin + blockIdx.x * (NT * R);
@@ -267,14 +275,18 @@ __global__ void __launch_bounds__(NT) synth2_kernel(KParams p) {
     }
     return e;
   };
-  tile[0][tid] = load_entry(l0 + tid);
+#pragma unroll
+  for (int q = 0; q < TLS / NT; ++q) tile[0][tid + q * NT] = load_entry(l0 + tid + q * NT);
   __syncthreads();
   int buf = 0;
-  for (int lt = l0; lt <= p.lmax; lt += TL, buf ^= 1) {
-    const bool more = lt + TL <= p.lmax;
-    TileS2 nxt;
-    if (more) nxt = load_entry(lt + TL + tid);
-    const int ngroups = min(TL, p.lmax - lt + 8) / 8;
+  for (int lt = l0; lt <= p.lmax; lt += TLS, buf ^= 1) {
+    const bool more = lt + TLS <= p.lmax;
+    TileS2 nxt[TLS / NT];
+    if (more) {
+#pragma unroll
+      for (int q = 0; q < TLS / NT; ++q) nxt[q] = load_entry(lt + TLS + tid + q * NT);
+    }
+    const int ngroups = min(TLS, p.lmax - lt + 8) / 8;
 #pragma unroll 1
     for (int g = 0; g < ngroups; ++g) {
       bool all_on = true, none_on = true;
@@ -284,7 +296,10 @@ __global__ void __launch_bounds__(NT) synth2_kernel(KParams p) {
       else if (__all_sync(FULL, none_on)) synth2_group<0, R>(tile[buf] + 8 * g, x, P, Pp, M, Mp, a, k);
       else synth2_group<1, R>(tile[buf] + 8 * g, x, P, Pp, M, Mp, a, k);
     }
-    if (more) tile[buf ^ 1][tid] = nxt;
+    if (more) {
+#pragma unroll
+      for (int q = 0; q < TLS / NT; ++q) tile[buf ^ 1][tid + q * NT] = nxt[q];
+    }
     __syncthreads();
   }
   // sg_l = (-1)^(l+m+2) = sg0 * (-1)^(l-l0)

@@ -59,37 +59,108 @@ __device__ __forceinline__ double *map_ptr(const FParams &p, int c) {
 }
 
 // ---- synthesis, before the FFT: fold phases into the spectrum Z = X_north + i X_south
-__global__ void __launch_bounds__(256) fold_kernel(FParams p) {
-  const int pair = blockIdx.x, c = blockIdx.y;
+// Generic gather form (any ring length, aliasing allowed): bin k sums the m == +-k (mod n).
+// Short rings have few bins and long m-chains, so the chain of each bin is split over
+// `parts` threads and combined through shared memory.
+__device__ __forceinline__ double2 fold_one(const FParams &p, const PhaseLayout &L, int c, int pair, int n,
+                                            bool shifted, int m, bool conj_term) {
+  int src = L.m2src[m];
+  if (src < 0) return make_double2(0.0, 0.0);
+  double4 q = p.ph[((size_t)(src * L.ncomp_tot + L.comp0 + c) * L.NML + L.m2im[m]) * L.NPL + L.pair0 + pair];
+  double2 e = shifted ? expipi(m, n) : make_double2(1.0, 0.0);
+  double2 pn = cmul(make_double2(q.x, q.y), e), ps = cmul(make_double2(q.z, q.w), e);
+  if (conj_term) return make_double2(pn.x + ps.y, -pn.y + ps.x);       // conj p_m
+  if (m == 0) return make_double2(pn.x, ps.x);
+  return make_double2(pn.x - ps.y, pn.y + ps.x);
+}
+
+__global__ void __launch_bounds__(256) fold_kernel(FParams p, int first_pair) {
+  __shared__ double2 part_sum[256];
+  const int pair = first_pair + blockIdx.x, c = blockIdx.y;
   const int n = p.nph[pair], len = p.zlen[pair];
   const bool blue = p.zblue[pair], shifted = p.shifted[pair];
   double2 *out = p.buf + zoff(p, pair, c);
   const PhaseLayout &L = p.L;
+  int parts = 1;
+  while (parts * 2 * n <= 256) parts *= 2;          // power of two, parts * n <= 256
+  if (parts > 1) {
+    const int k = threadIdx.x % n, part = threadIdx.x / n;   // threads >= parts*n idle
+    double2 acc = make_double2(0.0, 0.0);
+    if (part < parts) {
+      for (int m = k + part * n; m <= L.mmax; m += parts * n) {
+        double2 t = fold_one(p, L, c, pair, n, shifted, m, false);
+        acc.x += t.x; acc.y += t.y;
+      }
+      int start = (n - k) % n;
+      if (start == 0) start = n;
+      for (int m = start + part * n; m <= L.mmax; m += parts * n) {
+        double2 t = fold_one(p, L, c, pair, n, shifted, m, true);
+        acc.x += t.x; acc.y += t.y;
+      }
+    }
+    part_sum[threadIdx.x] = acc;
+    __syncthreads();
+    for (int kk = threadIdx.x; kk < len; kk += blockDim.x) {
+      double2 tot = make_double2(0.0, 0.0);
+      if (kk < n) {
+        for (int q = 0; q < parts; ++q) { tot.x += part_sum[kk + q * n].x; tot.y += part_sum[kk + q * n].y; }
+        if (blue) tot = cmul(tot, expipi((long long)kk * kk, n));
+      }
+      out[kk] = tot;
+    }
+    return;
+  }
   for (int k = threadIdx.x; k < len; k += blockDim.x) {
     double2 acc = make_double2(0.0, 0.0);
     if (k < n) {
       for (int m = k; m <= L.mmax; m += n) {          // m == k (mod n): X_k += p_m
-        int src = L.m2src[m];
-        if (src < 0) continue;
-        double4 q = p.ph[((size_t)(src * L.ncomp_tot + L.comp0 + c) * L.NML + L.m2im[m]) * L.NPL + L.pair0 + pair];
-        double2 e = shifted ? expipi(m, n) : make_double2(1.0, 0.0);
-        double2 pn = cmul(make_double2(q.x, q.y), e), ps = cmul(make_double2(q.z, q.w), e);
-        if (m == 0) { acc.x += pn.x; acc.y += ps.x; }
-        else { acc.x += pn.x - ps.y; acc.y += pn.y + ps.x; }
+        double2 t = fold_one(p, L, c, pair, n, shifted, m, false);
+        acc.x += t.x; acc.y += t.y;
       }
       int start = (n - k) % n;
       if (start == 0) start = n;
       for (int m = start; m <= L.mmax; m += n) {      // m == -k (mod n): X_k += conj p_m
-        int src = L.m2src[m];
-        if (src < 0) continue;
-        double4 q = p.ph[((size_t)(src * L.ncomp_tot + L.comp0 + c) * L.NML + L.m2im[m]) * L.NPL + L.pair0 + pair];
-        double2 e = shifted ? expipi(m, n) : make_double2(1.0, 0.0);
-        double2 pn = cmul(make_double2(q.x, q.y), e), ps = cmul(make_double2(q.z, q.w), e);
-        acc.x += pn.x + ps.y; acc.y += -pn.y + ps.x;
+        double2 t = fold_one(p, L, c, pair, n, shifted, m, true);
+        acc.x += t.x; acc.y += t.y;
       }
       if (blue) acc = cmul(acc, expipi((long long)k * k, n));
     }
     out[k] = acc;
+  }
+}
+
+// Rings without aliasing (n >= 2 mmax + 1, the belt at lmax <= 2 nside): every m owns the two
+// bins k = m and k = n - m, so the fold is a transpose.  A 32 (m) x 32 (pair) tile goes through
+// shared memory so that both the phase reads (pair-contiguous) and the spectrum writes
+// (m-contiguous) are coalesced.  The bins in between are cleared by a memset beforehand.
+__global__ void __launch_bounds__(256) fold_transpose_kernel(FParams p, int first_pair, int npairs_r, int n) {
+  __shared__ double4 tile[32][33];
+  const PhaseLayout &L = p.L;
+  const int c = blockIdx.z;
+  const int e0 = blockIdx.y * 32, p0 = blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;     // 32 x 8
+  for (int r = ty; r < 32; r += 8) {
+    int e = e0 + r, pr = p0 + tx;
+    double4 q = make_double4(0, 0, 0, 0);
+    if (e < L.nm_total && pr < npairs_r)
+      q = p.ph[((size_t)(L.mlist_src[e] * L.ncomp_tot + L.comp0 + c) * L.NML + L.mlist_im[e]) * L.NPL + L.pair0 + first_pair + pr];
+    tile[r][tx] = q;
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    int pr = p0 + r, e = e0 + tx;
+    if (pr >= npairs_r || e >= L.nm_total) continue;
+    const int pair = first_pair + pr;
+    const int m = L.mlist[e];
+    double4 q = tile[tx][r];
+    double2 ph = p.shifted[pair] ? expipi(m, n) : make_double2(1.0, 0.0);
+    double2 pn = cmul(make_double2(q.x, q.y), ph), ps = cmul(make_double2(q.z, q.w), ph);
+    double2 *out = p.buf + zoff(p, pair, c);
+    if (m == 0) out[0] = make_double2(pn.x, ps.x);
+    else {
+      out[m] = make_double2(pn.x - ps.y, pn.y + ps.x);
+      out[n - m] = make_double2(pn.x + ps.y, -pn.y + ps.x);
+    }
   }
 }
 
@@ -253,8 +324,18 @@ void ringfft_synth(sharp_geom_info *g, int ncomp, const PhaseLayout &L, const do
   p.ph = const_cast<double4 *>(ph);
   p.map0 = map[0]; p.map1 = ncomp > 1 ? map[1] : nullptr; p.map2 = ncomp > 2 ? map[2] : nullptr;
   p.weighted = weighted; p.add = add;
-  fold_kernel<<<dim3(g->npairs, ncomp), 256, 0, st>>>(p);
-  count_launch();
+  for (size_t r = 0; r < g->regions.size(); ++r) {
+    const FftRegion &R = g->regions[r];
+    if (R.np == 0) continue;
+    if (!R.bluestein && R.len >= 2 * L.mmax + 1) {      // no aliasing: coalesced transpose
+      CMDR_CUDA_CHECK(cudaMemsetAsync(buf + (size_t)ncomp * R.base, 0, sizeof(double2) * (size_t)ncomp * R.np * R.len, st));
+      dim3 grid((R.np + 31) / 32, (L.nm_total + 31) / 32, ncomp);
+      fold_transpose_kernel<<<grid, 256, 0, st>>>(p, R.first, R.np, R.len);
+    } else {
+      fold_kernel<<<dim3(R.np, ncomp), 256, 0, st>>>(p, R.first);
+    }
+    count_launch();
+  }
   run_ffts(g, ncomp, buf, CUFFT_INVERSE, p, st);
   scatter_kernel<<<dim3(g->npairs, ncomp), 256, 0, st>>>(p);
   count_launch();
