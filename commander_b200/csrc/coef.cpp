@@ -70,7 +70,9 @@ void build_coef_table(int lmax, int spin, const std::vector<int> &mval, std::vec
     long long n = lmax >= l0 ? (lmax - l0 + 1) : 0;
     ofs[i + 1] = ofs[i] + n * per;
   }
-  tab.assign((size_t)ofs[nm] + 4, 0.0);
+  // zero padding: the kernels stage whole tiles of up to 256 rows with cp.async and may run past
+  // the last row of the last m
+  tab.assign((size_t)ofs[nm] + 4 * 256 + 4, 0.0);
   unsigned nt = std::thread::hardware_concurrency();
   if (nt == 0) nt = 4;
   if (nt > 32) nt = 32;

@@ -24,7 +24,8 @@
 namespace cmdr {
 
 constexpr int TL = 128;    // l per shared-memory tile, analysis kernels (one entry per thread)
-constexpr int TLS = 256;   // l per tile, synthesis kernels (TLS / NT entries per thread)
+constexpr int TLS = 256;   // l per tile, spin-0 synthesis (TLS / NT entries per thread)
+constexpr int TLS2 = 128;  // l per tile, spin-2 synthesis (measured: 256 is slower there)
 constexpr int NT = 128;    // threads per CTA
 constexpr unsigned FULL = 0xffffffffu;
 constexpr double SCALE_DOWN = 7.458340731200207e-155;   // 2^-512
@@ -97,7 +98,7 @@ __global__ void __launch_bounds__(NT) synth0_kernel(KParams p) {
   const double K = p.Kstart[m];
 #pragma unroll
   for (int r = 0; r < R; ++r) {
-    slot[r] = chunk0 + r * NT + tid;
+    slot[r] = chunk0 + tid * R + r;
     bool valid = slot[r] < p.nslots && m <= p.mlim[min(slot[r], p.nslots - 1)];
     per[r] = pei[r] = por[r] = poi[r] = 0.0;
     prev[r] = 0.0; cur[r] = 0.0; k[r] = 0; x[r] = 0.0;
@@ -216,7 +217,7 @@ __device__ __forceinline__ void synth2_group(const TileS2 *t, const double (&x)[
 
 template <int R>
 __global__ void __launch_bounds__(NT) synth2_kernel(KParams p) {
-  __shared__ TileS2 tile[2][TLS];
+  __shared__ TileS2 tile[2][TLS2];
   const int im = blockIdx.y, m = p.mval[im];
   const int tid = threadIdx.x;
   const int chunk0 = p.slot_begin + blockIdx.x * (NT * R);
@@ -227,7 +228,7 @@ __global__ void __launch_bounds__(NT) synth2_kernel(KParams p) {
   const double K = p.Kstart[m];
 #pragma unroll
   for (int r = 0; r < R; ++r) {
-    slot[r] = chunk0 + r * NT + tid;
+    slot[r] = chunk0 + tid * R + r;
     bool valid = slot[r] < p.nslots && m <= p.mlim[min(slot[r], p.nslots - 1)] && l0 <= p.lmax;
 #pragma unroll
     for (int q = 0; q < 8; ++q) a[r][q] = 0.0;
@@ -276,17 +277,17 @@ __global__ void __launch_bounds__(NT) synth2_kernel(KParams p) {
     return e;
   };
 #pragma unroll
-  for (int q = 0; q < TLS / NT; ++q) tile[0][tid + q * NT] = load_entry(l0 + tid + q * NT);
+  for (int q = 0; q < TLS2 / NT; ++q) tile[0][tid + q * NT] = load_entry(l0 + tid + q * NT);
   __syncthreads();
   int buf = 0;
-  for (int lt = l0; lt <= p.lmax; lt += TLS, buf ^= 1) {
-    const bool more = lt + TLS <= p.lmax;
-    TileS2 nxt[TLS / NT];
+  for (int lt = l0; lt <= p.lmax; lt += TLS2, buf ^= 1) {
+    const bool more = lt + TLS2 <= p.lmax;
+    TileS2 nxt[TLS2 / NT];
     if (more) {
 #pragma unroll
-      for (int q = 0; q < TLS / NT; ++q) nxt[q] = load_entry(lt + TLS + tid + q * NT);
+      for (int q = 0; q < TLS2 / NT; ++q) nxt[q] = load_entry(lt + TLS2 + tid + q * NT);
     }
-    const int ngroups = min(TLS, p.lmax - lt + 8) / 8;
+    const int ngroups = min(TLS2, p.lmax - lt + 8) / 8;
 #pragma unroll 1
     for (int g = 0; g < ngroups; ++g) {
       bool all_on = true, none_on = true;
@@ -298,7 +299,7 @@ __global__ void __launch_bounds__(NT) synth2_kernel(KParams p) {
     }
     if (more) {
 #pragma unroll
-      for (int q = 0; q < TLS / NT; ++q) tile[buf ^ 1][tid + q * NT] = nxt[q];
+      for (int q = 0; q < TLS2 / NT; ++q) tile[buf ^ 1][tid + q * NT] = nxt[q];
     }
     __syncthreads();
   }
@@ -318,64 +319,119 @@ __global__ void __launch_bounds__(NT) synth2_kernel(KParams p) {
 }
 
 // ------------------------------------------------------------------------------------
-// Ring reduction helpers for analysis.  Each lane holds v[G] partial sums (one per l of
-// the group); on return lane L holds the warp total of entry (L >> SH) in v[0].
+// Ring reduction for analysis.  Each lane holds 16 partial sums per group (the l of the group
+// times the real outputs per l); a 5-stage butterfly reduce-scatter over the warp leaves one
+// distinct total in every even lane: 16 double shuffles + 16 DADD per 16 outputs.
+//
+// The stages that split on a bit of the OUTPUT index (re/im; for spin 2 also S1/S2) need no
+// per-lane register selection: the lanes with the corresponding lane bit set accumulate with
+// their per-ring inputs permuted (re<->im swapped, P<->M roles swapped), so their register
+// named "re" holds an imaginary part, etc., and every lane simply keeps the even-named and
+// sends the odd-named register.  Only the stages that split on l need selects.
 // ------------------------------------------------------------------------------------
 __device__ __forceinline__ double shfl_xor_d(double v, int mask) { return __shfl_xor_sync(FULL, v, mask); }
 
-__device__ __forceinline__ void warp_reduce_scatter8(double (&v)[8], int lane) {
-  {  // 8 -> 4 over lane bit 4
-    const bool hi = lane & 16;
+// 16-byte asynchronous global -> shared copies (LDGSTS): the coefficient tiles of the analysis
+// kernels are raw rows of the tables built by coef.cpp, so staging needs no registers.
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src) {
+  unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+template <int H>
+__device__ __forceinline__ void bfly_select(double *v, int lane, int bit) {
+  const bool hi = lane & bit;
+#pragma unroll
+  for (int i = 0; i < H; ++i) {
+    double send = hi ? v[i] : v[i + H], keep = hi ? v[i + H] : v[i];
+    v[i] = keep + shfl_xor_d(send, bit);
+  }
+}
+template <int H>
+__device__ __forceinline__ void bfly_fixed(double *v, int bit) {
+#pragma unroll
+  for (int i = 0; i < H; ++i) v[i] = v[2 * i] + shfl_xor_d(v[2 * i + 1], bit);
+}
+
+// spin 0: acc[2 j + c], j = l in group (8), c = re/im as NAMED (lane bit 4 swaps the meaning).
+// On return the even lanes have stored the total of l = 4 b3 + 2 b2 + b1, part = b4.
+__device__ __forceinline__ int store_index_s0(int lane) {
+  return 2 * (((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1)) + ((lane >> 4) & 1);
+}
+__device__ __forceinline__ void reduce_store_s0(double (&v)[16], double *dst, int lane) {
+  bfly_fixed<8>(v, 16);          // v[j], j = 0..7
+  bfly_select<4>(v, lane, 8);    // j bit 2 <- lane bit 3
+  bfly_select<2>(v, lane, 4);
+  bfly_select<1>(v, lane, 2);
+  v[0] += shfl_xor_d(v[0], 1);
+  if (!(lane & 1)) dst[store_index_s0(lane)] = v[0];
+}
+// spin 2: acc[4 j + 2 s + c], j = l in group (4), s = S1/S2 as named (lane bit 3 swaps),
+// c = re/im as named (lane bit 4 swaps).  Even lanes store l = 2 b2 + b1, s = b3, part = b4.
+__device__ __forceinline__ int store_index_s2(int lane) {
+  return 4 * (((lane >> 2) & 1) * 2 + ((lane >> 1) & 1)) + 2 * ((lane >> 3) & 1) + ((lane >> 4) & 1);
+}
+__device__ __forceinline__ void reduce_store_s2(double (&v)[16], double *dst, int lane) {
+  bfly_fixed<8>(v, 16);          // v[2 j + s]
+  bfly_fixed<4>(v, 8);           // v[j]
+  bfly_select<2>(v, lane, 4);
+  bfly_select<1>(v, lane, 2);
+  v[0] += shfl_xor_d(v[0], 1);
+  if (!(lane & 1)) dst[store_index_s2(lane)] = v[0];
+}
+
+// Software-pipelined form of the same butterfly for the steady phase.  In the step that runs
+// the FMAs of group g, stage 1 is applied to g's sums as they complete, stage 2 to the state
+// left by g-1, stage 3 to g-2, stage 4 to g-3 and stage 5 (+ the store) to g-4: five mutually
+// independent shuffle rounds per step instead of one dependent chain of five, so no warp ever
+// sits in a latency-only phase (with 2-3 resident warps per scheduler such phases line up and
+// leave the FP64 pipe idle).  Same 15 live doubles as holding one extra group of sums.
+struct ReducePipe { double v1[8], v2[4], v3[2], v4; };
+
+template <bool SPIN2>
+__device__ __forceinline__ void pipe_tail(const ReducePipe &in, ReducePipe &out, double *dst, bool store, int lane) {
+  {  // stage 5 -> shared memory (group g-4)
+    double v5 = in.v4 + shfl_xor_d(in.v4, 1);
+    if (store && !(lane & 1)) dst[SPIN2 ? store_index_s2(lane) : store_index_s0(lane)] = v5;
+  }
+  {  // stage 4 (group g-3)
+    const bool hi = lane & 2;
+    double send = hi ? in.v3[0] : in.v3[1], keep = hi ? in.v3[1] : in.v3[0];
+    out.v4 = keep + shfl_xor_d(send, 2);
+  }
+  {  // stage 3 (group g-2)
+    const bool hi = lane & 4;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      double send = hi ? in.v2[i] : in.v2[i + 2], keep = hi ? in.v2[i + 2] : in.v2[i];
+      out.v3[i] = keep + shfl_xor_d(send, 4);
+    }
+  }
+  // stage 2 (group g-1)
+  if (SPIN2) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) out.v2[i] = in.v1[2 * i] + shfl_xor_d(in.v1[2 * i + 1], 8);
+  } else {
+    const bool hi = lane & 8;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      double send = hi ? v[i] : v[i + 4], keep = hi ? v[i + 4] : v[i];
-      v[i] = keep + shfl_xor_d(send, 16);
+      double send = hi ? in.v1[i] : in.v1[i + 4], keep = hi ? in.v1[i + 4] : in.v1[i];
+      out.v2[i] = keep + shfl_xor_d(send, 8);
     }
   }
-  {  // 4 -> 2 over lane bit 3
-    const bool hi = lane & 8;
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {
-      double send = hi ? v[i] : v[i + 2], keep = hi ? v[i + 2] : v[i];
-      v[i] = keep + shfl_xor_d(send, 8);
-    }
-  }
-  {  // 2 -> 1 over lane bit 2
-    const bool hi = lane & 4;
-    double send = hi ? v[0] : v[1], keep = hi ? v[1] : v[0];
-    v[0] = keep + shfl_xor_d(send, 4);
-  }
-  v[0] += shfl_xor_d(v[0], 2);
-  v[0] += shfl_xor_d(v[0], 1);
-}   // entry index held by lane: (lane >> 2) & 7
-
-__device__ __forceinline__ void warp_reduce_scatter4(double (&v)[4], int lane) {
-  {
-    const bool hi = lane & 16;
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {
-      double send = hi ? v[i] : v[i + 2], keep = hi ? v[i + 2] : v[i];
-      v[i] = keep + shfl_xor_d(send, 16);
-    }
-  }
-  {
-    const bool hi = lane & 8;
-    double send = hi ? v[0] : v[1], keep = hi ? v[1] : v[0];
-    v[0] = keep + shfl_xor_d(send, 8);
-  }
-  v[0] += shfl_xor_d(v[0], 4);
-  v[0] += shfl_xor_d(v[0], 2);
-  v[0] += shfl_xor_d(v[0], 1);
-}   // entry index held by lane: (lane >> 3) & 3
+}
 
 // ------------------------------------------------------------------------------------
 // spin-0 analysis:  a_l = sum_rings mu_l * (l-m even ? qN+qS : qN-qS)
+// One group = 8 l; acc[2 j + {0,1}] = {re, im} (as named) of l = group start + j.
 // ------------------------------------------------------------------------------------
 template <int MODE, int R>
-__device__ __forceinline__ void anal0_group(const TileA0 *tA, const double (&x)[R], double (&cur)[R],
-                                            double (&prev)[R], const double (&sr)[R], const double (&si)[R],
-                                            const double (&dr)[R], const double (&di)[R], int (&k)[R],
-                                            double (&accr)[8], double (&acci)[8]) {
+__device__ __forceinline__ void anal0_fma(const TileA0 *tA, const double (&x)[R], double (&cur)[R],
+                                          double (&prev)[R], const double (&sr)[R], const double (&si)[R],
+                                          const double (&dr)[R], const double (&di)[R], int (&k)[R],
+                                          double (&acc)[16]) {
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const double A = tA[j].A;
@@ -390,7 +446,7 @@ __device__ __forceinline__ void anal0_group(const TileA0 *tA, const double (&x)[
       double nxt = step0(A, x[r], cur[r], prev[r]);
       prev[r] = cur[r]; cur[r] = nxt;
     }
-    accr[j] = ar; acci[j] = ai;
+    if (MODE >= 1) { acc[2 * j] = ar; acc[2 * j + 1] = ai; }
   }
   if (MODE < 2) {
 #pragma unroll
@@ -399,20 +455,56 @@ __device__ __forceinline__ void anal0_group(const TileA0 *tA, const double (&x)[
   }
 }
 
-template <int R>
-__global__ void __launch_bounds__(NT) anal0_kernel(KParams p) {
-  __shared__ TileA0 tile[2][TL];
-  __shared__ double red[2][NT / 32][TL][2];
+// steady-phase step: FMAs of one group with stage 1 applied per l, stages 2-5 on the older groups
+template <int R, bool FMA>
+__device__ __forceinline__ void anal0_step(const TileA0 *tA, const double (&x)[R], double (&cur)[R],
+                                           double (&prev)[R], const double (&sr)[R], const double (&si)[R],
+                                           const double (&dr)[R], const double (&di)[R],
+                                           const ReducePipe &in, ReducePipe &out, double *dst, bool store, int lane) {
+  pipe_tail<false>(in, out, dst, store, lane);
+  if (FMA) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const double A = tA[j].A;
+      double ar = 0.0, ai = 0.0;
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        if (j & 1) { ar = fma(cur[r], dr[r], ar); ai = fma(cur[r], di[r], ai); }
+        else       { ar = fma(cur[r], sr[r], ar); ai = fma(cur[r], si[r], ai); }
+        double nxt = step0(A, x[r], cur[r], prev[r]);
+        prev[r] = cur[r]; cur[r] = nxt;
+      }
+      out.v1[j] = ar + shfl_xor_d(ai, 16);
+    }
+  }
+}
+
+// Analysis kernels, common structure: ONE WARP PER CTA, no block-level synchronisation at all.
+// A thread owns R ADJACENT ring pairs, the warp 32 R adjacent ones (similar colatitude, so they
+// cross the accumulation threshold at similar l, and whole warps fall beyond the m cut-off near
+// the poles).  The warp stages its own coefficient tiles (TL l, double buffered, cp.async
+// straight from the table) and walks the groups of a tile in two phases: a transient one while
+// some of its rings are still below the threshold (warp-uniform choice between "recurrence only"
+// and "predicated", reduction done at once) and a steady one (all rings on -- they stay on) in
+// which the butterfly of group g-1 sits in the same basic block as the FMAs of group g, so the
+// shuffle latency hides behind FP64 work.  After each tile the reduced sums are read back l-major
+// from shared memory and added to the a_lm with fully coalesced atomics (other warps hold the
+// other rings of the same m).
+template <int R, int MINB>
+__global__ void __launch_bounds__(32, MINB) anal0_kernel(KParams p) {
+  __shared__ __align__(16) TileA0 tile[2][TL];
+  __shared__ __align__(16) double red[TL * 2];
   const int im = blockIdx.y, m = p.mval[im];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int chunk0 = p.slot_begin + blockIdx.x * (NT * R);
+  const int lane = threadIdx.x;
+  const int chunk0 = p.slot_begin + blockIdx.x * (32 * R);
   double x[R], cur[R], prev[R], sr[R], si[R], dr[R], di[R];
   int k[R];
   bool any = false;
   const double K = p.Kstart[m];
+  const bool swapRI = lane & 16;
 #pragma unroll
   for (int r = 0; r < R; ++r) {
-    int slot = chunk0 + r * NT + tid;
+    int slot = chunk0 + lane * R + r;
     bool valid = slot < p.nslots && m <= p.mlim[min(slot, p.nslots - 1)];
     prev[r] = cur[r] = x[r] = 0.0; k[r] = 0;
     sr[r] = si[r] = dr[r] = di[r] = 0.0;
@@ -422,67 +514,89 @@ __global__ void __launch_bounds__(NT) anal0_kernel(KParams p) {
       x[r] = g.cth;
       start_spin0(m, K, g, cur[r], k[r]);
       double4 q = p.ph[ph_index(p, 0, im, slot)];
-      sr[r] = q.x + q.z; si[r] = q.y + q.w; dr[r] = q.x - q.z; di[r] = q.y - q.w;
+      const double re_s = q.x + q.z, im_s = q.y + q.w, re_d = q.x - q.z, im_d = q.y - q.w;
+      sr[r] = swapRI ? im_s : re_s; si[r] = swapRI ? re_s : im_s;
+      dr[r] = swapRI ? im_d : re_d; di[r] = swapRI ? re_d : im_d;
       any = true;
     }
   }
-  if (!__syncthreads_or(any)) return;
+  if (!__any_sync(FULL, any)) return;
   const double *coef = p.coef + p.cofs[im];
   const long long mvs = p.mvstart[im];
   // real-packed: orthonormal real basis (sqrt2 both ways).  complex a_lm: the phases carry the
   // factor 2 of the m>0 terms, so the adjoint needs 1/2 to return sum conj(Y) x as libsharp2 does
   const double nrm = m > 0 ? (p.real_packed ? 0.70710678118654752440 : 0.5) : 1.0;
-  auto load_entry = [&](int l) {
-    TileA0 e{0.0, 0.0};
-    if (l <= p.lmax) { double2 c = reinterpret_cast<const double2 *>(coef)[l - m]; e.A = c.x; e.g = c.y; }
-    return e;
+  // rows past lmax belong to the next m (or the table's zero padding): finite, never used
+  auto issue_tile = [&](int b, int lt) {
+    const char *src = reinterpret_cast<const char *>(coef + 2 * (size_t)(lt - m));
+    char *dst = reinterpret_cast<char *>(tile[b]);
+#pragma unroll
+    for (int q = 0; q < (int)(TL * sizeof(TileA0)) / 512; ++q) cp_async16(dst + (q * 32 + lane) * 16, src + (q * 32 + lane) * 16);
+    cp_async_commit();
   };
-  tile[0][tid] = load_entry(m + tid);
-  __syncthreads();
+  issue_tile(0, m);
+  cp_async_wait_all();
+  __syncwarp();
   int buf = 0;
+  bool steady = false;
   for (int lt = m; lt <= p.lmax; lt += TL, buf ^= 1) {
-    const bool more = lt + TL <= p.lmax;
-    TileA0 nxt;
-    if (more) nxt = load_entry(lt + TL + tid);
+    if (lt + TL <= p.lmax) issue_tile(buf ^ 1, lt + TL);
     const int ngroups = min(TL, p.lmax - lt + 8) / 8;
+    const TileA0 *T = tile[buf];
+    double *dst = red;
+    int g = 0;
+    if (!steady) {
 #pragma unroll 1
-    for (int g = 0; g < ngroups; ++g) {
-      bool all_on = true, none_on = true;
+      for (; g < ngroups; ++g) {
+        bool all_on = true, none_on = true;
 #pragma unroll
-      for (int r = 0; r < R; ++r) { all_on &= (k[r] == 0); none_on &= (k[r] < 0); }
-      double accr[8], acci[8];
-      const bool w_none = __all_sync(FULL, none_on);
-      if (__all_sync(FULL, all_on)) anal0_group<2, R>(tile[buf] + 8 * g, x, cur, prev, sr, si, dr, di, k, accr, acci);
-      else if (w_none) anal0_group<0, R>(tile[buf] + 8 * g, x, cur, prev, sr, si, dr, di, k, accr, acci);
-      else anal0_group<1, R>(tile[buf] + 8 * g, x, cur, prev, sr, si, dr, di, k, accr, acci);
-      if (!w_none) { warp_reduce_scatter8(accr, lane); warp_reduce_scatter8(acci, lane); }
-      if ((lane & 3) == 0) {
-        int j = (lane >> 2) & 7;
-        red[buf][warp][8 * g + j][0] = w_none ? 0.0 : accr[0];
-        red[buf][warp][8 * g + j][1] = w_none ? 0.0 : acci[0];
-      }
-    }
-    if (more) tile[buf ^ 1][tid] = nxt;
-    __syncthreads();
-    // cross-warp sum of this tile (one l per thread); red[buf]/tile[buf] are rewritten only
-    // after the next barrier
-    {
-      int l = lt + tid;
-      if (l <= p.lmax) {
-        double re = 0.0, im_ = 0.0;
-#pragma unroll
-        for (int w = 0; w < NT / 32; ++w) { re += red[buf][w][tid][0]; im_ += red[buf][w][tid][1]; }
-        double gs = tile[buf][tid].g * nrm;
-        double *a = p.alm0;
-        if (p.real_packed) {
-          if (m == 0) atomicAdd(&a[mvs + l], gs * re);
-          else { atomicAdd(&a[mvs + 2 * (long long)l], gs * re); atomicAdd(&a[mvs + 2 * (long long)l + 1], gs * im_); }
+        for (int r = 0; r < R; ++r) { all_on &= (k[r] == 0); none_on &= (k[r] < 0); }
+        if (__all_sync(FULL, all_on)) { steady = true; break; }
+        double acc[16];
+        if (__all_sync(FULL, none_on)) {
+          anal0_fma<0, R>(T + 8 * g, x, cur, prev, sr, si, dr, di, k, acc);
+          if (!(lane & 1)) dst[16 * g + (lane >> 1)] = 0.0;
         } else {
-          atomicAdd(&a[2 * (mvs + l)], gs * re);
-          if (m > 0) atomicAdd(&a[2 * (mvs + l) + 1], gs * im_);
+          anal0_fma<1, R>(T + 8 * g, x, cur, prev, sr, si, dr, di, k, acc);
+          reduce_store_s0(acc, dst + 16 * g, lane);
         }
       }
     }
+    if (g < ngroups) {
+      const int gs = g;
+      ReducePipe st;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) st.v1[i] = 0.0;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) st.v2[i] = 0.0;
+      st.v3[0] = st.v3[1] = st.v4 = 0.0;
+#pragma unroll 2
+      for (; g < ngroups; ++g) {
+        ReducePipe nx;
+        anal0_step<R, true>(T + 8 * g, x, cur, prev, sr, si, dr, di, st, nx, dst + 16 * (g - 4), g - 4 >= gs, lane);
+        st = nx;
+      }
+#pragma unroll
+      for (int d = 0; d < 4; ++d, ++g) {   // drain
+        ReducePipe nx;
+        anal0_step<R, false>(T, x, cur, prev, sr, si, dr, di, st, nx, dst + 16 * (g - 4), g - 4 >= gs, lane);
+        st = nx;
+      }
+    }
+    cp_async_wait_all();
+    __syncwarp();
+    // flush the tile: lane pair (2i, 2i+1) = (re, im) of one l -> contiguous atomics
+    double *a = p.alm0;
+#pragma unroll 1
+    for (int e = lane; e < 2 * TL; e += 32) {
+      const int li = e >> 1, part = e & 1, l = lt + li;
+      if (l <= p.lmax && (m > 0 || part == 0)) {
+        const double val = T[li].g * nrm * red[e];
+        const long long idx = p.real_packed ? (m == 0 ? mvs + l : mvs + 2 * (long long)l + part) : 2 * (mvs + l) + part;
+        atomicAdd(&a[idx], val);
+      }
+    }
+    __syncwarp();
   }
 }
 
@@ -490,145 +604,220 @@ __global__ void __launch_bounds__(NT) anal0_kernel(KParams p) {
 // spin-2 analysis.  zp = qQ + i qU, zm = qQ - i qU per ring (north, south*sg0);
 //   S1_l = sum P zpN + sg M zpS ; S2_l = sum M zmN + sg P zmS
 //   E_l = -(S1+S2)/2 ; B_l = (i/2)(S1-S2)
+// One group = 4 l; acc[4 j + 2 s + c] = {S1.re, S1.im, S2.re, S2.im} (as named) of l = start + j.
+// Pa / Pb are the recurrences in the "P role" (u = A x + Cs) and "M role" (u = A x - Cs); lanes
+// with bit 3 set run them swapped (Cs = -C', Pa = M, Pb = P, w permuted) so that their registers
+// named S1 hold S2 and vice versa (see the reduction above).
 // ------------------------------------------------------------------------------------
 template <int MODE, int R>
-__device__ __forceinline__ void anal2_group(const TileA2 *t, const double (&x)[R], double (&P)[R],
-                                            double (&Pp)[R], double (&M)[R], double (&Mp)[R],
-                                            const double (&z)[R][8], int (&k)[R], double (&acc)[4][4]) {
+__device__ __forceinline__ void anal2_fma(const TileA2 *t, const double csign, const double (&x)[R], double (&Pa)[R],
+                                          double (&Pap)[R], double (&Pb)[R], double (&Pbp)[R],
+                                          const double (&w)[R][8], int (&k)[R], double (&acc)[16]) {
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
-    const double A = t[j].A, C = t[j].C;
+    const double A = t[j].A, C = t[j].C * csign;
     double s1r = 0.0, s1i = 0.0, s2r = 0.0, s2i = 0.0;
 #pragma unroll
     for (int r = 0; r < R; ++r) {
       if (MODE >= 1) {
         bool on = (MODE == 2 || k[r] == 0);
-        double vp = on ? P[r] : 0.0, vm = on ? M[r] : 0.0;
-        // z: 0,1 zpN ; 2,3 zmN ; 4,5 zpS ; 6,7 zmS
-        s1r = fma(vp, z[r][0], s1r); s1i = fma(vp, z[r][1], s1i);
-        s2r = fma(vm, z[r][2], s2r); s2i = fma(vm, z[r][3], s2i);
+        double va = on ? Pa[r] : 0.0, vb = on ? Pb[r] : 0.0;
+        // w: 0,1 zpN ; 2,3 zmN ; 4,5 zpS ; 6,7 zmS  (before the per-lane permutation)
+        s1r = fma(va, w[r][0], s1r); s1i = fma(va, w[r][1], s1i);
+        s2r = fma(vb, w[r][2], s2r); s2i = fma(vb, w[r][3], s2i);
         if (j & 1) {
-          s1r = fma(-vm, z[r][4], s1r); s1i = fma(-vm, z[r][5], s1i);
-          s2r = fma(-vp, z[r][6], s2r); s2i = fma(-vp, z[r][7], s2i);
+          s1r = fma(-vb, w[r][4], s1r); s1i = fma(-vb, w[r][5], s1i);
+          s2r = fma(-va, w[r][6], s2r); s2i = fma(-va, w[r][7], s2i);
         } else {
-          s1r = fma(vm, z[r][4], s1r); s1i = fma(vm, z[r][5], s1i);
-          s2r = fma(vp, z[r][6], s2r); s2i = fma(vp, z[r][7], s2i);
+          s1r = fma(vb, w[r][4], s1r); s1i = fma(vb, w[r][5], s1i);
+          s2r = fma(va, w[r][6], s2r); s2i = fma(va, w[r][7], s2i);
         }
       }
-      double up = fma(A, x[r], C), um = fma(A, x[r], -C);
-      double np_ = fma(up, P[r], -Pp[r]), nm_ = fma(um, M[r], -Mp[r]);
-      Pp[r] = P[r]; P[r] = np_; Mp[r] = M[r]; M[r] = nm_;
+      double ua = fma(A, x[r], C), ub = fma(A, x[r], -C);
+      double na = fma(ua, Pa[r], -Pap[r]), nb = fma(ub, Pb[r], -Pbp[r]);
+      Pap[r] = Pa[r]; Pa[r] = na; Pbp[r] = Pb[r]; Pb[r] = nb;
     }
-    acc[0][j] = s1r; acc[1][j] = s1i; acc[2][j] = s2r; acc[3][j] = s2i;
+    if (MODE >= 1) { acc[4 * j] = s1r; acc[4 * j + 1] = s1i; acc[4 * j + 2] = s2r; acc[4 * j + 3] = s2i; }
   }
   if (MODE < 2) {
 #pragma unroll
     for (int r = 0; r < R; ++r)
-      if (k[r] < 0 && (needs_rescale(P[r]) || needs_rescale(M[r]))) {
-        P[r] *= SCALE_DOWN; Pp[r] *= SCALE_DOWN; M[r] *= SCALE_DOWN; Mp[r] *= SCALE_DOWN; ++k[r];
+      if (k[r] < 0 && (needs_rescale(Pa[r]) || needs_rescale(Pb[r]))) {
+        Pa[r] *= SCALE_DOWN; Pap[r] *= SCALE_DOWN; Pb[r] *= SCALE_DOWN; Pbp[r] *= SCALE_DOWN; ++k[r];
       }
   }
 }
 
-template <int R>
-__global__ void __launch_bounds__(NT) anal2_kernel(KParams p) {
-  __shared__ TileA2 tile[2][TL];
-  __shared__ double red[2][NT / 32][TL][4];
+// Loop order: ring outer, l inner.  For a fixed ring the recurrence is a dependent chain over l,
+// so the scheduler issues [next value, 4 accumulates] of one lambda back to back -- five DFMAs with
+// the same first operand, which then comes from the operand-reuse cache (a DFMA costs
+// max(2, #vector operands fetched from the register file) cycles on B200).
+template <int R, bool FMA>
+__device__ __forceinline__ void anal2_step(const TileA2 *t, const double csign, const double (&x)[R], double (&Pa)[R],
+                                           double (&Pap)[R], double (&Pb)[R], double (&Pbp)[R],
+                                           const double (&w)[R][8], const ReducePipe &in, ReducePipe &out,
+                                           double *dst, bool store, int lane) {
+  pipe_tail<true>(in, out, dst, store, lane);
+  if (FMA) {
+    double s[4][4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.0;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      double ua[4], ub[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const double A = t[j].A, C = t[j].C * csign;
+        ua[j] = fma(x[r], A, C); ub[j] = fma(x[r], A, -C);
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const double va = Pa[r], vb = Pb[r];
+        const double na = fma(va, ua[j], -Pap[r]);
+        s[j][0] = fma(va, w[r][0], s[j][0]); s[j][1] = fma(va, w[r][1], s[j][1]);
+        if (j & 1) { s[j][2] = fma(-va, w[r][6], s[j][2]); s[j][3] = fma(-va, w[r][7], s[j][3]); }
+        else       { s[j][2] = fma(va, w[r][6], s[j][2]);  s[j][3] = fma(va, w[r][7], s[j][3]); }
+        const double nb = fma(vb, ub[j], -Pbp[r]);
+        s[j][2] = fma(vb, w[r][2], s[j][2]); s[j][3] = fma(vb, w[r][3], s[j][3]);
+        if (j & 1) { s[j][0] = fma(-vb, w[r][4], s[j][0]); s[j][1] = fma(-vb, w[r][5], s[j][1]); }
+        else       { s[j][0] = fma(vb, w[r][4], s[j][0]);  s[j][1] = fma(vb, w[r][5], s[j][1]); }
+        Pap[r] = va; Pa[r] = na; Pbp[r] = vb; Pb[r] = nb;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      out.v1[2 * j] = s[j][0] + shfl_xor_d(s[j][1], 16);
+      out.v1[2 * j + 1] = s[j][2] + shfl_xor_d(s[j][3], 16);
+    }
+  }
+}
+
+template <int R, int MINB>
+__global__ void __launch_bounds__(32, MINB) anal2_kernel(KParams p) {
+  __shared__ __align__(16) TileA2 tile[2][TL];
+  __shared__ __align__(16) double red[TL * 4];
   const int im = blockIdx.y, m = p.mval[im];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int chunk0 = p.slot_begin + blockIdx.x * (NT * R);
+  const int lane = threadIdx.x;
+  const int chunk0 = p.slot_begin + blockIdx.x * (32 * R);
   const int l0 = max(m, 2);
   if (l0 > p.lmax) return;
-  double x[R], P[R], Pp[R], M[R], Mp[R], z[R][8];
+  double x[R], Pa[R], Pap[R], Pb[R], Pbp[R], w[R][8];
   int k[R];
   bool any = false;
   const double K = p.Kstart[m];
   const double sg0 = ((l0 + m) & 1) ? -1.0 : 1.0;
+  const bool swapRI = lane & 16, swapPM = lane & 8;
+  const double csign = swapPM ? -1.0 : 1.0;
 #pragma unroll
   for (int r = 0; r < R; ++r) {
-    int slot = chunk0 + r * NT + tid;
+    int slot = chunk0 + lane * R + r;
     bool valid = slot < p.nslots && m <= p.mlim[min(slot, p.nslots - 1)];
-    P[r] = M[r] = Pp[r] = Mp[r] = x[r] = 0.0; k[r] = 0;
+    Pa[r] = Pb[r] = Pap[r] = Pbp[r] = x[r] = 0.0; k[r] = 0;
 #pragma unroll
-    for (int q = 0; q < 8; ++q) z[r][q] = 0.0;
+    for (int q = 0; q < 8; ++q) w[r][q] = 0.0;
     if (valid) {
       const double4 tg = reinterpret_cast<const double4 *>(p.trig)[slot];
       RingTrig g{tg.x, tg.y, tg.z, tg.w};
       x[r] = g.cth;
-      start_spin2(m, K, g, P[r], M[r], k[r]);
+      double P0, M0;
+      start_spin2(m, K, g, P0, M0, k[r]);
+      Pa[r] = swapPM ? M0 : P0; Pb[r] = swapPM ? P0 : M0;
       double4 q = p.ph[ph_index(p, 0, im, slot)], u = p.ph[ph_index(p, 1, im, slot)];
-      z[r][0] = q.x - u.y; z[r][1] = q.y + u.x;            // zpN = qQ + i qU
-      z[r][2] = q.x + u.y; z[r][3] = q.y - u.x;            // zmN = qQ - i qU
-      z[r][4] = sg0 * (q.z - u.w); z[r][5] = sg0 * (q.w + u.z);
-      z[r][6] = sg0 * (q.z + u.w); z[r][7] = sg0 * (q.w - u.z);
+      double z[8];
+      z[0] = q.x - u.y; z[1] = q.y + u.x;            // zpN = qQ + i qU
+      z[2] = q.x + u.y; z[3] = q.y - u.x;            // zmN = qQ - i qU
+      z[4] = sg0 * (q.z - u.w); z[5] = sg0 * (q.w + u.z);
+      z[6] = sg0 * (q.z + u.w); z[7] = sg0 * (q.w - u.z);
+      // w[i] = z[i ^ (swapPM ? 2 : 0) ^ (swapRI ? 1 : 0)]
+#pragma unroll
+      for (int i = 0; i < 8; i += 2) {
+        double a0 = swapPM ? z[i ^ 2] : z[i], a1 = swapPM ? z[(i ^ 2) + 1] : z[i + 1];
+        w[r][i] = swapRI ? a1 : a0; w[r][i + 1] = swapRI ? a0 : a1;
+      }
       any = true;
     }
   }
-  if (!__syncthreads_or(any)) return;
+  if (!__any_sync(FULL, any)) return;
   const double *coef = p.coef + p.cofs[im];
   const long long mvs = p.mvstart[im];
   // real-packed: orthonormal real basis (sqrt2 both ways).  complex a_lm: the phases carry the
   // factor 2 of the m>0 terms, so the adjoint needs 1/2 to return sum conj(Y) x as libsharp2 does
   const double nrm = m > 0 ? (p.real_packed ? 0.70710678118654752440 : 0.5) : 1.0;
-  auto load_entry = [&](int l) {
-    TileA2 e{0.0, 0.0, 0.0, 0.0};
-    if (l <= p.lmax) { double4 c = reinterpret_cast<const double4 *>(coef)[l - l0]; e.A = c.x; e.C = c.y; e.g = c.z; }
-    return e;
+  // rows past lmax belong to the next m (or the table's zero padding): finite, never used
+  auto issue_tile = [&](int b, int lt) {
+    const char *src = reinterpret_cast<const char *>(coef + 4 * (size_t)(lt - l0));
+    char *dst = reinterpret_cast<char *>(tile[b]);
+#pragma unroll
+    for (int q = 0; q < (int)(TL * sizeof(TileA2)) / 512; ++q) cp_async16(dst + (q * 32 + lane) * 16, src + (q * 32 + lane) * 16);
+    cp_async_commit();
   };
-  tile[0][tid] = load_entry(l0 + tid);
-  __syncthreads();
+  issue_tile(0, l0);
+  cp_async_wait_all();
+  __syncwarp();
   int buf = 0;
+  bool steady = false;
   for (int lt = l0; lt <= p.lmax; lt += TL, buf ^= 1) {
-    const bool more = lt + TL <= p.lmax;
-    TileA2 nxt;
-    if (more) nxt = load_entry(lt + TL + tid);
+    if (lt + TL <= p.lmax) issue_tile(buf ^ 1, lt + TL);
     const int ngroups = min(TL, p.lmax - lt + 4) / 4;
+    const TileA2 *T = tile[buf];
+    double *dst = red;
+    int g = 0;
+    if (!steady) {
 #pragma unroll 1
-    for (int g = 0; g < ngroups; ++g) {
-      bool all_on = true, none_on = true;
+      for (; g < ngroups; ++g) {
+        bool all_on = true, none_on = true;
 #pragma unroll
-      for (int r = 0; r < R; ++r) { all_on &= (k[r] == 0); none_on &= (k[r] < 0); }
-      double acc[4][4];
-      const bool w_none = __all_sync(FULL, none_on);
-      if (__all_sync(FULL, all_on)) anal2_group<2, R>(tile[buf] + 4 * g, x, P, Pp, M, Mp, z, k, acc);
-      else if (w_none) anal2_group<0, R>(tile[buf] + 4 * g, x, P, Pp, M, Mp, z, k, acc);
-      else anal2_group<1, R>(tile[buf] + 4 * g, x, P, Pp, M, Mp, z, k, acc);
-      if (!w_none) {
-#pragma unroll
-        for (int v = 0; v < 4; ++v) warp_reduce_scatter4(acc[v], lane);
-      }
-      if ((lane & 7) == 0) {
-        int j = (lane >> 3) & 3;
-#pragma unroll
-        for (int v = 0; v < 4; ++v) red[buf][warp][4 * g + j][v] = w_none ? 0.0 : acc[v][0];
-      }
-    }
-    if (more) tile[buf ^ 1][tid] = nxt;
-    __syncthreads();
-    {
-      int l = lt + tid;
-      if (l <= p.lmax) {
-        double s[4] = {0.0, 0.0, 0.0, 0.0};
-#pragma unroll
-        for (int w = 0; w < NT / 32; ++w)
-#pragma unroll
-          for (int v = 0; v < 4; ++v) s[v] += red[buf][w][tid][v];
-        double gs = tile[buf][tid].g * nrm;
-        double Er = -0.5 * gs * (s[0] + s[2]), Ei = -0.5 * gs * (s[1] + s[3]);
-        double Br = -0.5 * gs * (s[1] - s[3]), Bi = 0.5 * gs * (s[0] - s[2]);
-        double *aE = p.alm0, *aB = p.alm1;
-        if (p.real_packed) {
-          if (m == 0) { atomicAdd(&aE[mvs + l], Er); atomicAdd(&aB[mvs + l], Br); }
-          else {
-            atomicAdd(&aE[mvs + 2 * (long long)l], Er); atomicAdd(&aE[mvs + 2 * (long long)l + 1], Ei);
-            atomicAdd(&aB[mvs + 2 * (long long)l], Br); atomicAdd(&aB[mvs + 2 * (long long)l + 1], Bi);
-          }
+        for (int r = 0; r < R; ++r) { all_on &= (k[r] == 0); none_on &= (k[r] < 0); }
+        if (__all_sync(FULL, all_on)) { steady = true; break; }
+        double acc[16];
+        if (__all_sync(FULL, none_on)) {
+          anal2_fma<0, R>(T + 4 * g, csign, x, Pa, Pap, Pb, Pbp, w, k, acc);
+          if (!(lane & 1)) dst[16 * g + (lane >> 1)] = 0.0;
         } else {
-          atomicAdd(&aE[2 * (mvs + l)], Er); atomicAdd(&aB[2 * (mvs + l)], Br);
-          if (m > 0) { atomicAdd(&aE[2 * (mvs + l) + 1], Ei); atomicAdd(&aB[2 * (mvs + l) + 1], Bi); }
+          anal2_fma<1, R>(T + 4 * g, csign, x, Pa, Pap, Pb, Pbp, w, k, acc);
+          reduce_store_s2(acc, dst + 16 * g, lane);
         }
       }
     }
+    if (g < ngroups) {
+      const int gs = g;
+      ReducePipe st;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) st.v1[i] = 0.0;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) st.v2[i] = 0.0;
+      st.v3[0] = st.v3[1] = st.v4 = 0.0;
+#pragma unroll 2
+      for (; g < ngroups; ++g) {
+        ReducePipe nx;
+        anal2_step<R, true>(T + 4 * g, csign, x, Pa, Pap, Pb, Pbp, w, st, nx, dst + 16 * (g - 4), g - 4 >= gs, lane);
+        st = nx;
+      }
+#pragma unroll
+      for (int d = 0; d < 4; ++d, ++g) {   // drain
+        ReducePipe nx;
+        anal2_step<R, false>(T, csign, x, Pa, Pap, Pb, Pbp, w, st, nx, dst + 16 * (g - 4), g - 4 >= gs, lane);
+        st = nx;
+      }
+    }
+    cp_async_wait_all();
+    __syncwarp();
+    // flush the tile: lane pair (2i, 2i+1) = (re, im) of one l -> contiguous atomics
+    double *aE = p.alm0, *aB = p.alm1;
+#pragma unroll 1
+    for (int e = lane; e < 2 * TL; e += 32) {
+      const int li = e >> 1, part = e & 1, l = lt + li;
+      if (l <= p.lmax && (m > 0 || part == 0)) {
+        const double4 v = reinterpret_cast<const double4 *>(red)[li];   // S1.re, S1.im, S2.re, S2.im
+        const double gs = T[li].g * nrm;
+        const double E = part ? -0.5 * gs * (v.y + v.w) : -0.5 * gs * (v.x + v.z);
+        const double B = part ? 0.5 * gs * (v.x - v.z) : -0.5 * gs * (v.y - v.w);
+        const long long idx = p.real_packed ? (m == 0 ? mvs + l : mvs + 2 * (long long)l + part) : 2 * (mvs + l) + part;
+        atomicAdd(&aE[idx], E);
+        atomicAdd(&aB[idx], B);
+      }
+    }
+    __syncwarp();
   }
 }
 
@@ -684,23 +873,40 @@ void launch_legendre_synth(int spin, const LegGeom &g, const LegAlm &a, const do
   CMDR_CUDA_CHECK(cudaGetLastError());
 }
 
+template <int R, typename K>
+static void launch_w(K kernel, const KParams &p, int nm, cudaStream_t st) {   // one warp per CTA
+  const int n = p.nslots - p.slot_begin;
+  if (n <= 0) return;
+  dim3 grid((n + 32 * R - 1) / (32 * R), nm);
+  kernel<<<grid, 32, 0, st>>>(p);
+}
+
 void launch_legendre_anal(int spin, const LegGeom &g, const LegAlm &a, double *const *alm,
                           const double4 *ph, cudaStream_t st) {
   if (a.nm == 0 || g.nslots == 0) return;
   KParams p = make_params(g, a, alm[0], spin ? alm[1] : nullptr, const_cast<double4 *>(ph));
   static const int r0 = env_int("CMDR_SHT_R_A0", 4), r2 = env_int("CMDR_SHT_R_A2", 4);
+  // resident warps per SM the register allocation is capped for (tuning: CMDR_SHT_MINB_A0 / _A2)
+  static const int b0 = env_int("CMDR_SHT_MINB_A0", 16), b2 = env_int("CMDR_SHT_MINB_A2", 12);
   if (spin == 0) {
-    switch (r0) {
-      case 2: launch_r<2>(anal0_kernel<2>, p, g.nslots, a.nm, st); break;
-      case 6: launch_r<6>(anal0_kernel<6>, p, g.nslots, a.nm, st); break;
-      case 8: launch_r<8>(anal0_kernel<8>, p, g.nslots, a.nm, st); break;
-      default: launch_r<4>(anal0_kernel<4>, p, g.nslots, a.nm, st); break;
+    switch (r0 * 100 + b0) {
+      case 416: launch_w<4>(anal0_kernel<4, 16>, p, a.nm, st); break;
+      case 408: launch_w<4>(anal0_kernel<4, 8>, p, a.nm, st); break;
+      case 612: launch_w<6>(anal0_kernel<6, 12>, p, a.nm, st); break;
+      case 608: launch_w<6>(anal0_kernel<6, 8>, p, a.nm, st); break;
+      case 812: launch_w<8>(anal0_kernel<8, 12>, p, a.nm, st); break;
+      case 808: launch_w<8>(anal0_kernel<8, 8>, p, a.nm, st); break;
+      default: launch_w<4>(anal0_kernel<4, 12>, p, a.nm, st); break;
     }
   } else {
-    switch (r2) {
-      case 3: launch_r<3>(anal2_kernel<3>, p, g.nslots, a.nm, st); break;
-      case 2: launch_r<2>(anal2_kernel<2>, p, g.nslots, a.nm, st); break;
-      default: launch_r<4>(anal2_kernel<4>, p, g.nslots, a.nm, st); break;
+    switch (r2 * 100 + b2) {
+      case 312: launch_w<3>(anal2_kernel<3, 12>, p, a.nm, st); break;
+      case 308: launch_w<3>(anal2_kernel<3, 8>, p, a.nm, st); break;
+      case 216: launch_w<2>(anal2_kernel<2, 16>, p, a.nm, st); break;
+      case 212: launch_w<2>(anal2_kernel<2, 12>, p, a.nm, st); break;
+      case 412: launch_w<4>(anal2_kernel<4, 12>, p, a.nm, st); break;
+      case 410: launch_w<4>(anal2_kernel<4, 10>, p, a.nm, st); break;
+      default: launch_w<4>(anal2_kernel<4, 8>, p, a.nm, st); break;
     }
   }
   count_launch();
