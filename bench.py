@@ -266,8 +266,12 @@ def run_ours(args):
 
     # ---- roofline of the dominant kernel (spin-2 Legendre), FP64 pipe
     fp64_peak = sharp.measure_fp64_tflops(4096, 5)
-    per = {}
+    per, stages = {}, {}
     for spin, direction, msv in leg:
+        if spin >= 100:     # 100+spin: ring-FFT stage, 200/201: exchange barriers or all-to-all
+            nm = (f"ringfft_spin{int(spin) - 100}" if spin < 200 else ("exchange_pre" if spin == 200 else "exchange_post")) + ("_analysis" if direction else "_synthesis")
+            stages.setdefault(nm, []).append(msv)
+            continue
         per.setdefault((spin, direction), []).append(msv)
     avg = {k: sum(v) / len(v) for k, v in per.items()}
     share = sum(sum(v) for v in per.values()) / max(ms_total, 1e-9)
@@ -277,6 +281,7 @@ def run_ours(args):
     achieved = flops2 / (dom[1] * 1e-3) / 1e12
     kern = {f"spin{k[0]}_{'analysis' if k[1] else 'synthesis'}_ms": round(v, 4) for k, v in sorted(avg.items())}
     kern["legendre_share_of_step"] = round(share, 4)
+    kern["other_stages_ms"] = {k: round(sum(v) / len(v), 4) for k, v in sorted(stages.items())}
     for k, v in sorted(avg.items()):
         fl = (8.0 if k[0] == 0 else 28.0) * ntriples(nside, lmax) * local_frac
         kern[f"spin{k[0]}_{'analysis' if k[1] else 'synthesis'}_tflops_nominal"] = round(fl / (v * 1e-3) / 1e12, 3)

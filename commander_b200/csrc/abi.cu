@@ -412,9 +412,13 @@ static void run_single(int type, int spin, double *const *alm, double *const *ma
     prof_begin(spin, 0, st);
     launch_legendre_synth(spin, G, A, alm, ph, st);
     prof_end(st);
+    prof_begin(100 + spin, 0, st);
     ringfft_synth(g, ncomp, L, ph, map, type == SHARP_WY, add, st);
+    prof_end(st);
   } else {
+    prof_begin(100 + spin, 1, st);
     ringfft_anal(g, ncomp, L, ph, map, type == SHARP_YtW, st);
+    prof_end(st);
     if (!add)
       for (int c = 0; c < ncomp; ++c)
         CMDR_CUDA_CHECK(cudaMemsetAsync(alm[c], 0, sizeof(double) * a->nalm * (a->real_packed ? 1 : 2), st));

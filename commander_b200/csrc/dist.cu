@@ -7,10 +7,16 @@
 // rank is whatever the caller's handles say (comm_mapinfo uses round-robin,
 // commander3/src/comm_map_mod.f90:197-261); it is discovered with NCCL all-gathers.
 //
-// The exchange is an NCCL all-to-all (grouped ncclSend/ncclRecv over NVLink/NVSwitch).
-// The Legendre kernels write their output directly in the per-destination block layout
-// ([owner][comp][m][ring pair]) and the fold kernel reads the received blocks in place,
-// so there is no separate pack/unpack pass on either side.
+// Default exchange: FUSED into the producing kernels.  Every rank owns two receive buffers
+// (synthesis side, analysis side) that all other ranks map through CUDA IPC; the synthesis
+// Legendre kernel stores each warp's phases straight into the ring owner's buffer and the analysis
+// Legendre kernel loads each warp's phases straight from the ring owner's buffer (coalesced
+// NVLink/NVSwitch peer accesses), so the m <-> ring transpose overlaps the math warp by warp and
+// there is no send buffer, no pack pass and no separate all-to-all.  Two 4-byte NCCL all-reduces per transform act as the cross-GPU
+// stream barriers (buffer free / buffer complete).
+// Fallback (CMDR_SHT_P2P=0, more than 8 ranks, or IPC mapping unavailable): an NCCL all-to-all
+// (grouped ncclSend/ncclRecv) between a send and a receive buffer in the same block layout
+// ([owner][comp][m][ring pair]); still no pack/unpack passes.
 #include <dlfcn.h>
 #include <nccl.h>
 
@@ -94,10 +100,19 @@ struct DistPlan {
   int *d_m2src = nullptr, *d_m2im = nullptr, *d_mlist = nullptr, *d_mlist_src = nullptr, *d_mlist_im = nullptr;
 };
 
+struct PeerBuf {                       // one receive buffer per rank, mapped by every rank
+  double *mine = nullptr;
+  size_t bytes = 0;
+  std::vector<double *> peer;          // [nranks], peer[rank] == mine
+};
+
 struct DistComm {
   ncclComm_t nccl = nullptr;
   int rank = 0, nranks = 1, device = 0;
   std::map<std::tuple<const sharp_geom_info *, const sharp_alm_info *>, DistPlan *> plans;
+  int p2p = -1;                        // -1 undecided, 0 NCCL all-to-all, 1 fused peer stores
+  PeerBuf pb[2];                       // [0] analysis side (written by unfold), [1] synthesis side
+  int *d_flag = nullptr;               // barrier token
 };
 
 static std::map<int, DistComm *> g_comms;
@@ -181,6 +196,81 @@ static const int *plan_mlim(DistPlan *P, int lmax, int spin) {
   return d;
 }
 
+// Cross-GPU stream barrier: work enqueued after it on any rank starts only after everything
+// enqueued before it on every rank has completed (kernel completion makes its peer stores
+// visible).
+static void stream_barrier(DistComm *C, cudaStream_t st) {
+  if (!C->d_flag) { CMDR_CUDA_CHECK(cudaMalloc(&C->d_flag, sizeof(int))); CMDR_CUDA_CHECK(cudaMemset(C->d_flag, 0, sizeof(int))); }
+  CMDR_NCCL_CHECK(nccl_api()->AllReduce(C->d_flag, C->d_flag, 1, ncclInt32, ncclMax, C->nccl, st));
+  count_launch(1);
+}
+
+static void close_peerbuf(DistComm *C, PeerBuf &B) {
+  for (int r = 0; r < (int)B.peer.size(); ++r)
+    if (r != C->rank && B.peer[r]) cudaIpcCloseMemHandle(B.peer[r]);
+  B.peer.clear();
+  if (B.mine) cudaFree(B.mine);
+  B.mine = nullptr; B.bytes = 0;
+}
+
+// Collective: (re)allocates this rank's receive buffer and maps everybody else's.  Sizes are
+// functions of the global maxima NML / NPL, so every rank grows at the same call.
+// Returns false (on all ranks) if any rank could not map a peer.
+static bool ensure_peerbuf(DistComm *C, int which, size_t bytes, cudaStream_t st) {
+  PeerBuf &B = C->pb[which];
+  if (B.bytes >= bytes) return true;
+  CMDR_CUDA_CHECK(cudaStreamSynchronize(st));
+  stream_barrier(C, st);                       // nobody still uses the old mapping
+  CMDR_CUDA_CHECK(cudaStreamSynchronize(st));
+  close_peerbuf(C, B);
+  size_t want = bytes + bytes / 16 + 256;
+  CMDR_CUDA_CHECK(cudaMalloc(&B.mine, want));
+  CMDR_CUDA_CHECK(cudaMemset(B.mine, 0, want));
+  B.bytes = want;
+  cudaIpcMemHandle_t h;
+  CMDR_CUDA_CHECK(cudaIpcGetMemHandle(&h, B.mine));
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  char *d_in = nullptr, *d_out = nullptr;
+  CMDR_CUDA_CHECK(cudaMalloc(&d_in, 64)); CMDR_CUDA_CHECK(cudaMalloc(&d_out, 64 * (size_t)C->nranks));
+  CMDR_CUDA_CHECK(cudaMemcpyAsync(d_in, &h, 64, cudaMemcpyHostToDevice, st));
+  CMDR_NCCL_CHECK(nccl_api()->AllGather(d_in, d_out, 64, ncclChar, C->nccl, st));
+  std::vector<cudaIpcMemHandle_t> all(C->nranks);
+  CMDR_CUDA_CHECK(cudaMemcpyAsync(all.data(), d_out, 64 * (size_t)C->nranks, cudaMemcpyDeviceToHost, st));
+  CMDR_CUDA_CHECK(cudaStreamSynchronize(st));
+  cudaFree(d_in); cudaFree(d_out);
+  B.peer.assign(C->nranks, nullptr);
+  int ok = 1;
+  for (int r = 0; r < C->nranks; ++r) {
+    if (r == C->rank) { B.peer[r] = B.mine; continue; }
+    void *ptr = nullptr;
+    cudaError_t e = cudaIpcOpenMemHandle(&ptr, all[r], cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) { cudaGetLastError(); ok = 0; break; }
+    B.peer[r] = static_cast<double *>(ptr);
+  }
+  // agree on the outcome
+  int *d_ok = nullptr;
+  CMDR_CUDA_CHECK(cudaMalloc(&d_ok, sizeof(int)));
+  CMDR_CUDA_CHECK(cudaMemcpyAsync(d_ok, &ok, sizeof(int), cudaMemcpyHostToDevice, st));
+  CMDR_NCCL_CHECK(nccl_api()->AllReduce(d_ok, d_ok, 1, ncclInt32, ncclMin, C->nccl, st));
+  CMDR_CUDA_CHECK(cudaMemcpyAsync(&ok, d_ok, sizeof(int), cudaMemcpyDeviceToHost, st));
+  CMDR_CUDA_CHECK(cudaStreamSynchronize(st));
+  cudaFree(d_ok);
+  if (!ok) {
+    if (C->rank == 0) fprintf(stderr, "cmdr_sht: CUDA IPC peer mapping unavailable, using the NCCL all-to-all exchange\n");
+    close_peerbuf(C, B);
+    return false;
+  }
+  return true;
+}
+
+static bool use_p2p(DistComm *C) {
+  if (C->p2p < 0) {
+    const char *e = getenv("CMDR_SHT_P2P");
+    C->p2p = (e && atoi(e) == 0) || C->nranks > CMDR_MAX_PEERS ? 0 : 1;
+  }
+  return C->p2p == 1;
+}
+
 // all-to-all of equal-sized blocks (in doubles)
 static void alltoall_blocks(DistComm *C, const double *send, double *recv, size_t block, cudaStream_t st) {
   CMDR_NCCL_CHECK(nccl_api()->GroupStart());
@@ -212,8 +302,6 @@ static void run_dist(DistComm *C, int type, const Part *parts, int nparts, int n
   ensure_alm_device(a);
   DistPlan *P = get_plan(C, g0, a, st);
   const size_t block = (size_t)ncomp_tot * P->NML * P->NPL * 4;   // doubles per peer block
-  double *bufA = static_cast<double *>(scratch_get("dist_phA", sizeof(double) * block * C->nranks));
-  double *bufB = static_cast<double *>(scratch_get("dist_phB", sizeof(double) * block * C->nranks));
   PhaseLayout L;
   L.NPL = P->NPL; L.NML = P->NML; L.ncomp_tot = ncomp_tot; L.mmax = P->mmax;
   L.m2src = P->d_m2src; L.m2im = P->d_m2im; L.nm_total = P->nm_total;
@@ -221,6 +309,75 @@ static void run_dist(DistComm *C, int type, const Part *parts, int nparts, int n
   LegGeom G;
   G.nslots = P->nslots; G.NPL = P->NPL; G.nowners = C->nranks; G.NML = P->NML; G.ncomp_tot = ncomp_tot;
   G.trig = P->d_trig;
+  // receive buffers are sized for 3 components so that T, QU and IQU calls share one mapping
+  const size_t cap = sizeof(double) * (size_t)3 * P->NML * P->NPL * 4 * C->nranks;
+  bool fused = use_p2p(C);
+  if (fused && !(ensure_peerbuf(C, 0, cap, st) && ensure_peerbuf(C, 1, cap, st))) { C->p2p = 0; fused = false; }
+
+  if (fused && synth) {
+    PeerBuf &B = C->pb[1];
+    G.npeer = C->nranks; G.src_rank = C->rank;
+    for (int r = 0; r < C->nranks; ++r) G.peer[r] = reinterpret_cast<double4 *>(B.peer[r]);
+    prof_begin(200, 0, st);
+    stream_barrier(C, st);                       // every rank has finished reading its buffer
+    prof_end(st);
+    for (int i = 0; i < nparts; ++i) {
+      const Part &p = parts[i];
+      LegAlm A = make_legalm(a, p.spin);
+      G.comp0 = p.comp0; G.mlim = plan_mlim(P, a->lmax, p.spin);
+      prof_begin(p.spin, 0, st);
+      launch_legendre_synth(p.spin, G, A, p.alm, reinterpret_cast<double4 *>(B.mine), st);
+      prof_end(st);
+    }
+    prof_begin(201, 0, st);
+    stream_barrier(C, st);                       // every rank's phases have landed
+    prof_end(st);
+    for (int i = 0; i < nparts; ++i) {
+      const Part &p = parts[i];
+      L.comp0 = p.comp0;
+      if (p.g->npairs == 0) continue;
+      prof_begin(100 + p.spin, 0, st);
+      ringfft_synth(p.g, p.ncomp, L, reinterpret_cast<double4 *>(B.mine), p.map, type == SHARP_WY, add, st);
+      prof_end(st);
+    }
+    return;
+  }
+  if (fused) {
+    // analysis: FFT + unfold fill this rank's buffer ([m owner][comp][m][pair]); after the barrier
+    // every rank's Legendre kernel loads its block from the ring owners' buffers over NVLink
+    PeerBuf &B = C->pb[0];
+    G.npeer = C->nranks; G.src_rank = C->rank;
+    for (int r = 0; r < C->nranks; ++r) G.peer[r] = reinterpret_cast<double4 *>(B.peer[r]);
+    prof_begin(200, 1, st);
+    stream_barrier(C, st);                       // every rank has finished reading my buffer
+    prof_end(st);
+    for (int i = 0; i < nparts; ++i) {
+      const Part &p = parts[i];
+      L.comp0 = p.comp0;
+      if (p.g->npairs == 0) continue;
+      prof_begin(100 + p.spin, 1, st);
+      ringfft_anal(p.g, p.ncomp, L, reinterpret_cast<double4 *>(B.mine), p.map, type == SHARP_YtW, st);
+      prof_end(st);
+    }
+    prof_begin(201, 1, st);
+    stream_barrier(C, st);                       // every rank's phases are complete
+    prof_end(st);
+    for (int i = 0; i < nparts; ++i) {
+      const Part &p = parts[i];
+      LegAlm A = make_legalm(a, p.spin);
+      G.comp0 = p.comp0; G.mlim = plan_mlim(P, a->lmax, p.spin);
+      const size_t nd = (size_t)a->nalm * (a->real_packed ? 1 : 2);
+      if (!add && nd)
+        for (int c = 0; c < p.ncomp; ++c) CMDR_CUDA_CHECK(cudaMemsetAsync(p.alm[c], 0, sizeof(double) * nd, st));
+      prof_begin(p.spin, 1, st);
+      launch_legendre_anal(p.spin, G, A, p.alm, reinterpret_cast<const double4 *>(B.mine), st);
+      prof_end(st);
+    }
+    return;
+  }
+
+  double *bufA = static_cast<double *>(scratch_get("dist_phA", sizeof(double) * block * C->nranks));
+  double *bufB = static_cast<double *>(scratch_get("dist_phB", sizeof(double) * block * C->nranks));
   if (synth) {
     // padded m rows are never written by the kernels: keep them defined
     if (a->nm < P->NML) CMDR_CUDA_CHECK(cudaMemsetAsync(bufA, 0, sizeof(double) * block * C->nranks, st));
@@ -232,12 +389,16 @@ static void run_dist(DistComm *C, int type, const Part *parts, int nparts, int n
       launch_legendre_synth(p.spin, G, A, p.alm, reinterpret_cast<double4 *>(bufA), st);
       prof_end(st);
     }
+    prof_begin(200, 0, st);
     alltoall_blocks(C, bufA, bufB, block, st);
+    prof_end(st);
     for (int i = 0; i < nparts; ++i) {
       const Part &p = parts[i];
       L.comp0 = p.comp0;
       if (p.g->npairs == 0) continue;
+      prof_begin(100 + p.spin, 0, st);
       ringfft_synth(p.g, p.ncomp, L, reinterpret_cast<double4 *>(bufB), p.map, type == SHARP_WY, add, st);
+      prof_end(st);
     }
   } else {
     CMDR_CUDA_CHECK(cudaMemsetAsync(bufA, 0, sizeof(double) * block * C->nranks, st));
@@ -245,9 +406,13 @@ static void run_dist(DistComm *C, int type, const Part *parts, int nparts, int n
       const Part &p = parts[i];
       L.comp0 = p.comp0;
       if (p.g->npairs == 0) continue;
+      prof_begin(100 + p.spin, 1, st);
       ringfft_anal(p.g, p.ncomp, L, reinterpret_cast<double4 *>(bufA), p.map, type == SHARP_YtW, st);
+      prof_end(st);
     }
+    prof_begin(200, 1, st);
     alltoall_blocks(C, bufA, bufB, block, st);
+    prof_end(st);
     for (int i = 0; i < nparts; ++i) {
       const Part &p = parts[i];
       LegAlm A = make_legalm(a, p.spin);
@@ -322,6 +487,8 @@ void cmdr_sht_comm_destroy(int comm) {
     for (auto &m : P->d_mlim) cudaFree(m.second);
     delete P;
   }
+  close_peerbuf(C, C->pb[0]); close_peerbuf(C, C->pb[1]);
+  if (C->d_flag) cudaFree(C->d_flag);
   if (C->nccl) nccl_api()->CommDestroy(C->nccl);
   g_comms.erase(comm);
   delete C;

@@ -10,6 +10,8 @@
 
 namespace cmdr {
 
+constexpr int CMDR_MAX_PEERS = 8;
+
 void count_launch(int n = 1);
 
 // Geometry as the Legendre stage sees it: `nslots` ring-pair slots laid out as
@@ -21,6 +23,12 @@ struct LegGeom {
   int ncomp_tot = 1, comp0 = 0;   // components in the phase buffer / first one written here
   const double *trig = nullptr;   // nslots*4
   const int *mlim = nullptr;      // nslots
+  // Fused exchange (multi-GPU): when npeer > 0, peer[o] is the phase buffer of ring owner o
+  // (peer-mapped memory over NVLink) and `src_rank` the block of this rank in it.  Synthesis
+  // stores the phases of owner o's slots straight into peer[o]; analysis loads them from there.
+  // No send buffer and no all-to-all in either direction.
+  int npeer = 0, src_rank = 0;
+  double4 *peer[CMDR_MAX_PEERS] = {};
 };
 
 // alm side of the Legendre stage (local m's of this rank)

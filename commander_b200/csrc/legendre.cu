@@ -45,6 +45,8 @@ struct KParams {
   const int *mlim;
   double *alm0, *alm1;
   double4 *ph;
+  int src_rank;                      // fused exchange: block of this rank in the ring owners' buffers (-1: local buffer, block = owner)
+  double4 *peer[CMDR_MAX_PEERS];     // phase buffer of each ring owner (all = ph without the fused exchange)
 };
 
 struct __align__(16) TileS0 { double A, ar, ai, pad; };
@@ -53,9 +55,19 @@ struct __align__(16) TileA0 { double A, g; };
 struct __align__(16) TileA2 { double A, C, g, pad; };
 static_assert(TL == NT, "tile staging assumes one entry per thread");
 
-__device__ __forceinline__ size_t ph_index(const KParams &p, int comp, int im, int slot) {
+// analysis input: blocks indexed by the rank that owns the rings in the local buffer; with the
+// fused exchange the block of THIS rank in the ring owner's buffer, read over NVLink
+__device__ __forceinline__ const double4 *ph_in(const KParams &p, int comp, int im, int slot) {
   int owner = slot / p.NPL, local = slot - owner * p.NPL;
-  return ((size_t)(owner * p.ncomp_tot + p.comp0 + comp) * p.NML + im) * p.NPL + local;
+  const int blk = p.src_rank >= 0 ? p.src_rank : owner;
+  return p.peer[owner] + ((size_t)(blk * p.ncomp_tot + p.comp0 + comp) * p.NML + im) * p.NPL + local;
+}
+// synthesis output: the ring owner's buffer (its own on one GPU, peer-mapped over NVLink
+// otherwise), block of the writing rank
+__device__ __forceinline__ double4 *ph_out(const KParams &p, int comp, int im, int slot) {
+  int owner = slot / p.NPL, local = slot - owner * p.NPL;
+  const int blk = p.src_rank >= 0 ? p.src_rank : owner;
+  return p.peer[owner] + ((size_t)(blk * p.ncomp_tot + p.comp0 + comp) * p.NML + im) * p.NPL + local;
 }
 
 // ------------------------------------------------------------------------------------
@@ -113,7 +125,7 @@ __global__ void __launch_bounds__(NT) synth0_kernel(KParams p) {
   if (!__syncthreads_or(any)) {   // whole chunk beyond the m cut-off: phases are zero
 #pragma unroll
     for (int r = 0; r < R; ++r)
-      if (slot[r] < p.nslots) p.ph[ph_index(p, 0, im, slot[r])] = make_double4(0, 0, 0, 0);
+      if (slot[r] < p.nslots) *ph_out(p, 0, im, slot[r]) = make_double4(0, 0, 0, 0);
     return;
   }
   const double *coef = p.coef + p.cofs[im];
@@ -169,7 +181,7 @@ __global__ void __launch_bounds__(NT) synth0_kernel(KParams p) {
 #pragma unroll
   for (int r = 0; r < R; ++r)
     if (slot[r] < p.nslots)
-      p.ph[ph_index(p, 0, im, slot[r])] =
+      *ph_out(p, 0, im, slot[r]) =
           make_double4(per[r] + por[r], pei[r] + poi[r], per[r] - por[r], pei[r] - poi[r]);
 }
 
@@ -245,8 +257,8 @@ __global__ void __launch_bounds__(NT) synth2_kernel(KParams p) {
 #pragma unroll
     for (int r = 0; r < R; ++r)
       if (slot[r] < p.nslots) {
-        p.ph[ph_index(p, 0, im, slot[r])] = make_double4(0, 0, 0, 0);
-        p.ph[ph_index(p, 1, im, slot[r])] = make_double4(0, 0, 0, 0);
+        *ph_out(p, 0, im, slot[r]) = make_double4(0, 0, 0, 0);
+        *ph_out(p, 1, im, slot[r]) = make_double4(0, 0, 0, 0);
       }
     return;
   }
@@ -313,8 +325,8 @@ __global__ void __launch_bounds__(NT) synth2_kernel(KParams p) {
       u.x = 0.5 * (a[r][1] - a[r][3]);  u.y = -0.5 * (a[r][0] - a[r][2]);
       q.z = sg0 * (a[r][4] + a[r][6]);  q.w = sg0 * (a[r][5] + a[r][7]);
       u.z = sg0 * (a[r][5] - a[r][7]);  u.w = -sg0 * (a[r][4] - a[r][6]);
-      p.ph[ph_index(p, 0, im, slot[r])] = q;
-      p.ph[ph_index(p, 1, im, slot[r])] = u;
+      *ph_out(p, 0, im, slot[r]) = q;
+      *ph_out(p, 1, im, slot[r]) = u;
     }
 }
 
@@ -513,7 +525,7 @@ __global__ void __launch_bounds__(32, MINB) anal0_kernel(KParams p) {
       RingTrig g{tg.x, tg.y, tg.z, tg.w};
       x[r] = g.cth;
       start_spin0(m, K, g, cur[r], k[r]);
-      double4 q = p.ph[ph_index(p, 0, im, slot)];
+      double4 q = *ph_in(p, 0, im, slot);
       const double re_s = q.x + q.z, im_s = q.y + q.w, re_d = q.x - q.z, im_d = q.y - q.w;
       sr[r] = swapRI ? im_s : re_s; si[r] = swapRI ? re_s : im_s;
       dr[r] = swapRI ? im_d : re_d; di[r] = swapRI ? re_d : im_d;
@@ -722,7 +734,7 @@ __global__ void __launch_bounds__(32, MINB) anal2_kernel(KParams p) {
       double P0, M0;
       start_spin2(m, K, g, P0, M0, k[r]);
       Pa[r] = swapPM ? M0 : P0; Pb[r] = swapPM ? P0 : M0;
-      double4 q = p.ph[ph_index(p, 0, im, slot)], u = p.ph[ph_index(p, 1, im, slot)];
+      double4 q = *ph_in(p, 0, im, slot), u = *ph_in(p, 1, im, slot);
       double z[8];
       z[0] = q.x - u.y; z[1] = q.y + u.x;            // zpN = qQ + i qU
       z[2] = q.x + u.y; z[3] = q.y - u.x;            // zmN = qQ - i qU
@@ -838,6 +850,8 @@ static KParams make_params(const LegGeom &g, const LegAlm &a, double *alm0, doub
   p.mval = a.mval; p.mvstart = a.mvstart; p.coef = a.coef; p.cofs = a.cofs; p.Kstart = a.Kstart;
   p.trig = g.trig; p.mlim = g.mlim;
   p.alm0 = alm0; p.alm1 = alm1; p.ph = ph;
+  p.src_rank = g.npeer ? g.src_rank : -1;
+  for (int i = 0; i < CMDR_MAX_PEERS; ++i) p.peer[i] = g.npeer ? g.peer[i] : ph;
   return p;
 }
 
