@@ -20,6 +20,7 @@
 #include <dlfcn.h>
 #include <nccl.h>
 
+#include <algorithm>
 #include <cstring>
 #include <map>
 #include <tuple>
@@ -93,9 +94,11 @@ static T *upload_v(const std::vector<T> &v) {
 struct DistPlan {
   int NPL = 0, NML = 0, mmax = -1, nm_total = 0;
   int nslots = 0;
-  double *d_trig = nullptr;                 // [nranks*NPL][4]
-  std::map<int, int *> d_mlim;              // per spin: [nranks*NPL]
-  std::vector<double> h_sth, h_cth;         // per slot (0 for empty)
+  // Legendre work order: all ranks' ring pairs sorted by colatitude, empty (padding) slots last
+  double *d_trig = nullptr;                 // [nranks*NPL][4], work order
+  int *d_wslot = nullptr;                   // work index -> storage slot owner*NPL + local
+  std::map<int, int *> d_mlim;              // per spin: [nranks*NPL], work order
+  std::vector<double> h_sth, h_cth;         // per work index (0 for empty)
   std::vector<int> h_valid;
   int *d_m2src = nullptr, *d_m2im = nullptr, *d_mlist = nullptr, *d_mlist_src = nullptr, *d_mlist_im = nullptr;
 };
@@ -154,18 +157,27 @@ static DistPlan *get_plan(DistComm *C, sharp_geom_info *g, sharp_alm_info *a, cu
   P->NML = NML; P->NPL = NPL; P->nslots = R * NPL;
   std::vector<int> all_m = allgather_ints(C, a->mval, NML, st);
   std::vector<int> all_north = allgather_ints(C, g->north, NPL, st);
-  // global slot geometry
+  // global slot geometry in work order
+  std::vector<std::pair<int, int>> order;   // (north ring, storage slot)
+  for (int r = 0; r < R; ++r)
+    for (int j = 0; j < sz[4 * r + 1]; ++j) order.emplace_back(all_north[(size_t)r * NPL + j], r * NPL + j);
+  std::sort(order.begin(), order.end());
+  std::vector<int> wslot(P->nslots, 0);
+  std::vector<char> used(P->nslots, 0);
   std::vector<double> trig(4 * (size_t)P->nslots, 0.0);
   P->h_sth.assign(P->nslots, 0.0); P->h_cth.assign(P->nslots, 0.0); P->h_valid.assign(P->nslots, 0);
-  for (int r = 0; r < R; ++r)
-    for (int j = 0; j < sz[4 * r + 1]; ++j) {
-      int s = r * NPL + j;
-      long double c, sn, sh, ch;
-      ring_trig_ld(g->nside, all_north[(size_t)r * NPL + j], c, sn, sh, ch);
-      trig[4 * s] = (double)c; trig[4 * s + 1] = (double)sn; trig[4 * s + 2] = (double)sh; trig[4 * s + 3] = (double)ch;
-      P->h_sth[s] = (double)sn; P->h_cth[s] = (double)c; P->h_valid[s] = 1;
-    }
+  int w = 0;
+  for (auto &o : order) {
+    long double c, sn, sh, ch;
+    ring_trig_ld(g->nside, o.first, c, sn, sh, ch);
+    trig[4 * w] = (double)c; trig[4 * w + 1] = (double)sn; trig[4 * w + 2] = (double)sh; trig[4 * w + 3] = (double)ch;
+    P->h_sth[w] = (double)sn; P->h_cth[w] = (double)c; P->h_valid[w] = 1;
+    wslot[w] = o.second; used[o.second] = 1;
+    ++w;
+  }
+  for (int s2 = 0; s2 < P->nslots; ++s2) if (!used[s2]) wslot[w++] = s2;   // padding slots: zero-filled, never read
   P->d_trig = upload_v(trig);
+  P->d_wslot = upload_v(wslot);
   // global m tables
   int mmax = -1;
   for (int r = 0; r < R; ++r) for (int i = 0; i < sz[4 * r]; ++i) mmax = std::max(mmax, all_m[(size_t)r * NML + i]);
@@ -308,7 +320,7 @@ static void run_dist(DistComm *C, int type, const Part *parts, int nparts, int n
   L.mlist = P->d_mlist; L.mlist_src = P->d_mlist_src; L.mlist_im = P->d_mlist_im;
   LegGeom G;
   G.nslots = P->nslots; G.NPL = P->NPL; G.nowners = C->nranks; G.NML = P->NML; G.ncomp_tot = ncomp_tot;
-  G.trig = P->d_trig;
+  G.trig = P->d_trig; G.wslot = P->d_wslot;
   // receive buffers are sized for 3 components so that T, QU and IQU calls share one mapping
   const size_t cap = sizeof(double) * (size_t)3 * P->NML * P->NPL * 4 * C->nranks;
   bool fused = use_p2p(C);
@@ -482,7 +494,7 @@ void cmdr_sht_comm_destroy(int comm) {
   if (!C) return;
   for (auto &kv : C->plans) {
     DistPlan *P = kv.second;
-    cudaFree(P->d_trig); cudaFree(P->d_m2src); cudaFree(P->d_m2im); cudaFree(P->d_mlist);
+    cudaFree(P->d_trig); cudaFree(P->d_wslot); cudaFree(P->d_m2src); cudaFree(P->d_m2im); cudaFree(P->d_mlist);
     cudaFree(P->d_mlist_src); cudaFree(P->d_mlist_im);
     for (auto &m : P->d_mlim) cudaFree(m.second);
     delete P;

@@ -14,8 +14,11 @@ constexpr int CMDR_MAX_PEERS = 8;
 
 void count_launch(int n = 1);
 
-// Geometry as the Legendre stage sees it: `nslots` ring-pair slots laid out as
-// [owner][NPL]; slot -> trig (cth,sth,sh,ch) and per-slot m cut-off (-1 = empty slot).
+// Geometry as the Legendre stage sees it: `nslots` ring-pair slots stored as [owner][NPL].
+// The kernels walk WORK indices; `trig` (cth,sth,sh,ch) and the per-ring m cut-off `mlim`
+// (-1 = empty slot) are in work order and `wslot` maps a work index to its storage slot.  On
+// several GPUs the work order is by colatitude, so that the 32 R rings of a warp are neighbours
+// on the sphere whoever owns them (identity on one GPU, where storage is already sorted).
 struct LegGeom {
   int nslots = 0, NPL = 0, nowners = 1;
   int slot_begin = 0, slot_end = -1;   // sub-range of slots to process (-1: all)
@@ -23,6 +26,7 @@ struct LegGeom {
   int ncomp_tot = 1, comp0 = 0;   // components in the phase buffer / first one written here
   const double *trig = nullptr;   // nslots*4
   const int *mlim = nullptr;      // nslots
+  const int *wslot = nullptr;     // nslots, or nullptr for the identity
   // Fused exchange (multi-GPU): when npeer > 0, peer[o] is the phase buffer of ring owner o
   // (peer-mapped memory over NVLink) and `src_rank` the block of this rank in it.  Synthesis
   // stores the phases of owner o's slots straight into peer[o]; analysis loads them from there.

@@ -43,6 +43,7 @@ struct KParams {
   const double *Kstart;
   const double *trig;
   const int *mlim;
+  const int *wslot;                  // work index -> storage slot (nullptr: identity)
   double *alm0, *alm1;
   double4 *ph;
   int src_rank;                      // fused exchange: block of this rank in the ring owners' buffers (-1: local buffer, block = owner)
@@ -57,14 +58,16 @@ static_assert(TL == NT, "tile staging assumes one entry per thread");
 
 // analysis input: blocks indexed by the rank that owns the rings in the local buffer; with the
 // fused exchange the block of THIS rank in the ring owner's buffer, read over NVLink
-__device__ __forceinline__ const double4 *ph_in(const KParams &p, int comp, int im, int slot) {
+__device__ __forceinline__ const double4 *ph_in(const KParams &p, int comp, int im, int work) {
+  const int slot = p.wslot ? p.wslot[work] : work;
   int owner = slot / p.NPL, local = slot - owner * p.NPL;
   const int blk = p.src_rank >= 0 ? p.src_rank : owner;
   return p.peer[owner] + ((size_t)(blk * p.ncomp_tot + p.comp0 + comp) * p.NML + im) * p.NPL + local;
 }
 // synthesis output: the ring owner's buffer (its own on one GPU, peer-mapped over NVLink
 // otherwise), block of the writing rank
-__device__ __forceinline__ double4 *ph_out(const KParams &p, int comp, int im, int slot) {
+__device__ __forceinline__ double4 *ph_out(const KParams &p, int comp, int im, int work) {
+  const int slot = p.wslot ? p.wslot[work] : work;
   int owner = slot / p.NPL, local = slot - owner * p.NPL;
   const int blk = p.src_rank >= 0 ? p.src_rank : owner;
   return p.peer[owner] + ((size_t)(blk * p.ncomp_tot + p.comp0 + comp) * p.NML + im) * p.NPL + local;
@@ -848,7 +851,7 @@ static KParams make_params(const LegGeom &g, const LegAlm &a, double *alm0, doub
   p.lmax = a.lmax; p.nm = a.nm; p.real_packed = a.real_packed;
   p.slot_begin = g.slot_begin; p.nslots = g.slot_end >= 0 ? g.slot_end : g.nslots; p.NPL = g.NPL; p.NML = g.NML; p.ncomp_tot = g.ncomp_tot; p.comp0 = g.comp0;
   p.mval = a.mval; p.mvstart = a.mvstart; p.coef = a.coef; p.cofs = a.cofs; p.Kstart = a.Kstart;
-  p.trig = g.trig; p.mlim = g.mlim;
+  p.trig = g.trig; p.mlim = g.mlim; p.wslot = g.wslot;
   p.alm0 = alm0; p.alm1 = alm1; p.ph = ph;
   p.src_rank = g.npeer ? g.src_rank : -1;
   for (int i = 0; i < CMDR_MAX_PEERS; ++i) p.peer[i] = g.npeer ? g.peer[i] : ph;
