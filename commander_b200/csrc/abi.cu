@@ -141,7 +141,9 @@ void ring_trig_ld(int nside, int north, long double &cth, long double &sth, long
   ch = sqrtl(1.0L - 0.5L * omc);
 }
 
-static int next_pow2(int v) { int m = 1; while (m < v) m <<= 1; return m; }
+// Bluestein work length of a polar-cap ring with nph points: a power of two >= 2 nph - 1, at
+// least 1024 so that the shortest rings share one batched plan instead of a dozen tiny launches
+static int blue_len(int nph) { int m = 1024; while (m < 2 * nph - 1) m <<= 1; return m; }
 
 
 // FFT regions: polar-cap pairs grouped by Bluestein work length, then the belt
@@ -151,9 +153,9 @@ static void build_regions(sharp_geom_info *g) {
   long long base = 0;
   int p = 0;
   while (p < g->npairs && g->north[p] < nside) {
-    int M = next_pow2(2 * g->nph[p] - 1);
+    int M = blue_len(g->nph[p]);
     FftRegion R; R.first = p; R.len = M; R.bluestein = true; R.base = base;
-    while (p < g->npairs && g->north[p] < nside && next_pow2(2 * g->nph[p] - 1) == M) ++p;
+    while (p < g->npairs && g->north[p] < nside && blue_len(g->nph[p]) == M) ++p;
     R.np = p - R.first;
     base += (long long)R.np * R.len;
     g->regions.push_back(R);

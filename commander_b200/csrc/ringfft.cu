@@ -324,6 +324,9 @@ void ringfft_synth(sharp_geom_info *g, int ncomp, const PhaseLayout &L, const do
   p.ph = const_cast<double4 *>(ph);
   p.map0 = map[0]; p.map1 = ncomp > 1 ? map[1] : nullptr; p.map2 = ncomp > 2 ? map[2] : nullptr;
   p.weighted = weighted; p.add = add;
+  // all pairs that need the generic (aliasing) fold go in ONE launch: the blocks of short rings are
+  // latency bound (long m chains per bin) and must overlap the big ones instead of queueing
+  int gen_first = -1, gen_np = 0;
   for (size_t r = 0; r < g->regions.size(); ++r) {
     const FftRegion &R = g->regions[r];
     if (R.np == 0) continue;
@@ -331,9 +334,17 @@ void ringfft_synth(sharp_geom_info *g, int ncomp, const PhaseLayout &L, const do
       CMDR_CUDA_CHECK(cudaMemsetAsync(buf + (size_t)ncomp * R.base, 0, sizeof(double2) * (size_t)ncomp * R.np * R.len, st));
       dim3 grid((R.np + 31) / 32, (L.nm_total + 31) / 32, ncomp);
       fold_transpose_kernel<<<grid, 256, 0, st>>>(p, R.first, R.np, R.len);
-    } else {
+      count_launch();
+    } else if (gen_first < 0 || R.first == gen_first + gen_np) {
+      if (gen_first < 0) gen_first = R.first;
+      gen_np += R.np;
+    } else {                                             // non-contiguous (not produced by build_regions)
       fold_kernel<<<dim3(R.np, ncomp), 256, 0, st>>>(p, R.first);
+      count_launch();
     }
+  }
+  if (gen_np > 0) {
+    fold_kernel<<<dim3(gen_np, ncomp), 256, 0, st>>>(p, gen_first);
     count_launch();
   }
   run_ffts(g, ncomp, buf, CUFFT_INVERSE, p, st);
