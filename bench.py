@@ -36,6 +36,30 @@ def ntriples(nside, lmax):
     return (lmax + 1) * (lmax + 2) / 2 * 2 * nside
 
 
+def executed_fraction(nside, lmax, spin, ms):
+    """Fraction of the nominal (l, m, ring pair) triples the kernels actually visit: rings beyond the
+    per-ring m cut-off (same formula as commander_b200/csrc/legendre_core.cuh mlim_for_ring) are
+    skipped.  The underflow region (ring not yet accumulating) still runs the recurrence and is
+    counted as visited."""
+    import numpy as np
+    i = np.arange(1, 2 * nside + 1, dtype=np.float64)
+    z = np.where(i < nside, 1.0 - i * i / (3.0 * nside * nside), (2.0 * nside - i) * 2.0 / (3.0 * nside))
+    sth, cth = np.sqrt(np.maximum(1.0 - z * z, 0.0)), z
+    ofs = max(100.0, 0.01 * lmax)
+    b = -2.0 * spin * np.abs(cth)
+    t1 = lmax * sth + ofs
+    c = spin * spin - t1 * t1
+    discr = b * b - 4 * c
+    mlim = np.where(discr <= 0, lmax, np.minimum((-b + np.sqrt(np.maximum(discr, 0))) / 2.0, lmax) + 0.5).astype(np.int64)
+    wpair = np.ones_like(i); wpair[-1] = 0.5          # the equator ring has no mirror
+    ms = np.asarray(ms, dtype=np.int64)
+    l0 = np.maximum(ms, spin)
+    nl = np.maximum(lmax + 1 - l0, 0).astype(np.float64)
+    visited = sum(float(nl[k]) * float(wpair[mlim >= ms[k]].sum()) for k in range(len(ms)))
+    nominal = float(sum(lmax + 1 - m for m in ms)) * float(wpair.sum())
+    return visited / nominal
+
+
 def workload(args):
     return {"workload": f"comm_map Y+YtW pair, IQU, nside={args.nside} lmax={args.lmax}, synthetic Gaussian alm",
             "nside": args.nside, "lmax": args.lmax, "nmaps": 3,
@@ -83,6 +107,18 @@ def cpu_pair_sample(nside, lmax, stride, nthreads=0):
             "threads": nthreads, "simd": S.lib().variant}
 
 
+def cpu_pick_stride(nside, lmax, budget_s=20.0):
+    """Chooses the m stride of the CPU sample so that it costs about `budget_s` seconds on this
+    box (a 1-core box and a 64-core box differ by two orders of magnitude): a stride-64 probe
+    measures the rate first."""
+    probe = cpu_pair_sample(nside, lmax, 64)
+    est_full = probe["seconds_full_est"]
+    stride = 1
+    while est_full / stride > budget_s and stride < 64:
+        stride *= 2
+    return stride
+
+
 def cpu_sample_text(r, stride):
     if stride == 1:
         return f"the complete workload, one pair, {r['wall']:.1f} s wall (Legendre {r['t_leg']:.1f} s, FFT {r['t_fft']:.1f} s)"
@@ -96,7 +132,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    stride = args.cpu_stride if args.cpu_stride > 0 else 8
+    stride = args.cpu_stride if args.cpu_stride > 0 else cpu_pick_stride(args.nside, args.lmax, 12.0)
     ests = []
     r = None
     for i in range(args.warmup + args.steps):
@@ -266,6 +302,7 @@ def run_ours(args):
 
     # ---- roofline of the dominant kernel (spin-2 Legendre), FP64 pipe
     fp64_peak = sharp.measure_fp64_tflops(4096, 5)
+    fp64_3op = sharp.measure_fp64_tflops_3op(4096, 3)
     per, stages = {}, {}
     for spin, direction, msv in leg:
         if spin >= 100:     # 100+spin: ring-FFT stage, 200/201: exchange barriers or all-to-all
@@ -279,18 +316,38 @@ def run_ours(args):
     flops2 = 28.0 * ntriples(nside, lmax) * local_frac   # nominal flops of one spin-2 launch on this rank
     dom = max(((k, v) for k, v in avg.items() if k[0] == 2), key=lambda kv: kv[1], default=((2, 1), float("nan")))
     achieved = flops2 / (dom[1] * 1e-3) / 1e12
+    exe = {0: executed_fraction(nside, lmax, 0, info.ms), 2: executed_fraction(nside, lmax, 2, info.ms)}
+    # FP64-pipe instructions the kernel really issues per visited triple: 4 (spin 0) / 12 (spin 2) DFMA
+    achieved_exec = 2.0 * 12.0 * ntriples(nside, lmax) * local_frac * exe[2] / (dom[1] * 1e-3) / 1e12
     kern = {f"spin{k[0]}_{'analysis' if k[1] else 'synthesis'}_ms": round(v, 4) for k, v in sorted(avg.items())}
     kern["legendre_share_of_step"] = round(share, 4)
     kern["other_stages_ms"] = {k: round(sum(v) / len(v), 4) for k, v in sorted(stages.items())}
     for k, v in sorted(avg.items()):
         fl = (8.0 if k[0] == 0 else 28.0) * ntriples(nside, lmax) * local_frac
         kern[f"spin{k[0]}_{'analysis' if k[1] else 'synthesis'}_tflops_nominal"] = round(fl / (v * 1e-3) / 1e12, 3)
+        fe = 2.0 * (4.0 if k[0] == 0 else 12.0) * ntriples(nside, lmax) * local_frac * exe[k[0]]
+        kern[f"spin{k[0]}_{'analysis' if k[1] else 'synthesis'}_tflops_executed"] = round(fe / (v * 1e-3) / 1e12, 3)
+    traffic = None
+    try:   # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from the committed ncu --set full capture
+        prof = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_summary.json")))
+        key = "anal2_kernel" if dom[0][1] else "synth2_kernel"
+        if world == 1 and nside == 2048 and lmax == 4000:
+            traffic = prof[key]["dram_bytes_per_launch"]
+    except (OSError, KeyError, ValueError):
+        pass
     roofline = {"bound": "fp64", "kernel": f"spin-2 Legendre {'analysis (anal2_kernel)' if dom[0][1] else 'synthesis (synth2_kernel)'}",
                 "achieved": round(achieved, 3), "peak": round(fp64_peak, 3), "unit": "TFLOP/s",
-                "frac": round(achieved / fp64_peak, 4), "traffic": None,
-                "peak_source": "measured live: cmdr_sht_measure_fp64_tflops DFMA probe (MEASURED_PEAKS.json has no FP64 entry)",
-                "flop_convention": "nominal 28 flops per (l,m,ring pair) for spin 2, 8 for spin 0 (SURVEY 8d); no work "
-                                   "subtracted for the m cut-off",
+                "frac": round(achieved / fp64_peak, 4), "traffic": traffic,
+                "peak_source": "measured live: cmdr_sht_measure_fp64_tflops, DFMA probe with two vector-register operands "
+                               "(MEASURED_PEAKS.json has no FP64 entry; nominal 148 SM x 64 FMA/clk x 2 x 1.965 GHz = 37.2)",
+                "flop_convention": "achieved = nominal 28 flops per (l,m,ring pair) for spin 2 (8 for spin 0; SURVEY 8d), no work "
+                                   "subtracted for the m cut-off, divided by the kernel's mean launch time (CUDA events on its stream)",
+                "achieved_executed": round(achieved_exec, 3), "frac_executed": round(achieved_exec / fp64_peak, 4),
+                "executed_convention": "DFMA instructions really issued: 12 per visited (l,m,ring pair) for spin 2 (4 for spin 0) x 2 flops; "
+                                       f"visited = {exe[2]:.3f} of the nominal triples (rings beyond the per-ring m cut-off are skipped)",
+                "peak_3operand": round(fp64_3op, 3),
+                "peak_3operand_note": "DFMA with three distinct vector-register operands (no operand-reuse-cache hit): the register file "
+                                      "feeds one 64-bit operand per cycle per scheduler, so such a DFMA issues every 3 cycles instead of 2",
                 "kernels": kern}
     peaks = {}
     try:
@@ -306,7 +363,7 @@ def run_ours(args):
     if rank == 0:
         cpu = None
         if not args.no_cpu_baseline and world == 1:   # contract: rank 0 at N=1 only
-            st = args.cpu_stride if args.cpu_stride > 0 else 1
+            st = args.cpu_stride if args.cpu_stride > 0 else cpu_pick_stride(nside, lmax, 20.0)
             r = cpu_pair_sample(nside, lmax, st)
             cpu = {"value": 1.0 / r["seconds_full_est"], "unit": UNIT, "cores": r["threads"], "kind": "port",
                    "simd": r["simd"], "sample": cpu_sample_text(r, st)}
@@ -372,7 +429,7 @@ def main():
     ap.add_argument("--nside", type=int, default=2048)
     ap.add_argument("--lmax", type=int, default=4000)
     ap.add_argument("--cpu-stride", type=int, default=0,
-                    help="CPU sample: every stride-th m (0: full workload for cpu_baseline, 8 for --impl reference)")
+                    help="CPU sample: every stride-th m (0: chosen so that the sample costs ~10-20 s of CPU time on this box)")
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-cg", action="store_true", help="skip the secondary CG iters/s measurement")

@@ -36,7 +36,7 @@ ABI_SYMBOLS = [
     "cmdr_sht_comm_register", "cmdr_sht_comm_destroy", "cmdr_sht_execute_dist",
     "cmdr_sht_execute_iqu_dist", "cmdr_sht_allreduce_sum", "cmdr_sht_launch_count",
     "cmdr_sht_set_profiling", "cmdr_sht_last_legendre_ms", "cmdr_sht_nominal_flops",
-    "cmdr_sht_release_caches", "cmdr_sht_measure_fp64_tflops",
+    "cmdr_sht_release_caches", "cmdr_sht_measure_fp64_tflops", "cmdr_sht_measure_fp64_tflops_3op",
 ]
 
 
@@ -80,6 +80,8 @@ def lib() -> C.CDLL:
     L.cmdr_sht_nominal_flops.restype = C.c_ulonglong
     L.cmdr_sht_measure_fp64_tflops.argtypes = [ci, ci]
     L.cmdr_sht_measure_fp64_tflops.restype = C.c_double
+    L.cmdr_sht_measure_fp64_tflops_3op.argtypes = [ci, ci]
+    L.cmdr_sht_measure_fp64_tflops_3op.restype = C.c_double
     _lib = L
     return L
 
