@@ -87,6 +87,14 @@ void ensure_coef(sharp_alm_info *a, int spin) {
   build_coef_table(a->lmax, spin, a->mval, tab, ofs);
   c.tab = upload(tab);
   c.ofs = upload(ofs);
+  std::vector<long long> tofs(a->nm + 1, 0);
+  for (int i = 0; i < a->nm; ++i) {
+    int l0 = a->mval[i] > spin ? a->mval[i] : spin;
+    long long n = a->lmax >= l0 ? a->lmax - l0 + 1 : 0;
+    tofs[i + 1] = tofs[i] + ((n + 7) & ~7LL);
+  }
+  c.tofs = upload(tofs);
+  c.trows = tofs[a->nm];
   c.ready = true;
 }
 
@@ -251,7 +259,7 @@ void sharp_destroy_alm_info(sharp_alm_info *a) {
   if (a->device >= 0) {
     forget_layout(a);
     cudaFree(a->d_mval); cudaFree(a->d_mvstart); cudaFree(a->d_m2im); cudaFree(a->d_K0); cudaFree(a->d_K2);
-    for (int s = 0; s < 2; ++s) if (a->coef[s].ready) { cudaFree(a->coef[s].tab); cudaFree(a->coef[s].ofs); }
+    for (int s = 0; s < 2; ++s) if (a->coef[s].ready) { cudaFree(a->coef[s].tab); cudaFree(a->coef[s].ofs); cudaFree(a->coef[s].tofs); }
   }
   delete a;
 }
@@ -383,6 +391,7 @@ LegAlm make_legalm(sharp_alm_info *a, int spin) {
   A.mval = a->d_mval; A.mvstart = a->d_mvstart;
   A.coef = a->coef[spin ? 1 : 0].tab; A.cofs = a->coef[spin ? 1 : 0].ofs;
   A.Kstart = spin ? a->d_K2 : a->d_K0;
+  A.tofs = a->coef[spin ? 1 : 0].tofs; A.trows = a->coef[spin ? 1 : 0].trows;
   return A;
 }
 
@@ -529,7 +538,7 @@ static bool try_pipelined(int type, int spin, double *const *alm, double *const 
     for (int i = ns - 1; i >= 0; --i) {          // belt (large rows) first, polar caps last
       sharp_geom_info *sub = g->subs[i];
       G.slot_begin = sub->pair0; G.slot_end = sub->pair0 + sub->npairs;
-      launch_legendre_synth(spin, G, A, alm_dev, ph, st);
+      launch_legendre_synth(spin, G, A, alm_dev, ph, st, i == ns - 1);   // a_lm rows prepared once
       L.pair0 = sub->pair0;
       ringfft_synth(sub, ncomp, L, ph, map_dev, type == SHARP_WY, false, st);
       cudaEvent_t e = pooled_event(i);

@@ -43,14 +43,18 @@ struct LegAlm {
   const double *coef = nullptr;
   const long long *cofs = nullptr;
   const double *Kstart = nullptr;  // K0 (spin 0) or K2 (spin 2), indexed by m
+  const long long *tofs = nullptr; // first synthesis tile row of each local m (rows padded to 8 per m)
+  long long trows = 0;             // total tile rows
 };
 
 // Phase buffer element: {north re, north im, south re, south im}.
 // Index: ((owner*ncomp_tot + comp0 + c)*NML + im)*NPL + local
 //
 // synthesis: alm (device, ncomp pointers) -> ph ; analysis: ph -> alm (atomic accumulate)
+// `prep`: (re)build the pre-scaled a_lm tile rows first; false when the same a_lm were already
+// prepared by an earlier launch of this transform (ring-pair chunks of the pipelined host path)
 void launch_legendre_synth(int spin, const LegGeom &g, const LegAlm &a, const double *const *alm,
-                           double4 *ph, cudaStream_t st);
+                           double4 *ph, cudaStream_t st, bool prep = true);
 void launch_legendre_anal(int spin, const LegGeom &g, const LegAlm &a, double *const *alm,
                           const double4 *ph, cudaStream_t st);
 

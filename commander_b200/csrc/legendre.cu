@@ -23,10 +23,7 @@
 
 namespace cmdr {
 
-constexpr int TL = 128;    // l per shared-memory tile, analysis kernels (one entry per thread)
-constexpr int TLS = 256;   // l per tile, spin-0 synthesis (TLS / NT entries per thread)
-constexpr int TLS2 = 128;  // l per tile, spin-2 synthesis (measured: 256 is slower there)
-constexpr int NT = 128;    // threads per CTA
+constexpr int TL = 128;    // l per shared-memory tile (per warp, double buffered)
 constexpr unsigned FULL = 0xffffffffu;
 constexpr double SCALE_DOWN = 7.458340731200207e-155;   // 2^-512
 
@@ -41,6 +38,8 @@ struct KParams {
   const double *coef;
   const long long *cofs;
   const double *Kstart;
+  const long long *tofs;             // synthesis: first tile row of each local m (rows padded to 8 per m)
+  double *trows;                     // synthesis: tile rows (TileS0 / TileS2), written by the prep kernels
   const double *trig;
   const int *mlim;
   const int *wslot;                  // work index -> storage slot (nullptr: identity)
@@ -54,7 +53,6 @@ struct __align__(16) TileS0 { double A, ar, ai, pad; };
 struct __align__(16) TileS2 { double A, C, cpr, cpi, cmr, cmi; };
 struct __align__(16) TileA0 { double A, g; };
 struct __align__(16) TileA2 { double A, C, g, pad; };
-static_assert(TL == NT, "tile staging assumes one entry per thread");
 
 // analysis input: blocks indexed by the rank that owns the rings in the local buffer; with the
 // fused exchange the block of THIS rank in the ring owner's buffer, read over NVLink
@@ -72,6 +70,16 @@ __device__ __forceinline__ double4 *ph_out(const KParams &p, int comp, int im, i
   const int blk = p.src_rank >= 0 ? p.src_rank : owner;
   return p.peer[owner] + ((size_t)(blk * p.ncomp_tot + p.comp0 + comp) * p.NML + im) * p.NPL + local;
 }
+
+// 16-byte asynchronous global -> shared copies (LDGSTS): every kernel stages its per-l
+// tiles as raw rows of a global table (coefficient tables for analysis, the pre-scaled a_lm rows
+// written by the prep kernels for synthesis), so staging needs no registers and no barrier.
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src) {
+  unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
 // ------------------------------------------------------------------------------------
 // spin-0 synthesis
@@ -101,19 +109,49 @@ __device__ __forceinline__ void synth0_group(const TileS0 *t, const double (&x)[
   }
 }
 
-template <int R>
-__global__ void __launch_bounds__(NT) synth0_kernel(KParams p) {
-  __shared__ TileS0 tile[2][TLS];
+// Tile rows for synthesis: {A', g a_lm} per (m, l), written once per transform by a prep kernel so
+// that every warp of the Legendre kernel can stage them with plain asynchronous copies.  Rows of one
+// m are padded with zero rows to a multiple of 8 (the kernels walk l in groups of 8).
+__global__ void __launch_bounds__(256) prep_s0_kernel(KParams p) {
   const int im = blockIdx.y, m = p.mval[im];
-  const int tid = threadIdx.x;
-  const int chunk0 = p.slot_begin + blockIdx.x * (NT * R);
+  const int j = blockIdx.x * blockDim.x + threadIdx.x, l = m + j;
+  const int npad = (p.lmax - m + 1 + 7) & ~7;
+  if (j >= npad) return;
+  TileS0 e{0.0, 0.0, 0.0, 0.0};
+  if (l <= p.lmax) {
+    const double *coef = p.coef + p.cofs[im];
+    const double *a = p.alm0;
+    const long long mvs = p.mvstart[im];
+    const double nrm = (p.real_packed && m > 0) ? 0.70710678118654752440 : 1.0;
+    double2 c = reinterpret_cast<const double2 *>(coef)[l - m];   // {A', g}
+    double gs = c.y * nrm;
+    e.A = c.x;
+    if (p.real_packed) {
+      if (m == 0) { e.ar = gs * a[mvs + l]; }
+      else { e.ar = gs * a[mvs + 2 * (long long)l]; e.ai = gs * a[mvs + 2 * (long long)l + 1]; }
+    } else {
+      e.ar = gs * a[2 * (mvs + l)];
+      e.ai = m == 0 ? 0.0 : gs * a[2 * (mvs + l) + 1];
+    }
+  }
+  reinterpret_cast<TileS0 *>(p.trows)[p.tofs[im] + j] = e;
+}
+
+// Synthesis kernels: ONE WARP PER CTA like the analysis kernels (no block barriers; a thread owns R
+// adjacent ring pairs; whole warps beyond the m cut-off only write zeros).
+template <int R, int MINB>
+__global__ void __launch_bounds__(32, MINB) synth0_kernel(KParams p) {
+  __shared__ __align__(16) TileS0 tile[2][TL];
+  const int im = blockIdx.y, m = p.mval[im];
+  const int lane = threadIdx.x;
+  const int chunk0 = p.slot_begin + blockIdx.x * (32 * R);
   double x[R], cur[R], prev[R], per[R], pei[R], por[R], poi[R];
   int k[R], slot[R];
   bool any = false;
   const double K = p.Kstart[m];
 #pragma unroll
   for (int r = 0; r < R; ++r) {
-    slot[r] = chunk0 + tid * R + r;
+    slot[r] = chunk0 + lane * R + r;
     bool valid = slot[r] < p.nslots && m <= p.mlim[min(slot[r], p.nslots - 1)];
     per[r] = pei[r] = por[r] = poi[r] = 0.0;
     prev[r] = 0.0; cur[r] = 0.0; k[r] = 0; x[r] = 0.0;
@@ -125,61 +163,34 @@ __global__ void __launch_bounds__(NT) synth0_kernel(KParams p) {
       any = true;
     }
   }
-  if (!__syncthreads_or(any)) {   // whole chunk beyond the m cut-off: phases are zero
+  if (__any_sync(FULL, any)) {
+    const TileS0 *rows = reinterpret_cast<const TileS0 *>(p.trows) + p.tofs[im];
+    auto issue_tile = [&](int b, int lt) {     // rows past this m's padded range are never used
+      const char *src = reinterpret_cast<const char *>(rows + (lt - m));
+      char *dst = reinterpret_cast<char *>(tile[b]);
 #pragma unroll
-    for (int r = 0; r < R; ++r)
-      if (slot[r] < p.nslots) *ph_out(p, 0, im, slot[r]) = make_double4(0, 0, 0, 0);
-    return;
-  }
-  const double *coef = p.coef + p.cofs[im];
-  const double *a = p.alm0;
-  const long long mvs = p.mvstart[im];
-  const double nrm = (p.real_packed && m > 0) ? 0.70710678118654752440 : 1.0;
-  // Tiles are double buffered: the next tile's global loads are issued before the current
-  // tile is consumed and land in shared memory afterwards -> one barrier per tile and the
-  // global latency is hidden behind the FP64 work.
-  auto load_entry = [&](int l) {
-    TileS0 e{0.0, 0.0, 0.0, 0.0};
-    if (l <= p.lmax) {
-      double2 c = reinterpret_cast<const double2 *>(coef)[l - m];   // {A', g}
-      double gs = c.y * nrm;
-      e.A = c.x;
-      if (p.real_packed) {
-        if (m == 0) { e.ar = gs * a[mvs + l]; }
-        else { e.ar = gs * a[mvs + 2 * (long long)l]; e.ai = gs * a[mvs + 2 * (long long)l + 1]; }
-      } else {
-        e.ar = gs * a[2 * (mvs + l)];
-        e.ai = m == 0 ? 0.0 : gs * a[2 * (mvs + l) + 1];
-      }
-    }
-    return e;
-  };
-#pragma unroll
-  for (int q = 0; q < TLS / NT; ++q) tile[0][tid + q * NT] = load_entry(m + tid + q * NT);
-  __syncthreads();
-  int buf = 0;
-  for (int lt = m; lt <= p.lmax; lt += TLS, buf ^= 1) {
-    const bool more = lt + TLS <= p.lmax;
-    TileS0 nxt[TLS / NT];
-    if (more) {
-#pragma unroll
-      for (int q = 0; q < TLS / NT; ++q) nxt[q] = load_entry(lt + TLS + tid + q * NT);
-    }
-    const int ngroups = min(TLS, p.lmax - lt + 8) / 8;
+      for (int q = 0; q < (int)(TL * sizeof(TileS0)) / 512; ++q) cp_async16(dst + (q * 32 + lane) * 16, src + (q * 32 + lane) * 16);
+      cp_async_commit();
+    };
+    issue_tile(0, m);
+    cp_async_wait_all();
+    __syncwarp();
+    int buf = 0;
+    for (int lt = m; lt <= p.lmax; lt += TL, buf ^= 1) {
+      if (lt + TL <= p.lmax) issue_tile(buf ^ 1, lt + TL);
+      const int ngroups = min(TL, p.lmax - lt + 8) / 8;
 #pragma unroll 1
-    for (int g = 0; g < ngroups; ++g) {
-      bool all_on = true, none_on = true;
+      for (int g = 0; g < ngroups; ++g) {
+        bool all_on = true, none_on = true;
 #pragma unroll
-      for (int r = 0; r < R; ++r) { all_on &= (k[r] == 0); none_on &= (k[r] < 0); }
-      if (__all_sync(FULL, all_on)) synth0_group<2, R>(tile[buf] + 8 * g, x, cur, prev, per, pei, por, poi, k);
-      else if (__all_sync(FULL, none_on)) synth0_group<0, R>(tile[buf] + 8 * g, x, cur, prev, per, pei, por, poi, k);
-      else synth0_group<1, R>(tile[buf] + 8 * g, x, cur, prev, per, pei, por, poi, k);
+        for (int r = 0; r < R; ++r) { all_on &= (k[r] == 0); none_on &= (k[r] < 0); }
+        if (__all_sync(FULL, all_on)) synth0_group<2, R>(tile[buf] + 8 * g, x, cur, prev, per, pei, por, poi, k);
+        else if (__all_sync(FULL, none_on)) synth0_group<0, R>(tile[buf] + 8 * g, x, cur, prev, per, pei, por, poi, k);
+        else synth0_group<1, R>(tile[buf] + 8 * g, x, cur, prev, per, pei, por, poi, k);
+      }
+      cp_async_wait_all();
+      __syncwarp();
     }
-    if (more) {
-#pragma unroll
-      for (int q = 0; q < TLS / NT; ++q) tile[buf ^ 1][tid + q * NT] = nxt[q];
-    }
-    __syncthreads();
   }
 #pragma unroll
   for (int r = 0; r < R; ++r)
@@ -230,12 +241,44 @@ __device__ __forceinline__ void synth2_group(const TileS2 *t, const double (&x)[
   }
 }
 
-template <int R>
-__global__ void __launch_bounds__(NT) synth2_kernel(KParams p) {
-  __shared__ TileS2 tile[2][TLS2];
+__global__ void __launch_bounds__(256) prep_s2_kernel(KParams p) {
   const int im = blockIdx.y, m = p.mval[im];
-  const int tid = threadIdx.x;
-  const int chunk0 = p.slot_begin + blockIdx.x * (NT * R);
+  const int l0 = max(m, 2);
+  const int j = blockIdx.x * blockDim.x + threadIdx.x, l = l0 + j;
+  const int npad = l0 <= p.lmax ? (p.lmax - l0 + 1 + 7) & ~7 : 0;
+  if (j >= npad) return;
+  TileS2 e{0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+  if (l <= p.lmax) {
+    const double *coef = p.coef + p.cofs[im];
+    const double *aE = p.alm0, *aB = p.alm1;
+    const long long mvs = p.mvstart[im];
+    const double nrm = (p.real_packed && m > 0) ? 0.70710678118654752440 : 1.0;
+    double4 c = reinterpret_cast<const double4 *>(coef)[l - l0];   // {A', C', g, 0}
+    double gs = c.z * nrm;
+    e.A = c.x; e.C = c.y;
+    double er, ei = 0.0, br, bi = 0.0;
+    if (p.real_packed) {
+      if (m == 0) { er = aE[mvs + l]; br = aB[mvs + l]; }
+      else {
+        er = aE[mvs + 2 * (long long)l]; ei = aE[mvs + 2 * (long long)l + 1];
+        br = aB[mvs + 2 * (long long)l]; bi = aB[mvs + 2 * (long long)l + 1];
+      }
+    } else {
+      er = aE[2 * (mvs + l)]; br = aB[2 * (mvs + l)];
+      if (m > 0) { ei = aE[2 * (mvs + l) + 1]; bi = aB[2 * (mvs + l) + 1]; }
+    }
+    e.cpr = -gs * (er - bi); e.cpi = -gs * (ei + br);
+    e.cmr = -gs * (er + bi); e.cmi = -gs * (ei - br);
+  }
+  reinterpret_cast<TileS2 *>(p.trows)[p.tofs[im] + j] = e;
+}
+
+template <int R, int MINB>
+__global__ void __launch_bounds__(32, MINB) synth2_kernel(KParams p) {
+  __shared__ __align__(16) TileS2 tile[2][TL];
+  const int im = blockIdx.y, m = p.mval[im];
+  const int lane = threadIdx.x;
+  const int chunk0 = p.slot_begin + blockIdx.x * (32 * R);
   const int l0 = max(m, 2);
   double x[R], P[R], Pp[R], M[R], Mp[R], a[R][8];
   int k[R], slot[R];
@@ -243,7 +286,7 @@ __global__ void __launch_bounds__(NT) synth2_kernel(KParams p) {
   const double K = p.Kstart[m];
 #pragma unroll
   for (int r = 0; r < R; ++r) {
-    slot[r] = chunk0 + tid * R + r;
+    slot[r] = chunk0 + lane * R + r;
     bool valid = slot[r] < p.nslots && m <= p.mlim[min(slot[r], p.nslots - 1)] && l0 <= p.lmax;
 #pragma unroll
     for (int q = 0; q < 8; ++q) a[r][q] = 0.0;
@@ -256,67 +299,34 @@ __global__ void __launch_bounds__(NT) synth2_kernel(KParams p) {
       any = true;
     }
   }
-  if (!__syncthreads_or(any)) {
+  if (__any_sync(FULL, any)) {
+    const TileS2 *rows = reinterpret_cast<const TileS2 *>(p.trows) + p.tofs[im];
+    auto issue_tile = [&](int b, int lt) {     // rows past this m's padded range are never used
+      const char *src = reinterpret_cast<const char *>(rows + (lt - l0));
+      char *dst = reinterpret_cast<char *>(tile[b]);
 #pragma unroll
-    for (int r = 0; r < R; ++r)
-      if (slot[r] < p.nslots) {
-        *ph_out(p, 0, im, slot[r]) = make_double4(0, 0, 0, 0);
-        *ph_out(p, 1, im, slot[r]) = make_double4(0, 0, 0, 0);
-      }
-    return;
-  }
-  const double *coef = p.coef + p.cofs[im];
-  const double *aE = p.alm0, *aB = p.alm1;
-  const long long mvs = p.mvstart[im];
-  const double nrm = (p.real_packed && m > 0) ? 0.70710678118654752440 : 1.0;
-  auto load_entry = [&](int l) {
-    TileS2 e{0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-    if (l <= p.lmax) {
-      double4 c = reinterpret_cast<const double4 *>(coef)[l - l0];   // {A', C', g, 0}
-      double gs = c.z * nrm;
-      e.A = c.x; e.C = c.y;
-      double er, ei = 0.0, br, bi = 0.0;
-      if (p.real_packed) {
-        if (m == 0) { er = aE[mvs + l]; br = aB[mvs + l]; }
-        else {
-          er = aE[mvs + 2 * (long long)l]; ei = aE[mvs + 2 * (long long)l + 1];
-          br = aB[mvs + 2 * (long long)l]; bi = aB[mvs + 2 * (long long)l + 1];
-        }
-      } else {
-        er = aE[2 * (mvs + l)]; br = aB[2 * (mvs + l)];
-        if (m > 0) { ei = aE[2 * (mvs + l) + 1]; bi = aB[2 * (mvs + l) + 1]; }
-      }
-      e.cpr = -gs * (er - bi); e.cpi = -gs * (ei + br);
-      e.cmr = -gs * (er + bi); e.cmi = -gs * (ei - br);
-    }
-    return e;
-  };
-#pragma unroll
-  for (int q = 0; q < TLS2 / NT; ++q) tile[0][tid + q * NT] = load_entry(l0 + tid + q * NT);
-  __syncthreads();
-  int buf = 0;
-  for (int lt = l0; lt <= p.lmax; lt += TLS2, buf ^= 1) {
-    const bool more = lt + TLS2 <= p.lmax;
-    TileS2 nxt[TLS2 / NT];
-    if (more) {
-#pragma unroll
-      for (int q = 0; q < TLS2 / NT; ++q) nxt[q] = load_entry(lt + TLS2 + tid + q * NT);
-    }
-    const int ngroups = min(TLS2, p.lmax - lt + 8) / 8;
+      for (int q = 0; q < (int)(TL * sizeof(TileS2)) / 512; ++q) cp_async16(dst + (q * 32 + lane) * 16, src + (q * 32 + lane) * 16);
+      cp_async_commit();
+    };
+    issue_tile(0, l0);
+    cp_async_wait_all();
+    __syncwarp();
+    int buf = 0;
+    for (int lt = l0; lt <= p.lmax; lt += TL, buf ^= 1) {
+      if (lt + TL <= p.lmax) issue_tile(buf ^ 1, lt + TL);
+      const int ngroups = min(TL, p.lmax - lt + 8) / 8;
 #pragma unroll 1
-    for (int g = 0; g < ngroups; ++g) {
-      bool all_on = true, none_on = true;
+      for (int g = 0; g < ngroups; ++g) {
+        bool all_on = true, none_on = true;
 #pragma unroll
-      for (int r = 0; r < R; ++r) { all_on &= (k[r] == 0); none_on &= (k[r] < 0); }
-      if (__all_sync(FULL, all_on)) synth2_group<2, R>(tile[buf] + 8 * g, x, P, Pp, M, Mp, a, k);
-      else if (__all_sync(FULL, none_on)) synth2_group<0, R>(tile[buf] + 8 * g, x, P, Pp, M, Mp, a, k);
-      else synth2_group<1, R>(tile[buf] + 8 * g, x, P, Pp, M, Mp, a, k);
+        for (int r = 0; r < R; ++r) { all_on &= (k[r] == 0); none_on &= (k[r] < 0); }
+        if (__all_sync(FULL, all_on)) synth2_group<2, R>(tile[buf] + 8 * g, x, P, Pp, M, Mp, a, k);
+        else if (__all_sync(FULL, none_on)) synth2_group<0, R>(tile[buf] + 8 * g, x, P, Pp, M, Mp, a, k);
+        else synth2_group<1, R>(tile[buf] + 8 * g, x, P, Pp, M, Mp, a, k);
+      }
+      cp_async_wait_all();
+      __syncwarp();
     }
-    if (more) {
-#pragma unroll
-      for (int q = 0; q < TLS2 / NT; ++q) tile[buf ^ 1][tid + q * NT] = nxt[q];
-    }
-    __syncthreads();
   }
   // sg_l = (-1)^(l+m+2) = sg0 * (-1)^(l-l0)
   const double sg0 = ((l0 + m) & 1) ? -0.5 : 0.5;
@@ -346,14 +356,6 @@ __global__ void __launch_bounds__(NT) synth2_kernel(KParams p) {
 // ------------------------------------------------------------------------------------
 __device__ __forceinline__ double shfl_xor_d(double v, int mask) { return __shfl_xor_sync(FULL, v, mask); }
 
-// 16-byte asynchronous global -> shared copies (LDGSTS): the coefficient tiles of the analysis
-// kernels are raw rows of the tables built by coef.cpp, so staging needs no registers.
-__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src) {
-  unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
 template <int H>
 __device__ __forceinline__ void bfly_select(double *v, int lane, int bit) {
@@ -851,6 +853,7 @@ static KParams make_params(const LegGeom &g, const LegAlm &a, double *alm0, doub
   p.lmax = a.lmax; p.nm = a.nm; p.real_packed = a.real_packed;
   p.slot_begin = g.slot_begin; p.nslots = g.slot_end >= 0 ? g.slot_end : g.nslots; p.NPL = g.NPL; p.NML = g.NML; p.ncomp_tot = g.ncomp_tot; p.comp0 = g.comp0;
   p.mval = a.mval; p.mvstart = a.mvstart; p.coef = a.coef; p.cofs = a.cofs; p.Kstart = a.Kstart;
+  p.tofs = nullptr; p.trows = nullptr;
   p.trig = g.trig; p.mlim = g.mlim; p.wslot = g.wslot;
   p.alm0 = alm0; p.alm1 = alm1; p.ph = ph;
   p.src_rank = g.npeer ? g.src_rank : -1;
@@ -859,43 +862,51 @@ static KParams make_params(const LegGeom &g, const LegAlm &a, double *alm0, doub
 }
 
 template <int R, typename K>
-static void launch_r(K kernel, const KParams &p, int /*nslots*/, int nm, cudaStream_t st) {
-  const int n = p.nslots - p.slot_begin;
-  if (n <= 0) return;
-  dim3 grid((n + NT * R - 1) / (NT * R), nm);
-  kernel<<<grid, NT, 0, st>>>(p);
-}
-
-void launch_legendre_synth(int spin, const LegGeom &g, const LegAlm &a, const double *const *alm,
-                           double4 *ph, cudaStream_t st) {
-  if (a.nm == 0 || g.nslots == 0) return;
-  KParams p = make_params(g, a, const_cast<double *>(alm[0]), spin ? const_cast<double *>(alm[1]) : nullptr, ph);
-  static const int r0 = env_int("CMDR_SHT_R_S0", 4), r2 = env_int("CMDR_SHT_R_S2", 2);
-  if (spin == 0) {
-    switch (r0) {
-      case 2: launch_r<2>(synth0_kernel<2>, p, g.nslots, a.nm, st); break;
-      case 6: launch_r<6>(synth0_kernel<6>, p, g.nslots, a.nm, st); break;
-      case 8: launch_r<8>(synth0_kernel<8>, p, g.nslots, a.nm, st); break;
-      default: launch_r<4>(synth0_kernel<4>, p, g.nslots, a.nm, st); break;
-    }
-  } else {
-    switch (r2) {
-      case 1: launch_r<1>(synth2_kernel<1>, p, g.nslots, a.nm, st); break;
-      case 3: launch_r<3>(synth2_kernel<3>, p, g.nslots, a.nm, st); break;
-      case 4: launch_r<4>(synth2_kernel<4>, p, g.nslots, a.nm, st); break;
-      default: launch_r<2>(synth2_kernel<2>, p, g.nslots, a.nm, st); break;
-    }
-  }
-  count_launch();
-  CMDR_CUDA_CHECK(cudaGetLastError());
-}
-
-template <int R, typename K>
 static void launch_w(K kernel, const KParams &p, int nm, cudaStream_t st) {   // one warp per CTA
   const int n = p.nslots - p.slot_begin;
   if (n <= 0) return;
   dim3 grid((n + 32 * R - 1) / (32 * R), nm);
   kernel<<<grid, 32, 0, st>>>(p);
+}
+
+void launch_legendre_synth(int spin, const LegGeom &g, const LegAlm &a, const double *const *alm,
+                           double4 *ph, cudaStream_t st, bool prep) {
+  if (a.nm == 0 || g.nslots == 0) return;
+  KParams p = make_params(g, a, const_cast<double *>(alm[0]), spin ? const_cast<double *>(alm[1]) : nullptr, ph);
+  // tile rows {A', [C',] g a_lm} for all local (m, l): written once per transform (`prep`), then
+  // streamed by every warp of the Legendre kernel
+  const size_t rowbytes = spin == 0 ? sizeof(TileS0) : sizeof(TileS2);
+  p.tofs = a.tofs;
+  p.trows = static_cast<double *>(scratch_get(spin == 0 ? "synth_rows0" : "synth_rows2", rowbytes * (size_t)(a.trows + TL)));
+  if (prep) {
+    dim3 pg((a.lmax + 8 + 255) / 256, a.nm);
+    if (spin == 0) prep_s0_kernel<<<pg, 256, 0, st>>>(p); else prep_s2_kernel<<<pg, 256, 0, st>>>(p);
+    count_launch();
+  }
+  static const int r0 = env_int("CMDR_SHT_R_S0", 4), r2 = env_int("CMDR_SHT_R_S2", 4);
+  static const int b0 = env_int("CMDR_SHT_MINB_S0", 16), b2 = env_int("CMDR_SHT_MINB_S2", 8);
+  if (spin == 0) {
+    switch (r0 * 100 + b0) {
+      case 216: launch_w<2>(synth0_kernel<2, 16>, p, a.nm, st); break;
+      case 412: launch_w<4>(synth0_kernel<4, 12>, p, a.nm, st); break;
+      case 612: launch_w<6>(synth0_kernel<6, 12>, p, a.nm, st); break;
+      case 812: launch_w<8>(synth0_kernel<8, 12>, p, a.nm, st); break;
+      case 808: launch_w<8>(synth0_kernel<8, 8>, p, a.nm, st); break;
+      default: launch_w<4>(synth0_kernel<4, 16>, p, a.nm, st); break;
+    }
+  } else {
+    switch (r2 * 100 + b2) {
+      case 116: launch_w<1>(synth2_kernel<1, 16>, p, a.nm, st); break;
+      case 212: launch_w<2>(synth2_kernel<2, 12>, p, a.nm, st); break;
+      case 312: launch_w<3>(synth2_kernel<3, 12>, p, a.nm, st); break;
+      case 308: launch_w<3>(synth2_kernel<3, 8>, p, a.nm, st); break;
+      case 412: launch_w<4>(synth2_kernel<4, 12>, p, a.nm, st); break;
+      case 408: launch_w<4>(synth2_kernel<4, 8>, p, a.nm, st); break;
+      default: launch_w<2>(synth2_kernel<2, 16>, p, a.nm, st); break;
+    }
+  }
+  count_launch();
+  CMDR_CUDA_CHECK(cudaGetLastError());
 }
 
 void launch_legendre_anal(int spin, const LegGeom &g, const LegAlm &a, double *const *alm,

@@ -18,6 +18,8 @@ struct CoefDev {            // device copy of one (alm_info, spin) coefficient t
   bool ready = false;
   double *tab = nullptr;    // spin 0: {A', g} per l ; spin 2: {A', C', g, 0} per l
   long long *ofs = nullptr; // per local m: offset (in doubles) of l = l0
+  long long *tofs = nullptr; // per local m: first synthesis tile row (rows padded to a multiple of 8)
+  long long trows = 0;       // total synthesis tile rows
 };
 
 // Region of the ring-FFT work buffer: pairs [first, first+np) share one FFT length.

@@ -232,3 +232,7 @@ def nominal_flops(geom_info: sharp_geom_info, alm_info: sharp_alm_info, spin: in
 
 def measure_fp64_tflops(iters: int = 4096, reps: int = 5) -> float:
     return float(lib().cmdr_sht_measure_fp64_tflops(iters, reps))
+
+
+def measure_fp64_tflops_3op(iters: int = 4096, reps: int = 3) -> float:
+    return float(lib().cmdr_sht_measure_fp64_tflops_3op(iters, reps))
