@@ -504,6 +504,33 @@ static void sub_ranges(const sharp_geom_info *s, long long &nb, long long &ne, l
   sb = s->ofsS[last]; se = s->ofsS[0] + s->nph[0];
 }
 
+// Columns of consecutive local m's are contiguous in the packed a_lm array for the layouts Commander
+// builds (sharp_make_mmajor_real_packed_alm_info): returns their start offsets (doubles) and cuts the
+// m range into `nch` pieces of about equal size.  False for layouts that are not dense.
+static bool alm_m_chunks(const sharp_alm_info *a, long long nalm_d, int nch, std::vector<long long> &mstart,
+                         std::vector<int> &mcut) {
+  mstart.assign(a->nm + 1, 0);
+  const long long f2 = a->real_packed ? 1 : 2;
+  long long pos = 0;
+  for (int i = 0; i < a->nm; ++i) {
+    const int m = a->mval[i];
+    const long long f = (a->real_packed && m > 0) ? 2 : 1;
+    const long long b = (a->mvstart[i] + f * m) * f2, e = (a->mvstart[i] + f * (a->lmax + 1)) * f2;
+    if (b != pos) return false;
+    mstart[i] = b; pos = e;
+  }
+  mstart[a->nm] = pos;
+  if (pos != nalm_d || a->nm < 64) return false;
+  mcut.assign(nch + 1, a->nm);
+  mcut[0] = 0;
+  for (int j = 1; j < nch; ++j) {
+    int i = mcut[j - 1];
+    while (i < a->nm && mstart[i] < nalm_d * j / nch) ++i;
+    mcut[j] = i;
+  }
+  return true;
+}
+
 static bool try_pipelined(int type, int spin, double *const *alm, double *const *map, sharp_geom_info *g,
                           sharp_alm_info *a, int flags, cudaStream_t st) {
   static const bool disabled = getenv("CMDR_SHT_NO_PIPELINE") != nullptr;
@@ -533,12 +560,40 @@ static bool try_pipelined(int type, int spin, double *const *alm, double *const 
   cudaStream_t cs = copy_stream();
   const int ns = (int)g->subs.size();
   if (synth) {
-    for (int c = 0; c < ncomp; ++c)
-      CMDR_CUDA_CHECK(cudaMemcpyAsync(alm_dev[c], alm[c], sizeof(double) * nalm_d, cudaMemcpyHostToDevice, st));
+    // a_lm upload in NMCH chunks of local m's (the packed columns of consecutive m's are contiguous): the
+    // first ring-pair chunk runs its Legendre kernel m-chunk by m-chunk as the data lands, so only the
+    // first quarter of the upload is exposed.  Falls back to one copy for layouts that are not dense.
+    constexpr int NMCH = 4;
+    std::vector<long long> mstart;
+    std::vector<int> mcut;
+    const int nmch = alm_m_chunks(a, nalm_d, NMCH, mstart, mcut) ? NMCH : 1;
+    if (nmch == 1) {
+      for (int c = 0; c < ncomp; ++c)
+        CMDR_CUDA_CHECK(cudaMemcpyAsync(alm_dev[c], alm[c], sizeof(double) * nalm_d, cudaMemcpyHostToDevice, st));
+    } else {
+      cudaEvent_t e0 = pooled_event(ns + 1);               // earlier work on `st` may still read the staging buffer
+      CMDR_CUDA_CHECK(cudaEventRecord(e0, st));
+      CMDR_CUDA_CHECK(cudaStreamWaitEvent(cs, e0, 0));
+      for (int j = 0; j < nmch; ++j) {
+        const long long b = mstart[mcut[j]], e = mstart[mcut[j + 1]];
+        for (int c = 0; c < ncomp; ++c)
+          if (e > b) CMDR_CUDA_CHECK(cudaMemcpyAsync(alm_dev[c] + b, alm[c] + b, sizeof(double) * (e - b), cudaMemcpyHostToDevice, cs));
+        CMDR_CUDA_CHECK(cudaEventRecord(pooled_event(ns + 2 + j), cs));
+      }
+    }
     for (int i = ns - 1; i >= 0; --i) {          // belt (large rows) first, polar caps last
       sharp_geom_info *sub = g->subs[i];
       G.slot_begin = sub->pair0; G.slot_end = sub->pair0 + sub->npairs;
-      launch_legendre_synth(spin, G, A, alm_dev, ph, st, i == ns - 1);   // a_lm rows prepared once
+      if (i == ns - 1 && nmch > 1) {
+        for (int j = 0; j < nmch; ++j) {
+          CMDR_CUDA_CHECK(cudaStreamWaitEvent(st, pooled_event(ns + 2 + j), 0));
+          LegAlm Aj = A;
+          Aj.im_begin = mcut[j]; Aj.im_end = mcut[j + 1];
+          launch_legendre_synth(spin, G, Aj, alm_dev, ph, st, true);
+        }
+      } else {
+        launch_legendre_synth(spin, G, A, alm_dev, ph, st, i == ns - 1);   // a_lm rows prepared once
+      }
       L.pair0 = sub->pair0;
       ringfft_synth(sub, ncomp, L, ph, map_dev, type == SHARP_WY, false, st);
       cudaEvent_t e = pooled_event(i);
@@ -555,6 +610,9 @@ static bool try_pipelined(int type, int spin, double *const *alm, double *const 
     CMDR_CUDA_CHECK(cudaStreamSynchronize(cs));
     CMDR_CUDA_CHECK(cudaStreamSynchronize(st));
   } else {
+    std::vector<long long> mstart;
+    std::vector<int> mcut;
+    const int nmch = alm_m_chunks(a, nalm_d, 4, mstart, mcut) ? 4 : 1;
     // the copy stream must not overwrite staging rows an earlier call on `st` still reads
     cudaEvent_t e0 = pooled_event(ns);
     CMDR_CUDA_CHECK(cudaEventRecord(e0, st));
@@ -575,10 +633,29 @@ static bool try_pipelined(int type, int spin, double *const *alm, double *const 
       L.pair0 = sub->pair0;
       ringfft_anal(sub, ncomp, L, ph, map_dev, type == SHARP_YtW, st);
       G.slot_begin = sub->pair0; G.slot_end = sub->pair0 + sub->npairs;
-      launch_legendre_anal(spin, G, A, alm_dev, ph, st);
+      if (i == ns - 1 && nmch > 1) {
+        // last ring-pair chunk: m-chunk by m-chunk, so that the finished a_lm columns go back to the host
+        // while the next m-chunk is still being accumulated (only the last quarter of the download is exposed)
+        for (int j = 0; j < nmch; ++j) {
+          LegAlm Aj = A;
+          Aj.im_begin = mcut[j]; Aj.im_end = mcut[j + 1];
+          launch_legendre_anal(spin, G, Aj, alm_dev, ph, st);
+          cudaEvent_t e = pooled_event(ns + 2 + j);
+          CMDR_CUDA_CHECK(cudaEventRecord(e, st));
+          CMDR_CUDA_CHECK(cudaStreamWaitEvent(cs, e, 0));
+          const long long b = mstart[mcut[j]], e2 = mstart[mcut[j + 1]];
+          for (int c = 0; c < ncomp; ++c)
+            if (e2 > b) CMDR_CUDA_CHECK(cudaMemcpyAsync(alm[c] + b, alm_dev[c] + b, sizeof(double) * (e2 - b), cudaMemcpyDeviceToHost, cs));
+        }
+      } else {
+        launch_legendre_anal(spin, G, A, alm_dev, ph, st);
+      }
     }
-    for (int c = 0; c < ncomp; ++c)
-      CMDR_CUDA_CHECK(cudaMemcpyAsync(alm[c], alm_dev[c], sizeof(double) * nalm_d, cudaMemcpyDeviceToHost, st));
+    if (nmch == 1) {
+      for (int c = 0; c < ncomp; ++c)
+        CMDR_CUDA_CHECK(cudaMemcpyAsync(alm[c], alm_dev[c], sizeof(double) * nalm_d, cudaMemcpyDeviceToHost, st));
+    }
+    CMDR_CUDA_CHECK(cudaStreamSynchronize(cs));
     CMDR_CUDA_CHECK(cudaStreamSynchronize(st));
   }
   return true;

@@ -38,6 +38,7 @@ struct LegGeom {
 // alm side of the Legendre stage (local m's of this rank)
 struct LegAlm {
   int lmax = 0, nm = 0, real_packed = 1;
+  int im_begin = 0, im_end = -1;   // sub-range of local m's to process (-1: all)
   const int *mval = nullptr;
   const long long *mvstart = nullptr;
   const double *coef = nullptr;

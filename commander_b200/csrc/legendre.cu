@@ -33,6 +33,7 @@ struct KParams {
   int lmax, nm, real_packed;
   int nslots, NPL, NML, ncomp_tot, comp0;
   int slot_begin;   // first slot handled by this launch (nslots = one past the last)
+  int im0;          // first local m handled by this launch (grid.y counts from it)
   const int *mval;
   const long long *mvstart;
   const double *coef;
@@ -113,7 +114,7 @@ __device__ __forceinline__ void synth0_group(const TileS0 *t, const double (&x)[
 // that every warp of the Legendre kernel can stage them with plain asynchronous copies.  Rows of one
 // m are padded with zero rows to a multiple of 8 (the kernels walk l in groups of 8).
 __global__ void __launch_bounds__(256) prep_s0_kernel(KParams p) {
-  const int im = blockIdx.y, m = p.mval[im];
+  const int im = p.im0 + blockIdx.y, m = p.mval[im];
   const int j = blockIdx.x * blockDim.x + threadIdx.x, l = m + j;
   const int npad = (p.lmax - m + 1 + 7) & ~7;
   if (j >= npad) return;
@@ -142,7 +143,7 @@ __global__ void __launch_bounds__(256) prep_s0_kernel(KParams p) {
 template <int R, int MINB>
 __global__ void __launch_bounds__(32, MINB) synth0_kernel(KParams p) {
   __shared__ __align__(16) TileS0 tile[2][TL];
-  const int im = blockIdx.y, m = p.mval[im];
+  const int im = p.im0 + blockIdx.y, m = p.mval[im];
   const int lane = threadIdx.x;
   const int chunk0 = p.slot_begin + blockIdx.x * (32 * R);
   double x[R], cur[R], prev[R], per[R], pei[R], por[R], poi[R];
@@ -242,7 +243,7 @@ __device__ __forceinline__ void synth2_group(const TileS2 *t, const double (&x)[
 }
 
 __global__ void __launch_bounds__(256) prep_s2_kernel(KParams p) {
-  const int im = blockIdx.y, m = p.mval[im];
+  const int im = p.im0 + blockIdx.y, m = p.mval[im];
   const int l0 = max(m, 2);
   const int j = blockIdx.x * blockDim.x + threadIdx.x, l = l0 + j;
   const int npad = l0 <= p.lmax ? (p.lmax - l0 + 1 + 7) & ~7 : 0;
@@ -276,7 +277,7 @@ __global__ void __launch_bounds__(256) prep_s2_kernel(KParams p) {
 template <int R, int MINB>
 __global__ void __launch_bounds__(32, MINB) synth2_kernel(KParams p) {
   __shared__ __align__(16) TileS2 tile[2][TL];
-  const int im = blockIdx.y, m = p.mval[im];
+  const int im = p.im0 + blockIdx.y, m = p.mval[im];
   const int lane = threadIdx.x;
   const int chunk0 = p.slot_begin + blockIdx.x * (32 * R);
   const int l0 = max(m, 2);
@@ -511,7 +512,7 @@ template <int R, int MINB>
 __global__ void __launch_bounds__(32, MINB) anal0_kernel(KParams p) {
   __shared__ __align__(16) TileA0 tile[2][TL];
   __shared__ __align__(16) double red[TL * 2];
-  const int im = blockIdx.y, m = p.mval[im];
+  const int im = p.im0 + blockIdx.y, m = p.mval[im];
   const int lane = threadIdx.x;
   const int chunk0 = p.slot_begin + blockIdx.x * (32 * R);
   double x[R], cur[R], prev[R], sr[R], si[R], dr[R], di[R];
@@ -713,7 +714,7 @@ template <int R, int MINB>
 __global__ void __launch_bounds__(32, MINB) anal2_kernel(KParams p) {
   __shared__ __align__(16) TileA2 tile[2][TL];
   __shared__ __align__(16) double red[TL * 4];
-  const int im = blockIdx.y, m = p.mval[im];
+  const int im = p.im0 + blockIdx.y, m = p.mval[im];
   const int lane = threadIdx.x;
   const int chunk0 = p.slot_begin + blockIdx.x * (32 * R);
   const int l0 = max(m, 2);
@@ -854,6 +855,7 @@ static KParams make_params(const LegGeom &g, const LegAlm &a, double *alm0, doub
   p.slot_begin = g.slot_begin; p.nslots = g.slot_end >= 0 ? g.slot_end : g.nslots; p.NPL = g.NPL; p.NML = g.NML; p.ncomp_tot = g.ncomp_tot; p.comp0 = g.comp0;
   p.mval = a.mval; p.mvstart = a.mvstart; p.coef = a.coef; p.cofs = a.cofs; p.Kstart = a.Kstart;
   p.tofs = nullptr; p.trows = nullptr;
+  p.im0 = a.im_begin;
   p.trig = g.trig; p.mlim = g.mlim; p.wslot = g.wslot;
   p.alm0 = alm0; p.alm1 = alm1; p.ph = ph;
   p.src_rank = g.npeer ? g.src_rank : -1;
@@ -872,6 +874,8 @@ static void launch_w(K kernel, const KParams &p, int nm, cudaStream_t st) {   //
 void launch_legendre_synth(int spin, const LegGeom &g, const LegAlm &a, const double *const *alm,
                            double4 *ph, cudaStream_t st, bool prep) {
   if (a.nm == 0 || g.nslots == 0) return;
+  const int nmr = (a.im_end >= 0 ? a.im_end : a.nm) - a.im_begin;   // local m's of this launch
+  if (nmr <= 0) return;
   KParams p = make_params(g, a, const_cast<double *>(alm[0]), spin ? const_cast<double *>(alm[1]) : nullptr, ph);
   // tile rows {A', [C',] g a_lm} for all local (m, l): written once per transform (`prep`), then
   // streamed by every warp of the Legendre kernel
@@ -879,7 +883,7 @@ void launch_legendre_synth(int spin, const LegGeom &g, const LegAlm &a, const do
   p.tofs = a.tofs;
   p.trows = static_cast<double *>(scratch_get(spin == 0 ? "synth_rows0" : "synth_rows2", rowbytes * (size_t)(a.trows + TL)));
   if (prep) {
-    dim3 pg((a.lmax + 8 + 255) / 256, a.nm);
+    dim3 pg((a.lmax + 8 + 255) / 256, nmr);
     if (spin == 0) prep_s0_kernel<<<pg, 256, 0, st>>>(p); else prep_s2_kernel<<<pg, 256, 0, st>>>(p);
     count_launch();
   }
@@ -887,22 +891,22 @@ void launch_legendre_synth(int spin, const LegGeom &g, const LegAlm &a, const do
   static const int b0 = env_int("CMDR_SHT_MINB_S0", 16), b2 = env_int("CMDR_SHT_MINB_S2", 8);
   if (spin == 0) {
     switch (r0 * 100 + b0) {
-      case 216: launch_w<2>(synth0_kernel<2, 16>, p, a.nm, st); break;
-      case 412: launch_w<4>(synth0_kernel<4, 12>, p, a.nm, st); break;
-      case 612: launch_w<6>(synth0_kernel<6, 12>, p, a.nm, st); break;
-      case 812: launch_w<8>(synth0_kernel<8, 12>, p, a.nm, st); break;
-      case 808: launch_w<8>(synth0_kernel<8, 8>, p, a.nm, st); break;
-      default: launch_w<4>(synth0_kernel<4, 16>, p, a.nm, st); break;
+      case 216: launch_w<2>(synth0_kernel<2, 16>, p, nmr, st); break;
+      case 412: launch_w<4>(synth0_kernel<4, 12>, p, nmr, st); break;
+      case 612: launch_w<6>(synth0_kernel<6, 12>, p, nmr, st); break;
+      case 812: launch_w<8>(synth0_kernel<8, 12>, p, nmr, st); break;
+      case 808: launch_w<8>(synth0_kernel<8, 8>, p, nmr, st); break;
+      default: launch_w<4>(synth0_kernel<4, 16>, p, nmr, st); break;
     }
   } else {
     switch (r2 * 100 + b2) {
-      case 116: launch_w<1>(synth2_kernel<1, 16>, p, a.nm, st); break;
-      case 212: launch_w<2>(synth2_kernel<2, 12>, p, a.nm, st); break;
-      case 312: launch_w<3>(synth2_kernel<3, 12>, p, a.nm, st); break;
-      case 308: launch_w<3>(synth2_kernel<3, 8>, p, a.nm, st); break;
-      case 412: launch_w<4>(synth2_kernel<4, 12>, p, a.nm, st); break;
-      case 408: launch_w<4>(synth2_kernel<4, 8>, p, a.nm, st); break;
-      default: launch_w<2>(synth2_kernel<2, 16>, p, a.nm, st); break;
+      case 116: launch_w<1>(synth2_kernel<1, 16>, p, nmr, st); break;
+      case 212: launch_w<2>(synth2_kernel<2, 12>, p, nmr, st); break;
+      case 312: launch_w<3>(synth2_kernel<3, 12>, p, nmr, st); break;
+      case 308: launch_w<3>(synth2_kernel<3, 8>, p, nmr, st); break;
+      case 412: launch_w<4>(synth2_kernel<4, 12>, p, nmr, st); break;
+      case 408: launch_w<4>(synth2_kernel<4, 8>, p, nmr, st); break;
+      default: launch_w<2>(synth2_kernel<2, 16>, p, nmr, st); break;
     }
   }
   count_launch();
@@ -912,29 +916,31 @@ void launch_legendre_synth(int spin, const LegGeom &g, const LegAlm &a, const do
 void launch_legendre_anal(int spin, const LegGeom &g, const LegAlm &a, double *const *alm,
                           const double4 *ph, cudaStream_t st) {
   if (a.nm == 0 || g.nslots == 0) return;
+  const int nmr = (a.im_end >= 0 ? a.im_end : a.nm) - a.im_begin;   // local m's of this launch
+  if (nmr <= 0) return;
   KParams p = make_params(g, a, alm[0], spin ? alm[1] : nullptr, const_cast<double4 *>(ph));
   static const int r0 = env_int("CMDR_SHT_R_A0", 4), r2 = env_int("CMDR_SHT_R_A2", 4);
   // resident warps per SM the register allocation is capped for (tuning: CMDR_SHT_MINB_A0 / _A2)
   static const int b0 = env_int("CMDR_SHT_MINB_A0", 16), b2 = env_int("CMDR_SHT_MINB_A2", 12);
   if (spin == 0) {
     switch (r0 * 100 + b0) {
-      case 416: launch_w<4>(anal0_kernel<4, 16>, p, a.nm, st); break;
-      case 408: launch_w<4>(anal0_kernel<4, 8>, p, a.nm, st); break;
-      case 612: launch_w<6>(anal0_kernel<6, 12>, p, a.nm, st); break;
-      case 608: launch_w<6>(anal0_kernel<6, 8>, p, a.nm, st); break;
-      case 812: launch_w<8>(anal0_kernel<8, 12>, p, a.nm, st); break;
-      case 808: launch_w<8>(anal0_kernel<8, 8>, p, a.nm, st); break;
-      default: launch_w<4>(anal0_kernel<4, 12>, p, a.nm, st); break;
+      case 416: launch_w<4>(anal0_kernel<4, 16>, p, nmr, st); break;
+      case 408: launch_w<4>(anal0_kernel<4, 8>, p, nmr, st); break;
+      case 612: launch_w<6>(anal0_kernel<6, 12>, p, nmr, st); break;
+      case 608: launch_w<6>(anal0_kernel<6, 8>, p, nmr, st); break;
+      case 812: launch_w<8>(anal0_kernel<8, 12>, p, nmr, st); break;
+      case 808: launch_w<8>(anal0_kernel<8, 8>, p, nmr, st); break;
+      default: launch_w<4>(anal0_kernel<4, 12>, p, nmr, st); break;
     }
   } else {
     switch (r2 * 100 + b2) {
-      case 312: launch_w<3>(anal2_kernel<3, 12>, p, a.nm, st); break;
-      case 308: launch_w<3>(anal2_kernel<3, 8>, p, a.nm, st); break;
-      case 216: launch_w<2>(anal2_kernel<2, 16>, p, a.nm, st); break;
-      case 212: launch_w<2>(anal2_kernel<2, 12>, p, a.nm, st); break;
-      case 412: launch_w<4>(anal2_kernel<4, 12>, p, a.nm, st); break;
-      case 410: launch_w<4>(anal2_kernel<4, 10>, p, a.nm, st); break;
-      default: launch_w<4>(anal2_kernel<4, 8>, p, a.nm, st); break;
+      case 312: launch_w<3>(anal2_kernel<3, 12>, p, nmr, st); break;
+      case 308: launch_w<3>(anal2_kernel<3, 8>, p, nmr, st); break;
+      case 216: launch_w<2>(anal2_kernel<2, 16>, p, nmr, st); break;
+      case 212: launch_w<2>(anal2_kernel<2, 12>, p, nmr, st); break;
+      case 412: launch_w<4>(anal2_kernel<4, 12>, p, nmr, st); break;
+      case 410: launch_w<4>(anal2_kernel<4, 10>, p, nmr, st); break;
+      default: launch_w<4>(anal2_kernel<4, 8>, p, nmr, st); break;
     }
   }
   count_launch();
