@@ -627,13 +627,17 @@ __global__ void __launch_bounds__(32, MINB) anal0_kernel(KParams p) {
 // with bit 3 set run them swapped (Cs = -C', Pa = M, Pb = P, w permuted) so that their registers
 // named S1 hold S2 and vice versa (see the reduction above).
 // ------------------------------------------------------------------------------------
+__device__ __forceinline__ double flip_sign(double v, int mask) {
+  return __hiloint2double(__double2hiint(v) ^ mask, __double2loint(v));
+}
+
 template <int MODE, int R>
-__device__ __forceinline__ void anal2_fma(const TileA2 *t, const double csign, const double (&x)[R], double (&Pa)[R],
+__device__ __forceinline__ void anal2_fma(const TileA2 *t, const int csign, const double (&x)[R], double (&Pa)[R],
                                           double (&Pap)[R], double (&Pb)[R], double (&Pbp)[R],
                                           const double (&w)[R][8], int (&k)[R], double (&acc)[16]) {
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
-    const double A = t[j].A, C = t[j].C * csign;
+    const double A = t[j].A, C = flip_sign(t[j].C, csign);
     double s1r = 0.0, s1i = 0.0, s2r = 0.0, s2i = 0.0;
 #pragma unroll
     for (int r = 0; r < R; ++r) {
@@ -671,7 +675,7 @@ __device__ __forceinline__ void anal2_fma(const TileA2 *t, const double csign, c
 // the same first operand, which then comes from the operand-reuse cache (a DFMA costs
 // max(2, #vector operands fetched from the register file) cycles on B200).
 template <int R, bool FMA>
-__device__ __forceinline__ void anal2_step(const TileA2 *t, const double csign, const double (&x)[R], double (&Pa)[R],
+__device__ __forceinline__ void anal2_step(const TileA2 *t, const int csign, const double (&x)[R], double (&Pa)[R],
                                            double (&Pap)[R], double (&Pb)[R], double (&Pbp)[R],
                                            const double (&w)[R][8], const ReducePipe &in, ReducePipe &out,
                                            double *dst, bool store, int lane) {
@@ -685,7 +689,7 @@ __device__ __forceinline__ void anal2_step(const TileA2 *t, const double csign, 
       double ua[4], ub[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const double A = t[j].A, C = t[j].C * csign;
+        const double A = t[j].A, C = flip_sign(t[j].C, csign);
         ua[j] = fma(x[r], A, C); ub[j] = fma(x[r], A, -C);
       }
 #pragma unroll
@@ -725,7 +729,7 @@ __global__ void __launch_bounds__(32, MINB) anal2_kernel(KParams p) {
   const double K = p.Kstart[m];
   const double sg0 = ((l0 + m) & 1) ? -1.0 : 1.0;
   const bool swapRI = lane & 16, swapPM = lane & 8;
-  const double csign = swapPM ? -1.0 : 1.0;
+  const int csign = swapPM ? 0x80000000 : 0;   // sign-bit mask applied to C' (an integer op, not a DMUL)
 #pragma unroll
   for (int r = 0; r < R; ++r) {
     int slot = chunk0 + lane * R + r;

@@ -26,7 +26,7 @@
 namespace cmdr {
 
 constexpr int SCALE_BITS = 512;    // one scale step
-constexpr int THRESH_BITS = 128;   // accumulate once |mu| >= 2^-128
+constexpr int THRESH_BITS = 70;    // accumulate once |mu| >= 2^-70 (libsharp2 starts at 2^-60, sharp_ftol; g_l = O(1..100) leaves margin)
 // rescale when the biased exponent reaches (SCALE_BITS-THRESH_BITS)+1023
 constexpr int RESCALE_EXP = SCALE_BITS - THRESH_BITS + 1023;
 
