@@ -298,6 +298,7 @@ def run_ours(args):
     e2e_ms = float(t_e2e[0].item()) / e2e_steps
     clocks = sampler.stop() if rank == 0 else None
     cg = run_cg_metric(args, comm, dev, world) if not args.no_cg else None
+    batch = run_batch_metric(dev) if (world == 1 and not args.no_batch) else None
     bytes_alm, bytes_map = 3 * info.nalm * 8, 3 * info.np * 8
 
     # ---- roofline of the dominant kernel (spin-2 Legendre), FP64 pipe
@@ -376,11 +377,54 @@ def run_ours(args):
                 "e2e": {"value": 1e3 / e2e_ms, "unit": UNIT, "ms_per_step": e2e_ms, "steps": e2e_steps,
                         "h2d_bytes_per_step": bytes_alm + bytes_map, "d2h_bytes_per_step": bytes_alm + bytes_map,
                         "host_buffers": "pinned", "api": "comm_map.Y(); comm_map.YtW()  (4 sharp_execute calls)"},
-                "roofline": roofline, "cpu_baseline": cpu, "cg": cg}
+                "roofline": roofline, "cpu_baseline": cpu, "cg": cg, "batch": batch}
         print(json.dumps(line))
     if world > 1:
         cdist.destroy(comm)
         dist.destroy_process_group()
+
+
+def run_batch_metric(dev, nbands=30, nside=512, lmax=1500):
+    """BASELINE.json configs[4]: 30 frequency maps (nside 512, lmax 1500, IQU) through Y / YtW per Gibbs
+    step, pinned host buffers: (i) band by band through the ABI, (ii) through the batched entry point
+    that pipelines the bands' PCIe copies against the kernels."""
+    import numpy as np
+    import torch
+    from commander_b200 import comm_map, comm_mapinfo
+    info = comm_mapinfo(None, nside, lmax, 3, True)
+    maps = []
+    rng = np.random.default_rng(100)
+    for b in range(nbands):
+        m = comm_map(info)
+        m.alm = torch.empty((3, info.nalm), dtype=torch.float64).pin_memory().numpy()
+        m.map = torch.empty((3, info.np), dtype=torch.float64).pin_memory().numpy()
+        m.alm[:] = rng.standard_normal((3, info.nalm))
+        maps.append(m)
+
+    def seq():
+        for m in maps:
+            m.Y()
+        for m in maps:
+            m.YtW()
+
+    def bat():
+        comm_map.Y_batch(maps)
+        comm_map.YtW_batch(maps)
+    out = {}
+    for name, fn in (("sequential", seq), ("batched", bat)):
+        fn()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        reps = 2
+        for _ in range(reps):
+            fn()
+        torch.cuda.synchronize()
+        out[name] = nbands * reps / (time.perf_counter() - t0)
+    nbytes = 2 * 3 * (info.nalm + info.np) * 8
+    return {"metric": "SHT pairs/sec over a 30-band batch (nside 512, lmax 1500, IQU), host buffers", "unit": "pairs/s",
+            "sequential_abi_calls": round(out["sequential"], 2), "batched_entry_point": round(out["batched"], 2),
+            "pcie_bytes_per_pair": nbytes, "bands": nbands, "host_buffers": "pinned",
+            "api": "comm_map.Y()/YtW() per band  vs  comm_map.Y_batch()/YtW_batch() (cmdr_sht_execute_iqu_batch)"}
 
 
 def run_cg_metric(args, comm, dev, world):
@@ -434,6 +478,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-cg", action="store_true", help="skip the secondary CG iters/s measurement")
+    ap.add_argument("--no-batch", action="store_true", help="skip the 30-band batch measurement (config 5)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -249,6 +249,32 @@ class comm_map:
     def WY_iqu(self):
         self._exec_iqu(sharp.SHARP_WY)
 
+    # ---- band batches (extended API): the per-band loops of commander3/src/comm_cr_mod.f90:880-918
+    @staticmethod
+    def _exec_batch(job, maps):
+        info = maps[0].info
+        assert info.pol and info.nmaps == 3 and not (info.dist and info.comm is not None and info.comm.size > 1)
+        assert all(m.info is info for m in maps), "a batch shares one comm_mapinfo"
+        sharp.execute_iqu_batch(job, [m.alm for m in maps], [m.map for m in maps], info.geom_info_T,
+                                info.geom_info_P, info.alm_info)
+
+    @staticmethod
+    def Y_batch(maps):
+        """`call map%Y()` for every band of the list, host<->device copies pipelined band against band."""
+        comm_map._exec_batch(sharp.SHARP_Y, maps)
+
+    @staticmethod
+    def Yt_batch(maps):
+        comm_map._exec_batch(sharp.SHARP_Yt, maps)
+
+    @staticmethod
+    def YtW_batch(maps):
+        comm_map._exec_batch(sharp.SHARP_YtW, maps)
+
+    @staticmethod
+    def WY_batch(maps):
+        comm_map._exec_batch(sharp.SHARP_WY, maps)
+
     # commander3/src/comm_map_mod.f90:1109-1142
     def smooth(self, fwhm, fwhm_pol=None):
         if fwhm <= 0.0 and fwhm_pol is None:

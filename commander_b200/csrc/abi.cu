@@ -726,6 +726,89 @@ void cmdr_sht_execute_iqu(int type, double *const *alm3, double *const *map3, co
   if (sa.staged || sm.staged) CMDR_CUDA_CHECK(cudaStreamSynchronize(st));
 }
 
+// Batch of independent IQU transforms that share the handles (the 30 frequency bands of one Gibbs step,
+// BASELINE config 5; `comm_map%Y` / `%YtW` in a loop over bands, commander3/src/comm_cr_mod.f90:880-918).
+// With host buffers the bands are software-pipelined over three streams and two sets of staging buffers:
+// the upload of band b+1 and the download of band b-1 run beside the kernels of band b (both DMA
+// engines busy), instead of copy-compute-copy per band.  Pinned host buffers give the full overlap.
+void cmdr_sht_execute_iqu_batch(int type, int nbatch, double *const *alm3, double *const *map3,
+                                const sharp_geom_info *geom_T, const sharp_geom_info *geom_P,
+                                const sharp_alm_info *alm_info, int flags, void *stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  sharp_geom_info *gT = const_cast<sharp_geom_info *>(geom_T), *gP = const_cast<sharp_geom_info *>(geom_P);
+  sharp_alm_info *a = const_cast<sharp_alm_info *>(alm_info);
+  const bool synth = (type == SHARP_Y || type == SHARP_WY);
+  const bool add = (flags & SHARP_ADD) != 0;
+  const long long nalm_d = a->nalm * (a->real_packed ? 1 : 2);
+  const long long npix = gT->npix;
+  if (nbatch <= 0) return;
+  bool dev = true;
+  for (int i = 0; i < 3 * nbatch; ++i) dev = dev && is_device_ptr(alm3[i]) && is_device_ptr(map3[i]);
+  if (dev || nalm_d == 0 || npix == 0) {
+    for (int b = 0; b < nbatch; ++b)
+      cmdr_sht_execute_iqu(type, alm3 + 3 * b, map3 + 3 * b, geom_T, geom_P, alm_info, flags, stream);
+    return;
+  }
+  static std::map<int, std::pair<cudaStream_t, cudaStream_t>> cstreams;   // per device: copy-in, copy-out
+  int device = 0;
+  CMDR_CUDA_CHECK(cudaGetDevice(&device));
+  if (!cstreams.count(device)) {
+    cudaStream_t s1, s2;
+    CMDR_CUDA_CHECK(cudaStreamCreateWithFlags(&s1, cudaStreamNonBlocking));
+    CMDR_CUDA_CHECK(cudaStreamCreateWithFlags(&s2, cudaStreamNonBlocking));
+    cstreams[device] = {s1, s2};
+  }
+  cudaStream_t cin = cstreams[device].first, cout = cstreams[device].second;
+  double *abuf[2], *mbuf[2];
+  abuf[0] = static_cast<double *>(scratch_get("batch_alm0", sizeof(double) * (size_t)nalm_d * 3));
+  abuf[1] = static_cast<double *>(scratch_get("batch_alm1", sizeof(double) * (size_t)nalm_d * 3));
+  mbuf[0] = static_cast<double *>(scratch_get("batch_map0", sizeof(double) * (size_t)npix * 3));
+  mbuf[1] = static_cast<double *>(scratch_get("batch_map1", sizeof(double) * (size_t)npix * 3));
+  std::vector<cudaEvent_t> up(nbatch), done(nbatch), down(nbatch);
+  for (int b = 0; b < nbatch; ++b) {
+    CMDR_CUDA_CHECK(cudaEventCreateWithFlags(&up[b], cudaEventDisableTiming));
+    CMDR_CUDA_CHECK(cudaEventCreateWithFlags(&done[b], cudaEventDisableTiming));
+    CMDR_CUDA_CHECK(cudaEventCreateWithFlags(&down[b], cudaEventDisableTiming));
+  }
+  cudaEvent_t start;
+  CMDR_CUDA_CHECK(cudaEventCreateWithFlags(&start, cudaEventDisableTiming));
+  CMDR_CUDA_CHECK(cudaEventRecord(start, st));            // earlier work on `st` may still use the buffers
+  CMDR_CUDA_CHECK(cudaStreamWaitEvent(cin, start, 0));
+  CMDR_CUDA_CHECK(cudaStreamWaitEvent(cout, start, 0));
+  // inputs / outputs of one band
+  double **in_host = const_cast<double **>(synth ? alm3 : map3), **out_host = const_cast<double **>(synth ? map3 : alm3);
+  const long long nin = synth ? nalm_d : npix, nout = synth ? npix : nalm_d;
+  for (int b = 0; b < nbatch; ++b) {
+    const int s = b & 1;
+    double *in_dev = synth ? abuf[s] : mbuf[s], *out_dev = synth ? mbuf[s] : abuf[s];
+    // upload band b once the kernels of band b-2 no longer read this staging set
+    if (b >= 2) CMDR_CUDA_CHECK(cudaStreamWaitEvent(cin, done[b - 2], 0));
+    for (int c = 0; c < 3; ++c)
+      CMDR_CUDA_CHECK(cudaMemcpyAsync(in_dev + (size_t)c * nin, in_host[3 * b + c], sizeof(double) * nin, cudaMemcpyHostToDevice, cin));
+    if (add)   // accumulate into the caller's output: it has to come up too
+      for (int c = 0; c < 3; ++c)
+        CMDR_CUDA_CHECK(cudaMemcpyAsync(out_dev + (size_t)c * nout, out_host[3 * b + c], sizeof(double) * nout, cudaMemcpyHostToDevice, cin));
+    CMDR_CUDA_CHECK(cudaEventRecord(up[b], cin));
+    // kernels of band b: after its upload, and after the download of band b-2 released the output set
+    CMDR_CUDA_CHECK(cudaStreamWaitEvent(st, up[b], 0));
+    if (b >= 2) CMDR_CUDA_CHECK(cudaStreamWaitEvent(st, down[b - 2], 0));
+    double *ap[3], *mp[3];
+    for (int c = 0; c < 3; ++c) { ap[c] = abuf[s] + (size_t)c * nalm_d; mp[c] = mbuf[s] + (size_t)c * npix; }
+    run_single(type, 0, ap, mp, gT, a, flags, st);
+    run_single(type, 2, ap + 1, mp + 1, gP, a, flags, st);
+    CMDR_CUDA_CHECK(cudaEventRecord(done[b], st));
+    // download band b
+    CMDR_CUDA_CHECK(cudaStreamWaitEvent(cout, done[b], 0));
+    for (int c = 0; c < 3; ++c)
+      CMDR_CUDA_CHECK(cudaMemcpyAsync(out_host[3 * b + c], out_dev + (size_t)c * nout, sizeof(double) * nout, cudaMemcpyDeviceToHost, cout));
+    CMDR_CUDA_CHECK(cudaEventRecord(down[b], cout));
+  }
+  CMDR_CUDA_CHECK(cudaStreamSynchronize(cout));
+  CMDR_CUDA_CHECK(cudaStreamSynchronize(st));
+  for (int b = 0; b < nbatch; ++b) { cudaEventDestroy(up[b]); cudaEventDestroy(done[b]); cudaEventDestroy(down[b]); }
+  cudaEventDestroy(start);
+}
+
 unsigned long long cmdr_sht_launch_count(void) { return g_launches.load(); }
 void cmdr_sht_set_profiling(int on) { g_profiling = on; }
 int cmdr_sht_last_legendre_ms(double *entries3, int max) {

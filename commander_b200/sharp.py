@@ -32,7 +32,7 @@ ABI_SYMBOLS = [
     "sharp_destroy_alm_info", "sharp_make_subset_healpix_geom_info", "sharp_destroy_geom_info",
     "sharp_map_size", "sharp_execute", "sharp_execute_mpi_fortran",
     # part 2: additive
-    "cmdr_sht_version", "cmdr_sht_execute_dev", "cmdr_sht_execute_iqu", "cmdr_sht_get_unique_id",
+    "cmdr_sht_version", "cmdr_sht_execute_dev", "cmdr_sht_execute_iqu", "cmdr_sht_execute_iqu_batch", "cmdr_sht_get_unique_id",
     "cmdr_sht_comm_register", "cmdr_sht_comm_destroy", "cmdr_sht_execute_dist",
     "cmdr_sht_execute_iqu_dist", "cmdr_sht_allreduce_sum", "cmdr_sht_launch_count",
     "cmdr_sht_set_profiling", "cmdr_sht_last_legendre_ms", "cmdr_sht_nominal_flops",
@@ -65,6 +65,7 @@ def lib() -> C.CDLL:
     L.cmdr_sht_version.restype = ci
     L.cmdr_sht_execute_dev.argtypes = [ci, ci, vp, vp, vp, vp, ci, vp]
     L.cmdr_sht_execute_iqu.argtypes = [ci, vp, vp, vp, vp, vp, ci, vp]
+    L.cmdr_sht_execute_iqu_batch.argtypes = [ci, ci, vp, vp, vp, vp, vp, ci, vp]
     L.cmdr_sht_get_unique_id.argtypes = [vp]
     L.cmdr_sht_comm_register.argtypes = [ci, ci, ci, vp]
     L.cmdr_sht_comm_register.restype = ci
@@ -210,6 +211,29 @@ def execute_iqu(type, alm, map, geom_T: sharp_geom_info, geom_P: sharp_geom_info
                                     alm_info.handle, flags, st)
     else:
         L.cmdr_sht_execute_iqu(type, alm_ptr, map_ptr, geom_T.handle, geom_P.handle, alm_info.handle, flags, st)
+
+
+def execute_iqu_batch(type, alms, maps, geom_T: sharp_geom_info, geom_P: sharp_geom_info, alm_info: sharp_alm_info,
+                      add=False, stream=None):
+    """nbatch fused IQU transforms with shared handles (one per frequency band); alms / maps are
+    sequences of (3, n_alm) / (3, n_pix) arrays.  Host arrays are pipelined band against band."""
+    L = lib()
+    nb = len(alms)
+    if nb != len(maps):
+        raise ValueError("alms and maps must have the same length")
+    flags = SHARP_DP | (SHARP_ADD if add else 0)
+    aptr = (C.c_void_p * (3 * nb))()
+    mptr = (C.c_void_p * (3 * nb))()
+    keep = []
+    for b in range(nb):
+        pa, ka = _col_ptrs(alms[b], 3, alm_info.n_local)
+        pm, km = _col_ptrs(maps[b], 3, geom_T.n_local)
+        keep += [ka, km]
+        for c in range(3):
+            aptr[3 * b + c] = pa[c]
+            mptr[3 * b + c] = pm[c]
+    st = C.c_void_p(stream) if stream else None
+    L.cmdr_sht_execute_iqu_batch(type, nb, aptr, mptr, geom_T.handle, geom_P.handle, alm_info.handle, flags, st)
 
 
 def launch_count() -> int:

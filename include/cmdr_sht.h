@@ -106,6 +106,16 @@ void cmdr_sht_execute_iqu(int type, double *const *alm3, double *const *map3,
                           const sharp_geom_info *geom_T, const sharp_geom_info *geom_P,
                           const sharp_alm_info *alm_info, int flags, void *stream);
 
+/* nbatch independent IQU transforms sharing the handles: the per-band loop around comm_map%Y /
+ * %Yt / %YtW in cr_matmulA and the map updates (commander3/src/comm_cr_mod.f90:880-918; BASELINE
+ * config 5: 30 bands per Gibbs step).  alm3 / map3 hold 3*nbatch column pointers, band-major.
+ * With host buffers the bands are software-pipelined (upload of band b+1 and download of band b-1
+ * beside the kernels of band b; use pinned buffers for the full overlap); device pointers simply
+ * loop.  Single GPU. */
+void cmdr_sht_execute_iqu_batch(int type, int nbatch, double *const *alm3, double *const *map3,
+                                const sharp_geom_info *geom_T, const sharp_geom_info *geom_P,
+                                const sharp_alm_info *alm_info, int flags, void *stream);
+
 /* ---- multi-GPU (one process per GPU), libsharp-MPI layout: m's and ring pairs
  * round-robin per rank (commander3/src/comm_map_mod.f90:197-261), one
  * all-to-all of phases per transform. */
