@@ -64,7 +64,8 @@ def workload(args):
     return {"workload": f"comm_map Y+YtW pair, IQU, nside={args.nside} lmax={args.lmax}, synthetic Gaussian alm",
             "nside": args.nside, "lmax": args.lmax, "nmaps": 3,
             "l2_policy": "inputs larger than L2 (alm 0.38 GB, map 1.2 GB, phases 1.6 GB per direction)",
-            "parallelism": "m-distributed alm / ring-distributed map, NCCL all-to-all"}
+            "parallelism": "m-distributed alm / ring-distributed map; m<->ring exchange fused into the Legendre kernels over NVLink "
+                           "(NCCL all-to-all as fallback)"}
 
 
 # ------------------------------------------------------------------ CPU baseline / reference arm
