@@ -74,14 +74,22 @@ void ensure_alm_device(sharp_alm_info *a) {
   std::vector<int> m2im(a->mmax + 2, -1);
   for (int i = 0; i < a->nm; ++i) m2im[a->mval[i]] = i;
   a->d_m2im = upload(m2im);
-  std::vector<double> K0, K2;
-  build_start_norms(a->mmax < 0 ? 0 : a->mmax, K0, K2);
-  a->d_K0 = upload(K0);
-  a->d_K2 = upload(K2);
+}
+
+static const double *ensure_start_norms(sharp_alm_info *a, int spin) {
+  auto it = a->d_K.find(spin);
+  if (it != a->d_K.end()) return it->second;
+  const int mmax = a->mmax < 0 ? 0 : a->mmax;
+  std::vector<double> K0, K2, Ks;
+  if (spin == 0 || spin == 2) build_start_norms(mmax, K0, K2);
+  else build_start_norms_spin(mmax, spin, Ks);
+  double *d = upload(spin == 0 ? K0 : (spin == 2 ? K2 : Ks));
+  a->d_K[spin] = d;
+  return d;
 }
 
 void ensure_coef(sharp_alm_info *a, int spin) {
-  CoefDev &c = a->coef[spin ? 1 : 0];
+  CoefDev &c = a->coef[spin];
   if (c.ready) return;
   std::vector<double> tab; std::vector<long long> ofs;
   build_coef_table(a->lmax, spin, a->mval, tab, ofs);
@@ -258,8 +266,9 @@ void sharp_destroy_alm_info(sharp_alm_info *a) {
   if (!a) return;
   if (a->device >= 0) {
     forget_layout(a);
-    cudaFree(a->d_mval); cudaFree(a->d_mvstart); cudaFree(a->d_m2im); cudaFree(a->d_K0); cudaFree(a->d_K2);
-    for (int s = 0; s < 2; ++s) if (a->coef[s].ready) { cudaFree(a->coef[s].tab); cudaFree(a->coef[s].ofs); cudaFree(a->coef[s].tofs); }
+    cudaFree(a->d_mval); cudaFree(a->d_mvstart); cudaFree(a->d_m2im);
+    for (auto &kv : a->d_K) cudaFree(kv.second);
+    for (auto &kv : a->coef) if (kv.second.ready) { cudaFree(kv.second.tab); cudaFree(kv.second.ofs); cudaFree(kv.second.tofs); }
   }
   delete a;
 }
@@ -389,9 +398,10 @@ LegAlm make_legalm(sharp_alm_info *a, int spin) {
   LegAlm A;
   A.lmax = a->lmax; A.nm = a->nm; A.real_packed = a->real_packed ? 1 : 0;
   A.mval = a->d_mval; A.mvstart = a->d_mvstart;
-  A.coef = a->coef[spin ? 1 : 0].tab; A.cofs = a->coef[spin ? 1 : 0].ofs;
-  A.Kstart = spin ? a->d_K2 : a->d_K0;
-  A.tofs = a->coef[spin ? 1 : 0].tofs; A.trows = a->coef[spin ? 1 : 0].trows;
+  A.spin = spin;
+  A.coef = a->coef[spin].tab; A.cofs = a->coef[spin].ofs;
+  A.Kstart = ensure_start_norms(a, spin);
+  A.tofs = a->coef[spin].tofs; A.trows = a->coef[spin].trows;
   return A;
 }
 
@@ -399,7 +409,7 @@ LegAlm make_legalm(sharp_alm_info *a, int spin) {
 // handles components [comp0, comp0+ncomp) of it.
 static void run_single(int type, int spin, double *const *alm, double *const *map, sharp_geom_info *g,
                        sharp_alm_info *a, int flags, cudaStream_t st) {
-  if (!(spin == 0 || spin == 2)) { fprintf(stderr, "cmdr_sht: spin %d unsupported (0 or 2)\n", spin); abort(); }
+  if (spin < 0 || spin > CMDR_MAX_SPIN) { fprintf(stderr, "cmdr_sht: spin %d unsupported (0..%d)\n", spin, CMDR_MAX_SPIN); abort(); }
   if (type < 0 || type > 3) { fprintf(stderr, "cmdr_sht: job type %d unsupported\n", type); abort(); }
   if (flags & SHARP_NO_FFT) { fprintf(stderr, "cmdr_sht: SHARP_NO_FFT unsupported\n"); abort(); }
   const int ncomp = spin == 0 ? 1 : 2;
@@ -535,7 +545,7 @@ static bool try_pipelined(int type, int spin, double *const *alm, double *const 
                           sharp_alm_info *a, int flags, cudaStream_t st) {
   static const bool disabled = getenv("CMDR_SHT_NO_PIPELINE") != nullptr;
   const int ncomp = spin == 0 ? 1 : 2;
-  if (disabled || (flags & SHARP_ADD) || g->npix < (1 << 21) || a->nm == 0 || !(spin == 0 || spin == 2)) return false;
+  if (disabled || (flags & SHARP_ADD) || g->npix < (1 << 21) || a->nm == 0 || spin < 0 || spin > CMDR_MAX_SPIN) return false;
   if (type < 0 || type > 3) return false;
   for (int c = 0; c < ncomp; ++c) if (!is_pinned_host(alm[c]) || !is_pinned_host(map[c])) return false;
   static const int nchunks = getenv("CMDR_SHT_CHUNKS") ? atoi(getenv("CMDR_SHT_CHUNKS")) : 8;

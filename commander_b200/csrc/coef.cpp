@@ -115,4 +115,28 @@ void build_start_norms(int mmax, std::vector<double> &K0, std::vector<double> &K
   }
 }
 
+// Start-value normalisations for arbitrary spin s >= 1 (see legendre_core.cuh start_spin_s):
+//   m >= s: (+-s)lambda_{mm} = Ks[m] sth^(m-s) {sh^(2s), ch^(2s)}
+//           Ks[m] = (-1)^m sqrt((2m+1)/4pi) sqrt(prod_{k<=m}(2k-1)/(2k)) 2^s sqrt(prod_{i=1..s}(m-s+i)/(m+i))
+//   m <  s: (+s)lambda_{sm} = Ks[m] ch^(s-m) sh^(s+m),  (-s)lambda_{sm} = (-1)^(s-m) Ks[m] ch^(s+m) sh^(s-m)
+//           Ks[m] = (-1)^m sqrt((2s+1)/4pi) sqrt((2s)!/((s+m)!(s-m)!))
+void build_start_norms_spin(int mmax, int spin, std::vector<double> &Ks) {
+  Ks.assign(mmax + 1, 0.0);
+  const long double fourpi = 4.0L * acosl(-1.0L);
+  long double prod = 1.0L;   // prod_{k<=m} (2k-1)/(2k)
+  for (int m = 0; m <= mmax; ++m) {
+    if (m > 0) prod *= (2.0L * m - 1.0L) / (2.0L * m);
+    long double sg = (m & 1) ? -1.0L : 1.0L;
+    if (m >= spin) {
+      long double r = 1.0L;
+      for (int i = 1; i <= spin; ++i) r *= (long double)(m - spin + i) / (long double)(m + i);
+      Ks[m] = (double)(sg * sqrtl((2.0L * m + 1.0L) / fourpi * prod * r) * powl(2.0L, spin));
+    } else {
+      long double b = 1.0L;    // (2s)! / ((s+m)! (s-m)!) = binomial(2s, s+m)
+      for (int i = 1; i <= spin - m; ++i) b *= (long double)(spin + m + i) / (long double)i;
+      Ks[m] = (double)(sg * sqrtl((2.0L * spin + 1.0L) / fourpi * b));
+    }
+  }
+}
+
 }  // namespace cmdr

@@ -453,7 +453,7 @@ static void execute_dist_any(DistComm *C, int type, int nparts, const int *spins
   int c0 = 0;
   for (int i = 0; i < nparts; ++i) {
     int nc = spins[i] == 0 ? 1 : 2;
-    if (!(spins[i] == 0 || spins[i] == 2)) { fprintf(stderr, "cmdr_sht: spin %d unsupported\n", spins[i]); abort(); }
+    if (spins[i] < 0 || spins[i] > CMDR_MAX_SPIN) { fprintf(stderr, "cmdr_sht: spin %d unsupported\n", spins[i]); abort(); }
     parts[i] = Part{spins[i], c0, nc, geoms[i], sa.dev.data() + c0, sm.dev.data() + c0};
     c0 += nc;
   }

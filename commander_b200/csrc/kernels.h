@@ -11,6 +11,7 @@
 namespace cmdr {
 
 constexpr int CMDR_MAX_PEERS = 8;
+constexpr int CMDR_MAX_SPIN = 32;   // start values use plain powers sh^(2s), ch^(2s): fine in FP64 up to here
 
 void count_launch(int n = 1);
 
@@ -38,12 +39,13 @@ struct LegGeom {
 // alm side of the Legendre stage (local m's of this rank)
 struct LegAlm {
   int lmax = 0, nm = 0, real_packed = 1;
+  int spin = 0;                    // 0, or s >= 1 (two components; coefficient table and start norms of that spin)
   int im_begin = 0, im_end = -1;   // sub-range of local m's to process (-1: all)
   const int *mval = nullptr;
   const long long *mvstart = nullptr;
   const double *coef = nullptr;
   const long long *cofs = nullptr;
-  const double *Kstart = nullptr;  // K0 (spin 0) or K2 (spin 2), indexed by m
+  const double *Kstart = nullptr;  // start-value normalisation of this spin, indexed by m
   const long long *tofs = nullptr; // first synthesis tile row of each local m (rows padded to 8 per m)
   long long trows = 0;             // total tile rows
 };

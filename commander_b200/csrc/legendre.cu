@@ -31,6 +31,8 @@ static_assert(SCALE_BITS == 512, "SCALE_DOWN must equal 2^-SCALE_BITS");
 
 struct KParams {
   int lmax, nm, real_packed;
+  int spin;          // 0, or s >= 1 for the two-component kernels
+  double spinsign;   // sign of (+s)a = spinsign (E + iB): -1 for even s (HEALPix COSMO for s = 2), +1 for odd s
   int nslots, NPL, NML, ncomp_tot, comp0;
   int slot_begin;   // first slot handled by this launch (nslots = one past the last)
   int im0;          // first local m handled by this launch (grid.y counts from it)
@@ -244,7 +246,7 @@ __device__ __forceinline__ void synth2_group(const TileS2 *t, const double (&x)[
 
 __global__ void __launch_bounds__(256) prep_s2_kernel(KParams p) {
   const int im = p.im0 + blockIdx.y, m = p.mval[im];
-  const int l0 = max(m, 2);
+  const int l0 = max(m, p.spin);
   const int j = blockIdx.x * blockDim.x + threadIdx.x, l = l0 + j;
   const int npad = l0 <= p.lmax ? (p.lmax - l0 + 1 + 7) & ~7 : 0;
   if (j >= npad) return;
@@ -268,7 +270,9 @@ __global__ void __launch_bounds__(256) prep_s2_kernel(KParams p) {
       er = aE[2 * (mvs + l)]; br = aB[2 * (mvs + l)];
       if (m > 0) { ei = aE[2 * (mvs + l) + 1]; bi = aB[2 * (mvs + l) + 1]; }
     }
-    e.cpr = -gs * (er - bi); e.cpi = -gs * (ei + br);
+    // (+s)a = spinsign (E + iB), (-s)a = spinsign (-1)^s (E - iB) = -(E - iB); spinsign = -1 for even s
+    const double sgs = p.spinsign * gs;
+    e.cpr = sgs * (er - bi); e.cpi = sgs * (ei + br);
     e.cmr = -gs * (er + bi); e.cmi = -gs * (ei - br);
   }
   reinterpret_cast<TileS2 *>(p.trows)[p.tofs[im] + j] = e;
@@ -280,7 +284,7 @@ __global__ void __launch_bounds__(32, MINB) synth2_kernel(KParams p) {
   const int im = p.im0 + blockIdx.y, m = p.mval[im];
   const int lane = threadIdx.x;
   const int chunk0 = p.slot_begin + blockIdx.x * (32 * R);
-  const int l0 = max(m, 2);
+  const int l0 = max(m, p.spin);
   double x[R], P[R], Pp[R], M[R], Mp[R], a[R][8];
   int k[R], slot[R];
   bool any = false;
@@ -296,7 +300,7 @@ __global__ void __launch_bounds__(32, MINB) synth2_kernel(KParams p) {
       const double4 tg = reinterpret_cast<const double4 *>(p.trig)[slot[r]];
       RingTrig g{tg.x, tg.y, tg.z, tg.w};
       x[r] = g.cth;
-      start_spin2(m, K, g, P[r], M[r], k[r]);
+      if (p.spin == 2) start_spin2(m, K, g, P[r], M[r], k[r]); else start_spin_s(m, p.spin, K, g, P[r], M[r], k[r]);
       any = true;
     }
   }
@@ -721,7 +725,7 @@ __global__ void __launch_bounds__(32, MINB) anal2_kernel(KParams p) {
   const int im = p.im0 + blockIdx.y, m = p.mval[im];
   const int lane = threadIdx.x;
   const int chunk0 = p.slot_begin + blockIdx.x * (32 * R);
-  const int l0 = max(m, 2);
+  const int l0 = max(m, p.spin);
   if (l0 > p.lmax) return;
   double x[R], Pa[R], Pap[R], Pb[R], Pbp[R], w[R][8];
   int k[R];
@@ -742,7 +746,7 @@ __global__ void __launch_bounds__(32, MINB) anal2_kernel(KParams p) {
       RingTrig g{tg.x, tg.y, tg.z, tg.w};
       x[r] = g.cth;
       double P0, M0;
-      start_spin2(m, K, g, P0, M0, k[r]);
+      if (p.spin == 2) start_spin2(m, K, g, P0, M0, k[r]); else start_spin_s(m, p.spin, K, g, P0, M0, k[r]);
       Pa[r] = swapPM ? M0 : P0; Pb[r] = swapPM ? P0 : M0;
       double4 q = *ph_in(p, 0, im, slot), u = *ph_in(p, 1, im, slot);
       double z[8];
@@ -831,9 +835,10 @@ __global__ void __launch_bounds__(32, MINB) anal2_kernel(KParams p) {
       const int li = e >> 1, part = e & 1, l = lt + li;
       if (l <= p.lmax && (m > 0 || part == 0)) {
         const double4 v = reinterpret_cast<const double4 *>(red)[li];   // S1.re, S1.im, S2.re, S2.im
-        const double gs = T[li].g * nrm;
-        const double E = part ? -0.5 * gs * (v.y + v.w) : -0.5 * gs * (v.x + v.z);
-        const double B = part ? 0.5 * gs * (v.x - v.z) : -0.5 * gs * (v.y - v.w);
+        // adjoint of the synthesis combination: E = (sp S1 - S2)/2, B = -(i/2)(sp S1 + S2), sp = spinsign
+        const double gs = 0.5 * T[li].g * nrm, sp = p.spinsign;
+        const double E = part ? gs * (sp * v.y - v.w) : gs * (sp * v.x - v.z);
+        const double B = part ? -gs * (sp * v.x + v.z) : gs * (sp * v.y + v.w);
         const long long idx = p.real_packed ? (m == 0 ? mvs + l : mvs + 2 * (long long)l + part) : 2 * (mvs + l) + part;
         atomicAdd(&aE[idx], E);
         atomicAdd(&aB[idx], B);
@@ -856,6 +861,7 @@ static int env_int(const char *name, int dflt) {
 static KParams make_params(const LegGeom &g, const LegAlm &a, double *alm0, double *alm1, double4 *ph) {
   KParams p;
   p.lmax = a.lmax; p.nm = a.nm; p.real_packed = a.real_packed;
+  p.spin = a.spin; p.spinsign = (a.spin & 1) ? 1.0 : -1.0;
   p.slot_begin = g.slot_begin; p.nslots = g.slot_end >= 0 ? g.slot_end : g.nslots; p.NPL = g.NPL; p.NML = g.NML; p.ncomp_tot = g.ncomp_tot; p.comp0 = g.comp0;
   p.mval = a.mval; p.mvstart = a.mvstart; p.coef = a.coef; p.cofs = a.cofs; p.Kstart = a.Kstart;
   p.tofs = nullptr; p.trows = nullptr;

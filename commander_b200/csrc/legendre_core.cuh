@@ -106,6 +106,28 @@ CMDR_HD void start_spin2(int m, double K2m, const RingTrig &g, double &P, double
   }
 }
 
+// ---- arbitrary spin s >= 1 (conviqt: commander3/src/comm_conviqt_mod.f90:234-239) ---------------
+CMDR_HD double ipow(double b, int n) {      // b^n, n >= 0, by repeated squaring
+  double r = 1.0;
+  while (n) { if (n & 1) r *= b; b *= b; n >>= 1; }
+  return r;
+}
+// P = (+s)lambda_{l0,m}, M = (-s)lambda_{l0,m} at l0 = max(m,s); Ksm from build_start_norms_spin.
+// (+-s)lambda_lm(theta) = (-1)^m sqrt((2l+1)/4pi) d^l_{-m,+-s}(theta)   (Goldberg et al. 1967)
+CMDR_HD void start_spin_s(int m, int s, double Ksm, const RingTrig &g, double &P, double &M, int &k) {
+  if (m >= s) {
+    double mant; int ex;
+    pow_scaled(g.sth, m - s, mant, ex);
+    double base = Ksm * split_scale(mant, ex, k);
+    P = base * ipow(g.sh, 2 * s);
+    M = base * ipow(g.ch, 2 * s);
+  } else {
+    k = 0;
+    P = Ksm * ipow(g.ch, s - m) * ipow(g.sh, s + m);
+    M = (((s - m) & 1) ? -Ksm : Ksm) * ipow(g.ch, s + m) * ipow(g.sh, s - m);
+  }
+}
+
 // libsharp-style per-ring m cut-off (contributions above it are far below FP64
 // resolution).  Same form as the oracle's get_mlim.
 inline int mlim_for_ring(int lmax, int spin, double sth, double cth) {

@@ -13,6 +13,7 @@ namespace cmdr {
 void build_coef_table(int lmax, int spin, const std::vector<int> &mval, std::vector<double> &tab,
                       std::vector<long long> &ofs);
 void build_start_norms(int mmax, std::vector<double> &K0, std::vector<double> &K2);
+void build_start_norms_spin(int mmax, int spin, std::vector<double> &Ks);
 
 struct CoefDev {            // device copy of one (alm_info, spin) coefficient table
   bool ready = false;
@@ -44,8 +45,8 @@ struct sharp_alm_info {
   int *d_mval = nullptr;
   long long *d_mvstart = nullptr;
   int *d_m2im = nullptr;            // size mmax+1, -1 when m is not local
-  double *d_K0 = nullptr, *d_K2 = nullptr;
-  cmdr::CoefDev coef[2];            // [0] spin 0, [1] spin 2
+  std::map<int, double *> d_K;      // per spin: start-value normalisation per m
+  std::map<int, cmdr::CoefDev> coef; // per spin: coefficient table
   int device = -1;
 };
 

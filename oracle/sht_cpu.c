@@ -438,7 +438,7 @@ static void leg_anal0(int lmax, int m, const double *A, const double *B,
 
 /* --- spin s synthesis.  cp_l = -(E+iB)_l , cm_l = -(E-iB)_l  (complex, given re/im)
  *  A1 = sum cp P, A2 = sum cm M (north);  A3 = sum sg cp M, A4 = sum sg cm P (south),
- *  sg_l = (-1)^(l+m+s).  Output Q = (A1+A2)/2, U = -i (A1-A2)/2. */
+ *  sg_l = (-1)^(l+m).  Output Q = (A1+A2)/2, U = -i (A1-A2)/2. */
 static void leg_synths(int lmax, int m, int s, const double *A, const double *B, const double *C,
                        const double *cpr, const double *cpi, const double *cmr, const double *cmi,
                        int nb, const double *cth, const double *P0, const double *M0, const int *scale0,
@@ -456,7 +456,7 @@ static void leg_synths(int lmax, int m, int s, const double *A, const double *B,
   int nact = 0;
   for (int v = 0; v < NV2; ++v) nact += (sc[v] == 0);
   for (int l = l0; l <= lmax; ++l) {
-    const double sg = ((l + m + s) & 1) ? -1.0 : 1.0;
+    const double sg = ((l + m) & 1) ? -1.0 : 1.0;   /* (+s)lambda(pi-theta) = (-1)^(l+m) (-s)lambda(theta), any s */
     const double Al = A[l], Bl = B[l], Cl = C[l];
     const double c_pr = cpr[l], c_pi = cpi[l], c_mr = cmr[l], c_mi = cmi[l];
     if (nact == NV2) {
@@ -510,7 +510,7 @@ static void leg_synths(int lmax, int m, int s, const double *A, const double *B,
 
 /* --- spin s analysis.  zp = qQ + i qU, zm = qQ - i qU per ring.
  *  S1_l = sum_r P zpN + sg M zpS ; S2_l = sum_r M zmN + sg P zmS
- *  E_l = -(S1+S2)/2 ; B_l = (i/2)(S1-S2) */
+ *  even spin: E_l = -(S1+S2)/2 ; B_l = (i/2)(S1-S2) */
 static void leg_anals(int lmax, int m, int s, const double *A, const double *B, const double *C,
                       double *Er, double *Ei, double *Br, double *Bi,
                       int nb, const double *cth, const double *P0, const double *M0, const int *scale0,
@@ -532,7 +532,7 @@ static void leg_anals(int lmax, int m, int s, const double *A, const double *B, 
   int nact = 0;
   for (int v = 0; v < NV2; ++v) nact += (sc[v] == 0);
   for (int l = l0; l <= lmax; ++l) {
-    const double sg = ((l + m + s) & 1) ? -1.0 : 1.0;
+    const double sg = ((l + m) & 1) ? -1.0 : 1.0;   /* (+s)lambda(pi-theta) = (-1)^(l+m) (-s)lambda(theta), any s */
     const double Al = A[l], Bl = B[l], Cl = C[l];
     double s1r = 0, s1i = 0, s2r = 0, s2i = 0;
     if (nact == NV2) {
@@ -571,8 +571,10 @@ static void leg_anals(int lmax, int m, int s, const double *A, const double *B, 
             if (++sc[v] == 0) ++nact;
           }
     }
-    Er[l] += -0.5 * (s1r + s2r); Ei[l] += -0.5 * (s1i + s2i);
-    Br[l] += -0.5 * (s1i - s2i); Bi[l] += 0.5 * (s1r - s2r);
+    /* adjoint of (+s)a = sp (E + iB), (-s)a = -(E - iB):  E = (sp S1 - S2)/2,  B = (i/2)(-S2 - sp S1) */
+    const double sp = (s & 1) ? 1.0 : -1.0;
+    Er[l] += 0.5 * (sp * s1r - s2r); Ei[l] += 0.5 * (sp * s1i - s2i);
+    Br[l] += 0.5 * (sp * s1i + s2i); Bi[l] += 0.5 * (-s2r - sp * s1r);
   }
 }
 
@@ -617,7 +619,10 @@ int64_t osht_alm_count(int lmax, int nm, const int *ms) {
 int osht_execute(int type, int spin, int nside, int lmax,
                  int nrings, const int *rings, const double *weight,
                  int nm, const int *ms_in, double **alm, double **map, int add, int nthreads) {
-  if (!(spin == 0 || spin == 2)) return -1;
+  if (spin < 0 || spin > 32) return -1;
+  /* overall sign of the spin-s combination: -1 for even s (HEALPix COSMO convention at s = 2), +1 for odd s
+   * (libsharp2's sharp_Ylmgen_get_norm as remembered; unpinned for s != 2) */
+  const double ssg = (spin & 1) ? 1.0 : -1.0;
   if (type < 0 || type > 3) return -2;
   const int ncomp = spin == 0 ? 1 : 2;
   const int synth = (type == JOB_Y || type == JOB_WY);
@@ -743,8 +748,8 @@ int osht_execute(int type, int spin, int nside, int lmax,
             double er, ei, br, bi;
             if (m == 0) { er = aE[l]; ei = 0; br = aB[l]; bi = 0; }
             else { er = nrm * aE[2*(l-m)]; ei = nrm * aE[2*(l-m)+1]; br = nrm * aB[2*(l-m)]; bi = nrm * aB[2*(l-m)+1]; }
-            c0[l] = -(er - bi); c1[l] = -(ei + br);   /* cp = -(E + iB) */
-            c2[l] = -(er + bi); c3[l] = -(ei - br);   /* cm = -(E - iB) */
+            c0[l] = ssg * (er - bi); c1[l] = ssg * (ei + br);   /* (+s)a = ssg (E + iB), ssg = -1 for even spin */
+            c2[l] = -(er + bi); c3[l] = -(ei - br);             /* (-s)a = ssg (-1)^s (E - iB) = -(E - iB) */
           }
           for (int p = 0; p < pfirst; ++p)
             for (int c = 0; c < 2; ++c) for (int h = 0; h < 2; ++h) ph[PH(c,p,h,im)] = ph[PH(c,p,h,im)+1] = 0;

@@ -185,20 +185,25 @@ def Y_matrix(nside: int, lmax: int, spin: int, rings=None, ms=None, dps: int = 4
             else:
                 if l < spin:
                     continue
-                # (Q +- iU) = - sum_{l, all m} (aE_lm +- i aB_lm) (+-2)Y_lm,
-                # with a_{l,-m} = (-1)^m conj(a_lm).
+                # (Q +- iU) = ssg sum_{l, all m} (aE_lm +- i aB_lm) (+-s)Y_lm   (ssg = -1 for spin 2)
                 lp_p = float(slam(l, am, +spin, cth, sth))    # +2 lambda_{l,+m}
                 lm_p = float(slam(l, am, -spin, cth, sth))    # -2 lambda_{l,+m}
                 lp_n = float(slam(l, -am, +spin, cth, sth))   # +2 lambda_{l,-m}
                 lm_n = float(slam(l, -am, -spin, cth, sth))   # -2 lambda_{l,-m}
+                # (+s)a_lm = ssg (E + iB)_lm, (-s)a_lm = ssg (-1)^s (E - iB)_lm = -(E - iB)_lm, with
+                # a^X_{l,-m} = (-1)^m conj(a^X_lm) as for T: the two maps are real for every spin (this is the
+                # W/X formulation of HEALPix / libsharp2 written with complex coefficients).
+                # ssg = -1 for even spin (HEALPix COSMO at spin 2), +1 for odd spin (libsharp2's normalisation as
+                # recorded in SURVEY's appendix; unpinned for spin != 2).
                 sg = (-1) ** (am % 2)
+                ssg = 1.0 if (spin & 1) else -1.0
                 for comp_in, (cE, cB) in enumerate(((c, 0.0), (0.0, c))):
                     # positive-m term
-                    P = -(cE + 1j * cB) * lp_p * e       # contributes to Q+iU
-                    M = -(cE - 1j * cB) * lm_p * e       # contributes to Q-iU
+                    P = ssg * (cE + 1j * cB) * lp_p * e       # contributes to Q+iU
+                    M = -(cE - 1j * cB) * lm_p * e            # contributes to Q-iU
                     if am > 0:
                         cEn, cBn = sg * np.conj(cE), sg * np.conj(cB)
-                        P = P - (cEn + 1j * cBn) * lp_n * np.conj(e)
+                        P = P + ssg * (cEn + 1j * cBn) * lp_n * np.conj(e)
                         M = M - (cEn - 1j * cBn) * lm_n * np.conj(e)
                     Q = 0.5 * (P + M)
                     U = (P - M) / (2.0j)

@@ -11,14 +11,15 @@ extern "C" int emul_lambda(int spin, int lmax, int m, int nside, int north, doub
   std::vector<int> mval{m};
   std::vector<double> tab; std::vector<long long> ofs;
   build_coef_table(lmax, spin, mval, tab, ofs);
-  std::vector<double> K0, K2;
+  std::vector<double> K0, K2, Ks;
   build_start_norms(m, K0, K2);
+  if (spin != 0 && spin != 2) build_start_norms_spin(m, spin, Ks);
   long double omc, ns = nside;
   if (north < nside) omc = (long double)north * north / (3.0L * ns * ns);
   else omc = 1.0L - (2.0L * ns - north) * 2.0L / (3.0L * ns);
   RingTrig g{(double)(1.0L - omc), (double)sqrtl(omc * (2.0L - omc)), (double)sqrtl(0.5L * omc), (double)sqrtl(1.0L - 0.5L * omc)};
   const double SD = ldexp(1.0, -SCALE_BITS);
-  int l0 = spin == 0 ? m : (m > 2 ? m : 2);
+  int l0 = spin == 0 ? m : (m > spin ? m : spin);
   for (int l = 0; l <= lmax; ++l) { outP[l] = 0; if (outM) outM[l] = 0; }
   if (l0 > lmax) return 0;
   int k;
@@ -34,7 +35,7 @@ extern "C" int emul_lambda(int spin, int lmax, int m, int nside, int north, doub
     }
   } else {
     double P, M, Pp = 0, Mp = 0;
-    start_spin2(m, K2[m], g, P, M, k);
+    if (spin == 2) start_spin2(m, K2[m], g, P, M, k); else start_spin_s(m, spin, Ks[m], g, P, M, k);
     int cnt = 0;
     for (int l = l0; l <= lmax; ++l) {
       const double *c = &tab[4 * (l - l0)];

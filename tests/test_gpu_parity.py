@@ -403,3 +403,81 @@ def test_band_batch_api_matches_sequential(shtlib, cpu_oracle, pinned):
     refT = S.execute(S.Y, 0, nside, lmax, alm=alms[0, 0:1])
     refP = S.execute(S.Y, 2, nside, lmax, alm=alms[0, 1:3])
     assert rel(A[0].map[0:1], refT) <= TOL and rel(A[0].map[1:3], refP) <= TOL
+
+
+def _pixel_angles_ring(nside):
+    """theta, phi of every pixel in RING order (HEALPix geometry as in commander3/src/sharp.f90:145-166)."""
+    th, ph = [], []
+    for ring in range(1, 4 * nside):
+        north = 4 * nside - ring if ring > 2 * nside else ring
+        if north < nside:
+            cth = 1.0 - north * north / (3.0 * nside * nside)
+            nph = 4 * north
+            phi0 = np.pi / nph
+        else:
+            cth = (2 * nside - north) * 2.0 / (3.0 * nside)
+            nph = 4 * nside
+            phi0 = 0.0 if ((north - nside) & 1) else np.pi / nph
+        if ring != north:
+            cth = -cth
+        th.append(np.full(nph, np.arccos(cth)))
+        ph.append(phi0 + 2 * np.pi * np.arange(nph) / nph)
+    return np.concatenate(th), np.concatenate(ph)
+
+
+def test_closed_form_known_answers_large(shtlib):
+    """Closed forms whose signs the reference fixes, at nside 1024 / lmax 2048 (no oracle involved):
+    monopole, the dipole of commander3/src/comm_cmb_comp_mod.f90:145-156, and the spin-2 KATs of
+    SURVEY 8c-8 (a^E_20, a^B_20, complex a^E_22 = 1) in the HEALPix COSMO convention
+    (commander3/src/comm_map_mod.f90:1002)."""
+    from commander_b200 import comm_map, comm_mapinfo
+    nside, lmax = 1024, 2048
+    info = comm_mapinfo(None, nside, lmax, 3, True)
+    th, ph = _pixel_angles_ring(nside)
+    m = comm_map(info)
+    lm = {(int(l), int(mm)): i for i, (l, mm) in enumerate(zip(info.lm[0], info.lm[1]))}
+    # T: monopole + dipole d = (dx, dy, dz)
+    d = np.array([0.3, -1.1, 0.7])
+    m.alm[:] = 0.0
+    m.alm[0, lm[(0, 0)]] = 2.5
+    m.alm[0, lm[(1, 1)]] = -np.sqrt(4 * np.pi / 3) * d[0]
+    m.alm[0, lm[(1, 0)]] = np.sqrt(4 * np.pi / 3) * d[2]
+    m.alm[0, lm[(1, -1)]] = np.sqrt(4 * np.pi / 3) * d[1]
+    # E_20 = 1.5, B_20 = -0.5, complex E_22 = 1  (real-packed: alm[+2] = sqrt2)
+    m.alm[1, lm[(2, 0)]] = 1.5
+    m.alm[2, lm[(2, 0)]] = -0.5
+    m.alm[1, lm[(2, 2)]] = np.sqrt(2.0)
+    m.Y()
+    T = 2.5 / np.sqrt(4 * np.pi) + d[0] * np.sin(th) * np.cos(ph) + d[1] * np.sin(th) * np.sin(ph) + d[2] * np.cos(th)
+    k20 = -np.sqrt(15.0 / (32 * np.pi)) * np.sin(th) ** 2
+    Q = 1.5 * k20 - 0.25 * np.sqrt(5 / np.pi) * (1 + np.cos(th) ** 2) * np.cos(2 * ph)
+    U = -0.5 * k20 + 0.5 * np.sqrt(5 / np.pi) * np.cos(th) * np.sin(2 * ph)
+    assert rel(m.map[0], T) <= 1e-13
+    assert rel(m.map[1], Q) <= 1e-13
+    assert rel(m.map[2], U) <= 1e-13
+
+
+@pytest.mark.parametrize("nside,lmax", [(2, 9), (8, 16), (32, 64), (64, 200)])
+@pytest.mark.parametrize("spin", [1, 3, 5, 8])
+def test_arbitrary_spin_vs_oracle(shtlib, cpu_oracle, nside, lmax, spin):
+    """sharp_execute(SHARP_Y, j, 2, ...) as commander3/src/comm_conviqt_mod.f90:234-239 calls it for j up to bmax
+    (and the other three job types): (+-s)lambda of Goldberg et al., (+s)a = sgn (E+iB), (-s)a = -(E-iB),
+    sgn = -1 / +1 for even / odd s.  Parity unpinned for s != 2."""
+    sharp, S = shtlib, cpu_oracle
+    rng = np.random.default_rng(7000 * nside + 10 * lmax + spin)
+    w = rng.uniform(0.9, 1.1, 2 * nside)
+    ai, gi = _handles(sharp, nside, lmax, weight=w)
+    alm = rng.standard_normal((2, ai.n_local))
+    mp = rng.standard_normal((2, gi.n_local))
+    for job, name in ((sharp.SHARP_Y, "Y"), (sharp.SHARP_WY, "WY")):
+        out = np.full((2, gi.n_local), np.nan)
+        sharp.sharp_execute(job, spin, 2, alm.copy(), ai, out, gi)
+        ref = S.execute(job, spin, nside, lmax, alm=alm, weight=w)
+        assert rel(out, ref) <= TOL, (name, rel(out, ref))
+    for job, name in ((sharp.SHARP_Yt, "Yt"), (sharp.SHARP_YtW, "YtW")):
+        out = np.full((2, ai.n_local), np.nan)
+        sharp.sharp_execute(job, spin, 2, out, ai, mp.copy(), gi)
+        ref = S.execute(job, spin, nside, lmax, map=mp, weight=w)
+        assert rel(out, ref) <= TOL, (name, rel(out, ref))
+    sharp.sharp_destroy_alm_info(ai)
+    sharp.sharp_destroy_geom_info(gi)

@@ -124,6 +124,19 @@ def test_cpu_restatement_vs_dense(cpu_oracle, nside, lmax):
         assert rel(S.execute(S.Yt, spin, nside, lmax, map=mp), (Y.T @ mp.ravel()).reshape(nc, -1)) < 1e-13
 
 
+@pytest.mark.parametrize("spin", [1, 3, 4])
+def test_cpu_restatement_vs_dense_arbitrary_spin(cpu_oracle, spin):
+    """Spins other than 0 and 2 (conviqt path): the fast CPU restatement against the definitional matrices."""
+    S = cpu_oracle
+    nside, lmax = 4, 9
+    rng = np.random.default_rng(40 + spin)
+    Y = D.Y_matrix(nside, lmax, spin, dps=30)
+    alm = rng.standard_normal((2, S.alm_count(lmax)))
+    mp = rng.standard_normal((2, S.map_size(nside)))
+    assert rel(S.execute(S.Y, spin, nside, lmax, alm=alm), (Y @ alm.ravel()).reshape(2, -1)) < 1e-13
+    assert rel(S.execute(S.Yt, spin, nside, lmax, map=mp), (Y.T @ mp.ravel()).reshape(2, -1)) < 1e-13
+
+
 def test_cpu_restatement_scaled_range(cpu_oracle):
     """Large m near the poles exercises the 2^-800 rescaling; spin-0 columns are compared
     with the reference's own recurrence, mlim skipping with the unskipped result."""
