@@ -43,7 +43,8 @@ def gaussian_beam(lmax: int, fwhm_arcmin: float, nmaps: int = 3) -> np.ndarray:
 class cr_cmb_system:
     """One band, one component (CMB, F = 1) constrained-realisation system."""
 
-    def __init__(self, info: comm_mapinfo, siN, b_l: np.ndarray, Cl: np.ndarray, mask=None, mb_eff: float = 1.0):
+    def __init__(self, info: comm_mapinfo, siN, b_l: np.ndarray, Cl: np.ndarray, mask=None, mb_eff: float = 1.0,
+                 precond: str = "diagonal"):
         import torch
         self.torch = torch
         self.info = info
@@ -69,6 +70,18 @@ class cr_cmb_system:
         mean_invN = mean_invN / float(info.npix)
         invN_diag = mean_invN * float(info.npix) / (4.0 * math.pi)
         self.Minv = 1.0 / (1.0 + (self.sqrtS * self.bl) ** 2 * invN_diag[:, None])
+        # pseudo-inverse preconditioner (precond_type = 'pseudoinv')
+        if precond not in ("diagonal", "pseudoinv"):
+            raise ValueError("Preconditioner type not supported: " + precond)
+        self.precond = precond
+        # alpha_nu^2 = mean inverse noise variance in harmonic units (N%alpha_nu, :2293-2295): with it T / alpha^2 is
+        # O(1), which the pseudo-inverse needs (V = [alpha U; 1])
+        self.alpha2 = invN_diag[:, None]
+        U = self.sqrtS * self.bl * torch.sqrt(self.alpha2)
+        self.Uplus = U / (U * U + 1.0)
+        self.Pplus2 = 1.0 / (U * U + 1.0) ** 2
+        # N%N: sigma^2 per pixel; masked / unobserved pixels (N^-1 = 0) carry no information and are left out
+        self.N = torch.where(self.invN > 0, 1.0 / self.invN.clamp_min(1e-300), torch.zeros_like(self.invN))
         self.n_matmul = 0
 
     # -- communicator helpers
@@ -100,8 +113,26 @@ class cr_cmb_system:
         return x + m.alm
 
     def invM(self, r):
-        """cr_invM, :1026-1077 with the 'diagonal' preconditioner."""
+        """cr_invM, :1026-1077: 'diagonal' (default) or 'pseudoinv' preconditioner."""
+        if self.precond == "pseudoinv":
+            return self.invM_pseudoinv(r)
         return r * self.Minv
+
+    def invM_pseudoinv(self, r):
+        """applyDiffPrecond_pseudoinv, commander3/src/comm_diffuse_comp_mod.f90:2237-2380, for one band and one
+        component.  The system is A = V^T diag(T, 1) V with V = [U; 1], U = alpha b_l sqrt(C_l) per (l, pol) and
+        T = Y^T N^-1 Y / alpha^2; its pseudo-inverse preconditioner is V^+ diag(T^+, 1) V^+T with V^+ = [U, 1] / (U^2 + 1)
+        (the columns of P_cr%invM_diff, :1313-1557) and T^+ = alpha^2 YtW N WY (:2288-2292: `call invN_x%WY`,
+        `call data(k)%N%N(invN_x)`, `call invN_x%YtW`)."""
+        m = self.buf
+        m.alm.copy_(r)
+        m.alm.mul_(self.Uplus)                 # sum over (U^plus)^t, :2270-2285
+        m.WY()                                 # :2288
+        m.map.mul_(self.N)                     # N%N: noise covariance, :2290
+        m.YtW()                                # :2292
+        m.alm.mul_(self.alpha2)                # alpha_nu^2, :2293-2295
+        z = m.alm * self.Uplus                 # sum over U^plus, :2300-2315
+        return z + r * self.Pplus2             # prior terms, :2322-2346
 
     def computeRHS(self, data, eta_pix=None, eta_alm=None):
         """cr_computeRHS, :542-769: mean-field term, plus the two fluctuation terms when the white
