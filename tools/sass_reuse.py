@@ -267,6 +267,7 @@ def schedule_block(ins, blk, verbose=False, window=12, passes=6):
     wt_w = [first_wait(p, x.wbar) if not x.fp64 else p for p, x in enumerate(X)]
     wt_r = [first_wait(p, x.rbar) if not x.fp64 else p for p, x in enumerate(X)]
 
+    T_end = T[-1] + max(X[-1].stall, 1)
     mov = [p for p, x in enumerate(X) if x.fp64 and x.movable]
     if len(mov) < 4:
         return list(blk), {"lat": lat, "moved": 0, "cost": (0, 0)}
@@ -314,7 +315,14 @@ def schedule_block(ins, blk, verbose=False, window=12, passes=6):
                     else:
                         lo[q] = max(lo[q], wt_w[w] + 1)
             if q in movset and last_writer_of.get(r) == q:
-                hi[q] = min(hi[q], q)          # possibly live out of the block: never delayed
+                # possibly live out of the block (or loop carried): it may only be delayed as far as the last
+                # position that still leaves the full FP64 latency before the block ends -- whatever reads it in
+                # the successor block then sees it complete -- and never beyond where ptxas had it if that is later
+                lim = q
+                for pp in range(q + 1, npos):
+                    if T_end - T[pp] >= lat + 2:
+                        lim = pp
+                hi[q] = min(hi[q], lim)
     for q in mov:                             # barrier-like instructions are never crossed
         for f in fences:
             if f < q:
