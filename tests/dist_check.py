@@ -62,6 +62,21 @@ def main():
                 e2 = np.linalg.norm(out - refA[:, gidx]) / np.linalg.norm(refA[:, gidx])
                 worst = max(worst, e1, e2)
                 assert e1 <= 1e-10 and e2 <= 1e-10, (nside, lmax, fused, device, e1, e2)
+        # arbitrary spin through the distributed entry point (conviqt calls sharp_execute with comm=, spin=j)
+        if nside == 64:
+            for spin in (1, 3):
+                ref = S.execute(S.Y, spin, nside, lmax, alm=alm_g[1:3])
+                out = np.zeros((2, infow.np))
+                sharp.sharp_execute(sharp.SHARP_Y, spin, 2, np.ascontiguousarray(alm_g[1:3][:, gidx]), infow.alm_info, out,
+                                    infow.geom_info_T, comm=comm.handle)
+                e3 = np.linalg.norm(out - ref[:, infow.pix]) / np.linalg.norm(ref[:, infow.pix])
+                refa = S.execute(S.Yt, spin, nside, lmax, map=map_g[1:3])
+                outa = np.zeros((2, infow.nalm))
+                sharp.sharp_execute(sharp.SHARP_Yt, spin, 2, outa, infow.alm_info, np.ascontiguousarray(map_g[1:3][:, infow.pix]),
+                                    infow.geom_info_T, comm=comm.handle)
+                e4 = np.linalg.norm(outa - refa[:, gidx]) / np.linalg.norm(refa[:, gidx])
+                worst = max(worst, e3, e4)
+                assert e3 <= 1e-10 and e4 <= 1e-10, (spin, e3, e4)
         infow.dealloc()
     # CG dot-product all-reduce
     t = torch.full((3,), float(rank + 1), dtype=torch.float64, device=dev)
