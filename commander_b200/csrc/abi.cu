@@ -186,7 +186,7 @@ static void build_regions(sharp_geom_info *g) {
 }
 
 // Sub-geometry over parent pairs [a, b): same pixel offsets, own FFT regions / plans.
-static sharp_geom_info *make_subgeom(const sharp_geom_info *g, int a, int b) {
+sharp_geom_info *make_subgeom(const sharp_geom_info *g, int a, int b) {
   sharp_geom_info *s = new sharp_geom_info;
   s->nside = g->nside; s->nrings = 0; s->npix = g->npix; s->pair0 = a; s->npairs = b - a;
   auto cut = [&](auto &dst, const auto &src) { dst.assign(src.begin() + a, src.begin() + b); };
@@ -196,6 +196,19 @@ static sharp_geom_info *make_subgeom(const sharp_geom_info *g, int a, int b) {
   return s;
 }
 
+// True when the north rows (ascending) and the south rows (descending) of consecutive ring pairs are adjacent in the
+// map, so that any range of pairs is two plain memory ranges per component.
+bool pairs_contiguous(const sharp_geom_info *g) {
+  const int np = g->npairs;
+  for (int p = 0; p < np; ++p) {
+    if (g->ofsN[p] < 0) return false;
+    if (g->ofsS[p] < 0 && p != np - 1) return false;
+    if (p + 1 < np && g->ofsN[p + 1] != g->ofsN[p] + g->nph[p]) return false;
+    if (p + 1 < np && g->ofsS[p + 1] >= 0 && g->ofsS[p] != g->ofsS[p + 1] + g->nph[p + 1]) return false;
+  }
+  return np > 0;
+}
+
 // Splits the pairs into chunks of roughly equal pixel count whose north rings (ascending) and
 // south rings (descending) are each contiguous in the map, so that a chunk is two plain
 // memory ranges per component.  Leaves g->subs empty when the ring list does not allow that.
@@ -203,13 +216,7 @@ void ensure_subgeoms(sharp_geom_info *g, int nchunks) {
   if (g->subs_built) return;
   g->subs_built = true;
   const int np = g->npairs;
-  if (np < 1024) return;
-  for (int p = 0; p < np; ++p) {
-    if (g->ofsN[p] < 0) return;
-    if (g->ofsS[p] < 0 && p != np - 1) return;
-    if (p + 1 < np && g->ofsN[p + 1] != g->ofsN[p] + g->nph[p]) return;
-    if (p + 1 < np && g->ofsS[p + 1] >= 0 && g->ofsS[p] != g->ofsS[p + 1] + g->nph[p + 1]) return;
-  }
+  if (np < 1024 || !pairs_contiguous(g)) return;
   // chunk = a multiple of 512 ring pairs: the Legendre CTAs cover 256 or 512 pair slots, so
   // any other boundary would leave lanes idle in every CTA row of the chunk
   const int unit = 512;
@@ -476,13 +483,13 @@ void stage_out(Staged &s, long long count, cudaStream_t st) {
 // map rows of chunk c go D2H; analysis: H2D of chunk c+1 while chunk c is transformed and
 // accumulated into the a_lm).  Pageable buffers (the plain Fortran case) take the simple
 // staged path above; registering the arrays once with cudaHostRegister enables this one.
-static bool is_pinned_host(const void *p) {
+bool is_pinned_host(const void *p) {
   cudaPointerAttributes at;
   if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
   return at.type == cudaMemoryTypeHost;
 }
 
-static cudaStream_t copy_stream() {
+cudaStream_t copy_stream() {
   static std::map<int, cudaStream_t> cs;
   int dev = 0;
   CMDR_CUDA_CHECK(cudaGetDevice(&dev));
@@ -494,7 +501,7 @@ static cudaStream_t copy_stream() {
   return s;
 }
 
-static cudaEvent_t pooled_event(size_t i) {
+cudaEvent_t pooled_event(size_t i) {
   static std::vector<cudaEvent_t> pool;
   while (pool.size() <= i) {
     cudaEvent_t e;
@@ -505,7 +512,7 @@ static cudaEvent_t pooled_event(size_t i) {
 }
 
 // pixel ranges [begin, end) of a sub-geometry's northern and southern rows
-static void sub_ranges(const sharp_geom_info *s, long long &nb, long long &ne, long long &sb, long long &se) {
+void sub_ranges(const sharp_geom_info *s, long long &nb, long long &ne, long long &sb, long long &se) {
   const int n = s->npairs;
   nb = s->ofsN[0]; ne = s->ofsN[n - 1] + s->nph[n - 1];
   int last = n - 1;

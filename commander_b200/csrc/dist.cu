@@ -101,6 +101,13 @@ struct DistPlan {
   std::vector<double> h_sth, h_cth;         // per work index (0 for empty)
   std::vector<int> h_valid;
   int *d_m2src = nullptr, *d_m2im = nullptr, *d_mlist = nullptr, *d_mlist_src = nullptr, *d_mlist_im = nullptr;
+  // pinned-host pipeline: the valid work slots cut into chunks (multiples of 128 slots, the same on every
+  // rank) and, per chunk, this rank's local ring pairs in it (a contiguous range) as a sub-geometry
+  int nvalid = 0;
+  std::vector<int> wcut;                      // work-slot boundaries, size nchunk + 1
+  std::vector<int> lcut;                      // this rank's local pair boundaries, size nchunk + 1
+  std::vector<sharp_geom_info *> subs;        // per chunk (nullptr when this rank has no pair in it)
+  bool subs_built = false;
 };
 
 struct PeerBuf {                       // one receive buffer per rank, mapped by every rank
@@ -174,6 +181,22 @@ static DistPlan *get_plan(DistComm *C, sharp_geom_info *g, sharp_alm_info *a, cu
     P->h_sth[w] = (double)sn; P->h_cth[w] = (double)c; P->h_valid[w] = 1;
     wslot[w] = o.second; used[o.second] = 1;
     ++w;
+  }
+  P->nvalid = w;
+  {
+    const int K = 4;                                    // chunks per transform
+    int per = ((P->nvalid + K - 1) / K + 127) / 128 * 128;
+    if (per < 128) per = 128;
+    for (int b = 0; b < P->nvalid; b += per) P->wcut.push_back(b);
+    P->wcut.push_back(P->nvalid);
+    // my local pairs are sorted by ring number like the work order: the pairs of a chunk are a contiguous range
+    P->lcut.assign(P->wcut.size(), 0);
+    int mine = 0, ci = 1;
+    for (int wi = 0; wi < P->nvalid; ++wi) {
+      while (ci < (int)P->wcut.size() && wi >= P->wcut[ci]) P->lcut[ci++] = mine;
+      if (order[wi].second / NPL == C->rank) ++mine;
+    }
+    while (ci < (int)P->wcut.size()) P->lcut[ci++] = mine;
   }
   for (int s2 = 0; s2 < P->nslots; ++s2) if (!used[s2]) wslot[w++] = s2;   // padding slots: zero-filled, never read
   P->d_trig = upload_v(trig);
@@ -439,6 +462,111 @@ static void run_dist(DistComm *C, int type, const Part *parts, int nparts, int n
   }
 }
 
+// Host-buffer form of one distributed transform (one spin) with pinned caller arrays and the fused exchange:
+// the work slots are processed in chunks with one exchange barrier per chunk, so that the PCIe copy of the map
+// rows of chunk c runs beside the Legendre kernel of chunk c+-1 (synthesis: D2H after each chunk's FFT;
+// analysis: H2D ahead of each chunk's FFT).  Every rank walks the same chunks, so the barriers match.
+static bool try_dist_pipelined(DistComm *C, int type, int spin, double *const *alm, double *const *map,
+                               sharp_geom_info *g, sharp_alm_info *a, int flags, cudaStream_t st) {
+  static const bool disabled = getenv("CMDR_SHT_NO_PIPELINE") != nullptr;
+  const int ncomp = spin == 0 ? 1 : 2;
+  if (disabled || (flags & SHARP_ADD) || !use_p2p(C) || type < 0 || type > 3) return false;
+  // every rank must take the same decision: it depends only on properties that are equal on all ranks
+  // (global sizes) or that the caller keeps symmetric (pinned buffers on all ranks or on none)
+  if ((long long)g->nside * g->nside * 12 < (1LL << 20) * C->nranks) return false;
+  for (int c = 0; c < ncomp; ++c) if (!is_pinned_host(alm[c]) || !is_pinned_host(map[c])) return false;
+  if (g->npairs == 0 || a->nm == 0 || !pairs_contiguous(g)) return false;
+  const bool synth = (type == SHARP_Y || type == SHARP_WY);
+  ensure_geom_device(g);
+  ensure_alm_device(a);
+  DistPlan *P = get_plan(C, g, a, st);
+  const int K = (int)P->wcut.size() - 1;
+  if (!P->subs_built) {
+    P->subs_built = true;
+    for (int c = 0; c < K; ++c)
+      P->subs.push_back(P->lcut[c + 1] > P->lcut[c] ? make_subgeom(g, P->lcut[c], P->lcut[c + 1]) : nullptr);
+  }
+  const size_t cap = sizeof(double) * (size_t)3 * P->NML * P->NPL * 4 * C->nranks;
+  if (!(ensure_peerbuf(C, 0, cap, st) && ensure_peerbuf(C, 1, cap, st))) { C->p2p = 0; return false; }
+  const long long nalm_d = a->nalm * (a->real_packed ? 1 : 2);
+  double *alm_buf = static_cast<double *>(scratch_get("stage_alm", sizeof(double) * (size_t)nalm_d * ncomp));
+  double *map_buf = static_cast<double *>(scratch_get("stage_map", sizeof(double) * (size_t)g->npix * ncomp));
+  long long maxz = 0;
+  for (sharp_geom_info *sub : P->subs) if (sub) { ensure_geom_device(sub); maxz = std::max(maxz, sub->zlen_total); }
+  scratch_get("fftbuf", sizeof(double2) * (size_t)maxz * ncomp);
+  double *alm_dev[2], *map_dev[2];
+  for (int c = 0; c < ncomp; ++c) { alm_dev[c] = alm_buf + (size_t)c * nalm_d; map_dev[c] = map_buf + (size_t)c * g->npix; }
+  PhaseLayout L;
+  L.NPL = P->NPL; L.NML = P->NML; L.ncomp_tot = ncomp; L.comp0 = 0; L.mmax = P->mmax;
+  L.m2src = P->d_m2src; L.m2im = P->d_m2im; L.nm_total = P->nm_total;
+  L.mlist = P->d_mlist; L.mlist_src = P->d_mlist_src; L.mlist_im = P->d_mlist_im;
+  LegGeom G;
+  G.nslots = P->nslots; G.NPL = P->NPL; G.nowners = C->nranks; G.NML = P->NML; G.ncomp_tot = ncomp; G.comp0 = 0;
+  G.trig = P->d_trig; G.wslot = P->d_wslot; G.mlim = plan_mlim(P, a->lmax, spin);
+  PeerBuf &B = C->pb[synth ? 1 : 0];
+  G.npeer = C->nranks; G.src_rank = C->rank;
+  for (int r = 0; r < C->nranks; ++r) G.peer[r] = reinterpret_cast<double4 *>(B.peer[r]);
+  LegAlm A = make_legalm(a, spin);
+  cudaStream_t cs = copy_stream();
+  const size_t ev0 = 32;                                  // events 0..31 belong to the single-GPU pipeline
+  if (synth) {
+    for (int c = 0; c < ncomp; ++c)
+      CMDR_CUDA_CHECK(cudaMemcpyAsync(alm_dev[c], alm[c], sizeof(double) * nalm_d, cudaMemcpyHostToDevice, st));
+    stream_barrier(C, st);                                 // every rank has finished reading its buffer
+    for (int c = K - 1; c >= 0; --c) {                     // belt first, polar caps last
+      G.slot_begin = P->wcut[c]; G.slot_end = P->wcut[c + 1];
+      launch_legendre_synth(spin, G, A, alm_dev, reinterpret_cast<double4 *>(B.mine), st, c == K - 1);
+      stream_barrier(C, st);                               // chunk c has landed everywhere
+      sharp_geom_info *sub = P->subs[c];
+      if (!sub) continue;
+      L.pair0 = sub->pair0;
+      ringfft_synth(sub, ncomp, L, reinterpret_cast<double4 *>(B.mine), map_dev, type == SHARP_WY, false, st);
+      cudaEvent_t e = pooled_event(ev0 + c);
+      CMDR_CUDA_CHECK(cudaEventRecord(e, st));
+      CMDR_CUDA_CHECK(cudaStreamWaitEvent(cs, e, 0));
+      long long nb, ne, sb, se;
+      sub_ranges(sub, nb, ne, sb, se);
+      for (int k = 0; k < ncomp; ++k) {
+        CMDR_CUDA_CHECK(cudaMemcpyAsync(map[k] + nb, map_dev[k] + nb, sizeof(double) * (ne - nb), cudaMemcpyDeviceToHost, cs));
+        if (se > sb)
+          CMDR_CUDA_CHECK(cudaMemcpyAsync(map[k] + sb, map_dev[k] + sb, sizeof(double) * (se - sb), cudaMemcpyDeviceToHost, cs));
+      }
+    }
+    CMDR_CUDA_CHECK(cudaStreamSynchronize(cs));
+    CMDR_CUDA_CHECK(cudaStreamSynchronize(st));
+  } else {
+    cudaEvent_t e0 = pooled_event(ev0 + K);                // staging rows may still be read by earlier work on `st`
+    CMDR_CUDA_CHECK(cudaEventRecord(e0, st));
+    CMDR_CUDA_CHECK(cudaStreamWaitEvent(cs, e0, 0));
+    for (int c = 0; c < ncomp; ++c) CMDR_CUDA_CHECK(cudaMemsetAsync(alm_dev[c], 0, sizeof(double) * nalm_d, st));
+    stream_barrier(C, st);                                 // every rank has finished reading my buffer
+    for (int c = 0; c < K; ++c) {                          // polar chunks (short rows) first
+      sharp_geom_info *sub = P->subs[c];
+      if (sub) {
+        long long nb, ne, sb, se;
+        sub_ranges(sub, nb, ne, sb, se);
+        for (int k = 0; k < ncomp; ++k) {
+          CMDR_CUDA_CHECK(cudaMemcpyAsync(map_dev[k] + nb, map[k] + nb, sizeof(double) * (ne - nb), cudaMemcpyHostToDevice, cs));
+          if (se > sb)
+            CMDR_CUDA_CHECK(cudaMemcpyAsync(map_dev[k] + sb, map[k] + sb, sizeof(double) * (se - sb), cudaMemcpyHostToDevice, cs));
+        }
+        cudaEvent_t e = pooled_event(ev0 + c);
+        CMDR_CUDA_CHECK(cudaEventRecord(e, cs));
+        CMDR_CUDA_CHECK(cudaStreamWaitEvent(st, e, 0));
+        L.pair0 = sub->pair0;
+        ringfft_anal(sub, ncomp, L, reinterpret_cast<double4 *>(B.mine), map_dev, type == SHARP_YtW, st);
+      }
+      stream_barrier(C, st);                               // chunk c is complete on every rank
+      G.slot_begin = P->wcut[c]; G.slot_end = P->wcut[c + 1];
+      launch_legendre_anal(spin, G, A, alm_dev, reinterpret_cast<const double4 *>(B.mine), st);
+    }
+    for (int c = 0; c < ncomp; ++c)
+      CMDR_CUDA_CHECK(cudaMemcpyAsync(alm[c], alm_dev[c], sizeof(double) * nalm_d, cudaMemcpyDeviceToHost, st));
+    CMDR_CUDA_CHECK(cudaStreamSynchronize(st));
+  }
+  return true;
+}
+
 static void execute_dist_any(DistComm *C, int type, int nparts, const int *spins, double *const *alm,
                              double *const *map, sharp_geom_info *const *geoms, sharp_alm_info *a, int flags,
                              cudaStream_t st) {
@@ -447,6 +575,7 @@ static void execute_dist_any(DistComm *C, int type, int nparts, const int *spins
   int ncomp_tot = 0;
   for (int i = 0; i < nparts; ++i) ncomp_tot += spins[i] == 0 ? 1 : 2;
   const long long nalm_d = a->nalm * (a->real_packed ? 1 : 2);
+  if (nparts == 1 && try_dist_pipelined(C, type, spins[0], alm, map, geoms[0], a, flags, st)) return;
   Staged sa = stage_in("stage_alm", alm, ncomp_tot, nalm_d, synth || add, st);
   Staged sm = stage_in("stage_map", map, ncomp_tot, geoms[0]->npix, !synth || add, st);
   Part parts[4];
@@ -497,6 +626,7 @@ void cmdr_sht_comm_destroy(int comm) {
     cudaFree(P->d_trig); cudaFree(P->d_wslot); cudaFree(P->d_m2src); cudaFree(P->d_m2im); cudaFree(P->d_mlist);
     cudaFree(P->d_mlist_src); cudaFree(P->d_mlist_im);
     for (auto &m : P->d_mlim) cudaFree(m.second);
+    for (sharp_geom_info *sub : P->subs) if (sub) sharp_destroy_geom_info(sub);
     delete P;
   }
   close_peerbuf(C, C->pb[0]); close_peerbuf(C, C->pb[1]);

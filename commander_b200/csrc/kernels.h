@@ -92,6 +92,13 @@ extern thread_local int g_profiling;
 void prof_begin(int spin, int dir, cudaStream_t st);
 void prof_end(cudaStream_t st);
 void prof_collect();
+// pinned-host pipelining helpers (abi.cu), shared with the distributed path
+sharp_geom_info *make_subgeom(const sharp_geom_info *g, int a, int b);
+bool pairs_contiguous(const sharp_geom_info *g);
+void sub_ranges(const sharp_geom_info *s, long long &nb, long long &ne, long long &sb, long long &se);
+bool is_pinned_host(const void *p);
+cudaStream_t copy_stream();
+cudaEvent_t pooled_event(size_t i);
 struct Staged {
   std::vector<double *> dev;
   std::vector<double *> host;

@@ -78,6 +78,33 @@ def main():
                 worst = max(worst, e3, e4)
                 assert e3 <= 1e-10 and e4 <= 1e-10, (spin, e3, e4)
         infow.dealloc()
+    # pinned host buffers at a size where the chunked pipeline (per-chunk exchange barriers, PCIe copies beside
+    # the Legendre kernels) is taken
+    nside, lmax = 512, 767
+    info = comm_mapinfo(comm, nside, lmax, 3, True)
+    rng = np.random.default_rng(4321)
+    alm_g = rng.standard_normal((3, (lmax + 1) ** 2))
+    map_g = rng.standard_normal((3, 12 * nside ** 2))
+    mstart = np.zeros(lmax + 2, dtype=np.int64)
+    for m in range(lmax + 1):
+        mstart[m + 1] = mstart[m] + (lmax + 1 - m) * (1 if m == 0 else 2)
+    l, mm = info.lm[0].astype(np.int64), info.lm[1].astype(np.int64)
+    am = np.abs(mm)
+    gidx = mstart[am] + np.where(am == 0, l, 2 * (l - am) + (mm < 0))
+    m = comm_map(info)
+    m.alm = torch.empty((3, info.nalm), dtype=torch.float64).pin_memory().numpy()
+    m.map = torch.empty((3, info.np), dtype=torch.float64).pin_memory().numpy()
+    m.alm[:] = alm_g[:, gidx]
+    m.Y()
+    refY = np.concatenate([S.execute(S.Y, 0, nside, lmax, alm=alm_g[0:1]), S.execute(S.Y, 2, nside, lmax, alm=alm_g[1:3])])
+    e1 = np.linalg.norm(m.map - refY[:, info.pix]) / np.linalg.norm(refY[:, info.pix])
+    m.map[:] = map_g[:, info.pix]
+    m.Yt()
+    refA = np.concatenate([S.execute(S.Yt, 0, nside, lmax, map=map_g[0:1]), S.execute(S.Yt, 2, nside, lmax, map=map_g[1:3])])
+    e2 = np.linalg.norm(m.alm - refA[:, gidx]) / np.linalg.norm(refA[:, gidx])
+    worst = max(worst, e1, e2)
+    assert e1 <= 1e-10 and e2 <= 1e-10, ("pinned pipelined", e1, e2)
+    info.dealloc()
     # CG dot-product all-reduce
     t = torch.full((3,), float(rank + 1), dtype=torch.float64, device=dev)
     comm.allreduce_sum_(t)
