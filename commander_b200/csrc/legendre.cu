@@ -4,17 +4,19 @@
 // commander3/src/sharp.f90:226-240) for the job types of commander3/src/sharp.f90:8-14:
 //   synthesis (SHARP_Y, SHARP_WY):   ph[m][ring] = sum_l a_lm lambda_lm(theta_ring)
 //   analysis  (SHARP_Yt, SHARP_YtW): a_lm       = sum_ring lambda_lm(theta_ring) ph[m][ring]
-// for spin 0 (T) and spin 2 (Q,U <-> E,B; HEALPix "COSMO" convention,
-// commander3/src/comm_map_mod.f90:1002).
+// for spin 0 (T), spin 2 (Q,U <-> E,B; HEALPix "COSMO" convention,
+// commander3/src/comm_map_mod.f90:1002) and any other spin up to CMDR_MAX_SPIN
+// (commander3/src/comm_conviqt_mod.f90:234-239).
 //
-// Work decomposition: grid = (ring-pair chunks, local m).  A thread owns R ring pairs
-// (north ring + its southern mirror share one recurrence through the l+m parity), runs
-// the recurrence in registers over l, and reads per-l data (recurrence coefficients and,
-// for synthesis, the pre-scaled a_lm) as warp-uniform broadcasts from a shared-memory
-// tile of TL consecutive l.  FP64-pipe cost per (l, m, ring pair):
-//   spin 0: 2 (recurrence) + 2 (accumulate) ; spin 2: 4 + 8.
-// Analysis reduces over rings with a register butterfly (reduce-scatter over the l of a
-// group, then all-reduce) and one shared-memory hop across the warps of the CTA.
+// Work decomposition: grid = (ring-pair chunks, local m), ONE WARP PER CTA, no block-level
+// synchronisation.  A thread owns R adjacent ring pairs (north ring + its southern mirror
+// share one recurrence through the l+m parity), runs the recurrence in registers over l, and
+// reads per-l data (recurrence coefficients and, for synthesis, the pre-scaled a_lm) as
+// warp-uniform broadcasts from a shared-memory tile of TL consecutive l that the warp stages
+// itself with cp.async.  FP64-pipe cost per (l, m, ring pair):
+//   spin 0: 2 (recurrence) + 2 (accumulate) ; spin s: 4 + 8.
+// Analysis reduces over the rings of the warp with a select-free, software-pipelined register
+// butterfly and adds the sums to the a_lm with coalesced atomics.
 #include <cstdio>
 #include <cstdlib>
 
