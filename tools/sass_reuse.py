@@ -26,11 +26,13 @@ Safety rules (all conservative):
 usage: sass_reuse.py file.o [--kernels substr,substr] [--dry] [--min-fp64 24] [-v]
 Patches file.o in place (unless --dry) and prints the estimated FP64 issue cycles before/after.
 
-STATUS (round 1): EXPERIMENTAL, NOT PART OF THE BUILD.  On the current kernels the estimated gain is 1-4 %
-(synth2 R=2: 2.52 -> 2.39 cycles/DFMA in the steady block; analysis loops ~1 %): ptxas recycles the
-coefficient registers so quickly that false (WAR/WAW) dependences and loop-carried values pin most
-instructions.  Kept as the starting point for a loop-aware version; the patched object has not been
-run on a GPU and must pass the full parity suite before anyone enables it.
+STATUS (round 1): EXPERIMENTAL, NOT PART OF THE BUILD.  The patched library passes the whole GPU parity suite
+(57 tests), i.e. the dependence / scoreboard rules above are sound on these kernels, but it is NOT faster: the
+operand-fetch model predicts 1-4 % fewer FP64 issue cycles (false WAR/WAW dependences from ptxas's register
+recycling and loop-carried values pin most instructions), and on the B200 synth2 ran 4 % slower, anal2 0.4 %
+faster (gpurun log run 38).  The fetch model of tools/ubench/ubench3.cu is therefore incomplete for mixed
+instruction streams (bank effects of the swapped multiplicands and yield/reuse interplay are the suspects).
+Kept as the starting point for a loop-aware, measurement-calibrated version.
 """
 import argparse
 import re
