@@ -501,6 +501,21 @@ cudaStream_t copy_stream() {
   return s;
 }
 
+// second compute stream: consecutive m-chunk launches of the pipelined path alternate between the caller's
+// stream and this one, so that the next launch fills the SMs the previous one leaves idle while it drains
+// (an m-chunk launch is only ~2 waves of CTAs of similar length)
+static cudaStream_t aux_stream() {
+  static std::map<int, cudaStream_t> as;
+  int dev = 0;
+  CMDR_CUDA_CHECK(cudaGetDevice(&dev));
+  auto it = as.find(dev);
+  if (it != as.end()) return it->second;
+  cudaStream_t s;
+  CMDR_CUDA_CHECK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+  as[dev] = s;
+  return s;
+}
+
 cudaEvent_t pooled_event(size_t i) {
   static std::vector<cudaEvent_t> pool;
   while (pool.size() <= i) {
@@ -555,6 +570,31 @@ static bool try_pipelined(int type, int spin, double *const *alm, double *const 
   if (disabled || (flags & SHARP_ADD) || g->npix < (1 << 21) || a->nm == 0 || spin < 0 || spin > CMDR_MAX_SPIN) return false;
   if (type < 0 || type > 3) return false;
   for (int c = 0; c < ncomp; ++c) if (!is_pinned_host(alm[c]) || !is_pinned_host(map[c])) return false;
+  static const bool nocopy = getenv("CMDR_SHT_PIPE_NOCOPY") != nullptr;   // tuning aid: time the chunked kernels alone (results are garbage)
+#define PIPE_COPY(...) do { if (!nocopy) CMDR_CUDA_CHECK(cudaMemcpyAsync(__VA_ARGS__)); } while (0)
+  // tuning aid: CMDR_SHT_PIPE_TRACE=1 prints a timeline (ms since the call started) of the stream markers below
+  static const bool trace = getenv("CMDR_SHT_PIPE_TRACE") != nullptr;
+  std::vector<std::pair<std::string, cudaEvent_t>> marks;
+  auto mark = [&](const char *what, int i, cudaStream_t s) {
+    if (!trace) return;
+    cudaEvent_t e;
+    CMDR_CUDA_CHECK(cudaEventCreate(&e));
+    CMDR_CUDA_CHECK(cudaEventRecord(e, s));
+    marks.emplace_back(std::string(what) + " " + std::to_string(i), e);
+  };
+  auto dump_marks = [&]() {
+    if (!trace) return;
+    fprintf(stderr, "[cmdr_sht pipe] type %d spin %d:", type, spin);
+    for (size_t k = 1; k < marks.size(); ++k) {
+      float ms = 0;
+      cudaEventElapsedTime(&ms, marks[0].second, marks[k].second);
+      fprintf(stderr, " %s@%.2f", marks[k].first.c_str(), ms);
+    }
+    fprintf(stderr, "\n");
+    for (auto &m : marks) cudaEventDestroy(m.second);
+  };
+  static const bool two_streams = !(getenv("CMDR_SHT_TWO_STREAMS") && atoi(getenv("CMDR_SHT_TWO_STREAMS")) == 0);
+  static const int njoint = getenv("CMDR_SHT_JOINT") ? std::max(1, atoi(getenv("CMDR_SHT_JOINT"))) : 2;
   static const int nchunks = getenv("CMDR_SHT_CHUNKS") ? atoi(getenv("CMDR_SHT_CHUNKS")) : 8;
   ensure_subgeoms(g, nchunks);
   if (g->subs.empty()) return false;
@@ -576,17 +616,18 @@ static bool try_pipelined(int type, int spin, double *const *alm, double *const 
   PhaseLayout L = single_layout(a, g->npairs, ncomp, 0);
   cudaStream_t cs = copy_stream();
   const int ns = (int)g->subs.size();
+  mark("start", 0, st);
   if (synth) {
     // a_lm upload in NMCH chunks of local m's (the packed columns of consecutive m's are contiguous): the
     // first ring-pair chunk runs its Legendre kernel m-chunk by m-chunk as the data lands, so only the
     // first quarter of the upload is exposed.  Falls back to one copy for layouts that are not dense.
-    static const int NMCH = getenv("CMDR_SHT_MCHUNKS") ? std::max(1, std::min(16, atoi(getenv("CMDR_SHT_MCHUNKS")))) : 4;
+    static const int NMCH = getenv("CMDR_SHT_MCHUNKS") ? std::max(1, std::min(16, atoi(getenv("CMDR_SHT_MCHUNKS")))) : 8;
     std::vector<long long> mstart;
     std::vector<int> mcut;
     const int nmch = alm_m_chunks(a, nalm_d, NMCH, mstart, mcut) ? NMCH : 1;
     if (nmch == 1) {
       for (int c = 0; c < ncomp; ++c)
-        CMDR_CUDA_CHECK(cudaMemcpyAsync(alm_dev[c], alm[c], sizeof(double) * nalm_d, cudaMemcpyHostToDevice, st));
+        PIPE_COPY(alm_dev[c], alm[c], sizeof(double) * nalm_d, cudaMemcpyHostToDevice, st);
     } else {
       cudaEvent_t e0 = pooled_event(ns + 1);               // earlier work on `st` may still read the staging buffer
       CMDR_CUDA_CHECK(cudaEventRecord(e0, st));
@@ -594,40 +635,63 @@ static bool try_pipelined(int type, int spin, double *const *alm, double *const 
       for (int j = 0; j < nmch; ++j) {
         const long long b = mstart[mcut[j]], e = mstart[mcut[j + 1]];
         for (int c = 0; c < ncomp; ++c)
-          if (e > b) CMDR_CUDA_CHECK(cudaMemcpyAsync(alm_dev[c] + b, alm[c] + b, sizeof(double) * (e - b), cudaMemcpyHostToDevice, cs));
+          if (e > b) PIPE_COPY(alm_dev[c] + b, alm[c] + b, sizeof(double) * (e - b), cudaMemcpyHostToDevice, cs);
         CMDR_CUDA_CHECK(cudaEventRecord(pooled_event(ns + 2 + j), cs));
+        mark("up", j, cs);
       }
     }
-    for (int i = ns - 1; i >= 0; --i) {          // belt (large rows) first, polar caps last
+    // The first `nj` ring-pair chunks share the m-chunked start: per m-chunk the Legendre kernels of all of
+    // them run before the next m-chunk is needed, so the a_lm upload (4.7 ms for spin 2 at lmax 4000) hides
+    // behind nj chunks of compute instead of one.
+    const int nj = nmch > 1 ? std::min(njoint, ns) : 1;
+    auto finish_chunk = [&](int i) {
       sharp_geom_info *sub = g->subs[i];
-      G.slot_begin = sub->pair0; G.slot_end = sub->pair0 + sub->npairs;
-      if (i == ns - 1 && nmch > 1) {
-        for (int j = 0; j < nmch; ++j) {
-          CMDR_CUDA_CHECK(cudaStreamWaitEvent(st, pooled_event(ns + 2 + j), 0));
-          LegAlm Aj = A;
-          Aj.im_begin = mcut[j]; Aj.im_end = mcut[j + 1];
-          launch_legendre_synth(spin, G, Aj, alm_dev, ph, st, true);
-        }
-      } else {
-        launch_legendre_synth(spin, G, A, alm_dev, ph, st, i == ns - 1);   // a_lm rows prepared once
-      }
       L.pair0 = sub->pair0;
+      mark("leg", i, st);
       ringfft_synth(sub, ncomp, L, ph, map_dev, type == SHARP_WY, false, st);
+      mark("fft", i, st);
       cudaEvent_t e = pooled_event(i);
       CMDR_CUDA_CHECK(cudaEventRecord(e, st));
       CMDR_CUDA_CHECK(cudaStreamWaitEvent(cs, e, 0));
       long long nb, ne, sb, se;
       sub_ranges(sub, nb, ne, sb, se);
       for (int c = 0; c < ncomp; ++c) {
-        CMDR_CUDA_CHECK(cudaMemcpyAsync(map[c] + nb, map_dev[c] + nb, sizeof(double) * (ne - nb), cudaMemcpyDeviceToHost, cs));
+        PIPE_COPY(map[c] + nb, map_dev[c] + nb, sizeof(double) * (ne - nb), cudaMemcpyDeviceToHost, cs);
         if (se > sb)
-          CMDR_CUDA_CHECK(cudaMemcpyAsync(map[c] + sb, map_dev[c] + sb, sizeof(double) * (se - sb), cudaMemcpyDeviceToHost, cs));
+          PIPE_COPY(map[c] + sb, map_dev[c] + sb, sizeof(double) * (se - sb), cudaMemcpyDeviceToHost, cs);
       }
+      mark("down", i, cs);
+    };
+    if (nmch > 1) {
+      cudaStream_t as = two_streams ? aux_stream() : st;
+      if (as != st) CMDR_CUDA_CHECK(cudaStreamWaitEvent(as, pooled_event(ns + 1), 0));   // e0: earlier work on st
+      for (int j = 0; j < nmch; ++j) {
+        cudaStream_t sj = (j & 1) ? as : st;
+        CMDR_CUDA_CHECK(cudaStreamWaitEvent(sj, pooled_event(ns + 2 + j), 0));
+        LegAlm Aj = A;
+        Aj.im_begin = mcut[j]; Aj.im_end = mcut[j + 1];
+        // one launch over the merged slot range of the first nj chunks (consecutive ring pairs; belt first)
+        G.slot_begin = g->subs[ns - nj]->pair0; G.slot_end = g->subs[ns - 1]->pair0 + g->subs[ns - 1]->npairs;
+        launch_legendre_synth(spin, G, Aj, alm_dev, ph, sj, true);
+        mark("legm", j, sj);
+      }
+      if (as != st) {
+        cudaEvent_t ea = pooled_event(ns + 20);
+        CMDR_CUDA_CHECK(cudaEventRecord(ea, as));
+        CMDR_CUDA_CHECK(cudaStreamWaitEvent(st, ea, 0));
+      }
+      for (int i = ns - 1; i >= ns - nj; --i) finish_chunk(i);
+    }
+    for (int i = (nmch > 1 ? ns - nj : ns) - 1; i >= 0; --i) {
+      sharp_geom_info *sub = g->subs[i];
+      G.slot_begin = sub->pair0; G.slot_end = sub->pair0 + sub->npairs;
+      launch_legendre_synth(spin, G, A, alm_dev, ph, st, nmch == 1 && i == ns - 1);
+      finish_chunk(i);
     }
     CMDR_CUDA_CHECK(cudaStreamSynchronize(cs));
     CMDR_CUDA_CHECK(cudaStreamSynchronize(st));
   } else {
-    static const int NMCH = getenv("CMDR_SHT_MCHUNKS") ? std::max(1, std::min(16, atoi(getenv("CMDR_SHT_MCHUNKS")))) : 4;
+    static const int NMCH = getenv("CMDR_SHT_MCHUNKS") ? std::max(1, std::min(16, atoi(getenv("CMDR_SHT_MCHUNKS")))) : 8;
     std::vector<long long> mstart;
     std::vector<int> mcut;
     const int nmch = alm_m_chunks(a, nalm_d, NMCH, mstart, mcut) ? NMCH : 1;
@@ -636,46 +700,62 @@ static bool try_pipelined(int type, int spin, double *const *alm, double *const 
     CMDR_CUDA_CHECK(cudaEventRecord(e0, st));
     CMDR_CUDA_CHECK(cudaStreamWaitEvent(cs, e0, 0));
     for (int c = 0; c < ncomp; ++c) CMDR_CUDA_CHECK(cudaMemsetAsync(alm_dev[c], 0, sizeof(double) * nalm_d, st));
+    const int nj = nmch > 1 ? std::min(njoint, ns) : 1;
     for (int i = 0; i < ns; ++i) {               // small polar chunks first so compute starts early
       sharp_geom_info *sub = g->subs[i];
       long long nb, ne, sb, se;
       sub_ranges(sub, nb, ne, sb, se);
       for (int c = 0; c < ncomp; ++c) {
-        CMDR_CUDA_CHECK(cudaMemcpyAsync(map_dev[c] + nb, map[c] + nb, sizeof(double) * (ne - nb), cudaMemcpyHostToDevice, cs));
+        PIPE_COPY(map_dev[c] + nb, map[c] + nb, sizeof(double) * (ne - nb), cudaMemcpyHostToDevice, cs);
         if (se > sb)
-          CMDR_CUDA_CHECK(cudaMemcpyAsync(map_dev[c] + sb, map[c] + sb, sizeof(double) * (se - sb), cudaMemcpyHostToDevice, cs));
+          PIPE_COPY(map_dev[c] + sb, map[c] + sb, sizeof(double) * (se - sb), cudaMemcpyHostToDevice, cs);
       }
       cudaEvent_t e = pooled_event(i);
       CMDR_CUDA_CHECK(cudaEventRecord(e, cs));
+      mark("up", i, cs);
       CMDR_CUDA_CHECK(cudaStreamWaitEvent(st, e, 0));
       L.pair0 = sub->pair0;
       ringfft_anal(sub, ncomp, L, ph, map_dev, type == SHARP_YtW, st);
+      mark("fft", i, st);
       G.slot_begin = sub->pair0; G.slot_end = sub->pair0 + sub->npairs;
-      if (i == ns - 1 && nmch > 1) {
-        // last ring-pair chunk: m-chunk by m-chunk, so that the finished a_lm columns go back to the host
-        // while the next m-chunk is still being accumulated (only the last quarter of the download is exposed)
-        for (int j = 0; j < nmch; ++j) {
-          LegAlm Aj = A;
-          Aj.im_begin = mcut[j]; Aj.im_end = mcut[j + 1];
-          launch_legendre_anal(spin, G, Aj, alm_dev, ph, st);
-          cudaEvent_t e = pooled_event(ns + 2 + j);
-          CMDR_CUDA_CHECK(cudaEventRecord(e, st));
-          CMDR_CUDA_CHECK(cudaStreamWaitEvent(cs, e, 0));
-          const long long b = mstart[mcut[j]], e2 = mstart[mcut[j + 1]];
-          for (int c = 0; c < ncomp; ++c)
-            if (e2 > b) CMDR_CUDA_CHECK(cudaMemcpyAsync(alm[c] + b, alm_dev[c] + b, sizeof(double) * (e2 - b), cudaMemcpyDeviceToHost, cs));
-        }
-      } else {
-        launch_legendre_anal(spin, G, A, alm_dev, ph, st);
+      if (i < ns - nj) { launch_legendre_anal(spin, G, A, alm_dev, ph, st); mark("leg", i, st); }
+    }
+    // last `nj` ring-pair chunks: m-chunk by m-chunk over all of them, so that the finished a_lm columns go
+    // back to the host while the next m-chunk is still being accumulated (nj chunks of compute per slice of
+    // the download; only the last slice is exposed)
+    cudaStream_t as = (two_streams && nmch > 1) ? aux_stream() : st;
+    if (as != st) {
+      cudaEvent_t ef = pooled_event(ns + 20);              // ring FFTs and earlier chunks done
+      CMDR_CUDA_CHECK(cudaEventRecord(ef, st));
+      CMDR_CUDA_CHECK(cudaStreamWaitEvent(as, ef, 0));
+    }
+    for (int j = 0; j < nmch && nj > 0; ++j) {
+      cudaStream_t sj = (j & 1) ? as : st;
+      LegAlm Aj = A;
+      Aj.im_begin = mcut[j]; Aj.im_end = mcut[j + 1];
+      G.slot_begin = g->subs[ns - nj]->pair0; G.slot_end = g->subs[ns - 1]->pair0 + g->subs[ns - 1]->npairs;
+      launch_legendre_anal(spin, G, nmch > 1 ? Aj : A, alm_dev, ph, sj);   // merged slot range of the last nj chunks
+      if (nmch > 1) {
+        cudaEvent_t e = pooled_event(ns + 2 + j);
+        CMDR_CUDA_CHECK(cudaEventRecord(e, sj));
+        mark("legm", j, sj);
+        CMDR_CUDA_CHECK(cudaStreamWaitEvent(cs, e, 0));
+        const long long b = mstart[mcut[j]], e2 = mstart[mcut[j + 1]];
+        for (int c = 0; c < ncomp; ++c)
+          if (e2 > b) PIPE_COPY(alm[c] + b, alm_dev[c] + b, sizeof(double) * (e2 - b), cudaMemcpyDeviceToHost, cs);
+        mark("down", j, cs);
       }
     }
     if (nmch == 1) {
       for (int c = 0; c < ncomp; ++c)
-        CMDR_CUDA_CHECK(cudaMemcpyAsync(alm[c], alm_dev[c], sizeof(double) * nalm_d, cudaMemcpyDeviceToHost, st));
+        PIPE_COPY(alm[c], alm_dev[c], sizeof(double) * nalm_d, cudaMemcpyDeviceToHost, st);
     }
     CMDR_CUDA_CHECK(cudaStreamSynchronize(cs));
+    if (as != st) CMDR_CUDA_CHECK(cudaStreamSynchronize(as));
     CMDR_CUDA_CHECK(cudaStreamSynchronize(st));
   }
+#undef PIPE_COPY
+  dump_marks();
   return true;
 }
 
