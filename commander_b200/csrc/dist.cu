@@ -591,6 +591,12 @@ static void execute_dist_any(DistComm *C, int type, int nparts, const int *spins
   if (sa.staged || sm.staged) CMDR_CUDA_CHECK(cudaStreamSynchronize(st));
 }
 
+// map *= F, the pixel-space mixing step between Y and YtW (HBM-bound: 24 bytes per pixel)
+__global__ void __launch_bounds__(256) scale_map_kernel(double *__restrict__ m, const double *__restrict__ f, long long n) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) m[i] *= f[i];
+}
+
 }  // namespace cmdr
 
 using namespace cmdr;
@@ -668,6 +674,86 @@ void cmdr_sht_allreduce_sum(int comm, double *dev_buf, int n, void *stream) {
   if (!C || C->nranks == 1) return;
   CMDR_NCCL_CHECK(nccl_api()->AllReduce(dev_buf, dev_buf, n, ncclDouble, ncclSum, C->nccl, (cudaStream_t)stream));
   count_launch(1);
+}
+
+// Pixel-space mixing: alm <- YtW( F .* Y(alm) ), the spatially varying branch of evalDiffuseBand /
+// projectDiffuseBand (commander3/src/comm_diffuse_comp_mod.f90:2078-2080, 2148-2150: `call m%Y();
+// m%map = m%map * F%map; call m%YtW()`).  The reference makes four sharp_execute calls and multiplies
+// on the host; here the map never leaves the device: only the a_lm (and F, when the caller keeps it
+// on the host) cross PCIe.  nmaps = 1 (T) or 3 (IQU); alm and F are arrays of nmaps pointers, host
+// or device; with a registered `comm` the call is collective like sharp_execute_mpi_fortran.
+void cmdr_sht_mix(int comm, int nmaps, double *const *alm, const double *const *F,
+                  const sharp_geom_info *geom_T, const sharp_geom_info *geom_P,
+                  const sharp_alm_info *alm_info, void *stream) {
+  if (nmaps != 1 && nmaps != 3) { fprintf(stderr, "cmdr_sht_mix: nmaps %d unsupported (1 or 3)\n", nmaps); abort(); }
+  cudaStream_t st = (cudaStream_t)stream;
+  const sharp_alm_info *a = alm_info;
+  const long long nalm_d = a->nalm * (a->real_packed ? 1 : 2);
+  const long long npix = geom_T->npix;
+  if (nmaps == 3 && geom_P->npix != npix) { fprintf(stderr, "cmdr_sht_mix: T and P geometries differ in size\n"); abort(); }
+  bool alm_on_dev = true, f_on_dev = true;
+  for (int c = 0; c < nmaps; ++c) {
+    alm_on_dev = alm_on_dev && (nalm_d == 0 || is_device_ptr(alm[c]));
+    f_on_dev = f_on_dev && (npix == 0 || is_device_ptr(F[c]));
+  }
+  double *ad[3], *md[3];
+  const double *fd[3];
+  double *map_buf = static_cast<double *>(scratch_get("mix_map", sizeof(double) * (size_t)std::max<long long>(1, npix) * nmaps));
+  for (int c = 0; c < nmaps; ++c) md[c] = map_buf + (size_t)c * npix;
+  if (alm_on_dev) {
+    for (int c = 0; c < nmaps; ++c) ad[c] = alm[c];
+  } else {
+    double *alm_buf = static_cast<double *>(scratch_get("mix_alm", sizeof(double) * (size_t)std::max<long long>(1, nalm_d) * nmaps));
+    for (int c = 0; c < nmaps; ++c) {
+      ad[c] = alm_buf + (size_t)c * nalm_d;
+      if (nalm_d) CMDR_CUDA_CHECK(cudaMemcpyAsync(ad[c], alm[c], sizeof(double) * nalm_d, cudaMemcpyHostToDevice, st));
+    }
+  }
+  cudaEvent_t ef = nullptr;
+  if (f_on_dev) {
+    for (int c = 0; c < nmaps; ++c) fd[c] = F[c];
+  } else {
+    // F goes up on the copy stream while the synthesis runs
+    double *f_buf = static_cast<double *>(scratch_get("mix_F", sizeof(double) * (size_t)std::max<long long>(1, npix) * nmaps));
+    cudaStream_t cs = copy_stream();
+    cudaEvent_t e0 = pooled_event(60);          // an earlier call on `st` may still read the buffer
+    CMDR_CUDA_CHECK(cudaEventRecord(e0, st));
+    CMDR_CUDA_CHECK(cudaStreamWaitEvent(cs, e0, 0));
+    for (int c = 0; c < nmaps; ++c) {
+      fd[c] = f_buf + (size_t)c * npix;
+      if (npix) CMDR_CUDA_CHECK(cudaMemcpyAsync(f_buf + (size_t)c * npix, F[c], sizeof(double) * npix, cudaMemcpyHostToDevice, cs));
+    }
+    ef = pooled_event(61);
+    CMDR_CUDA_CHECK(cudaEventRecord(ef, cs));
+  }
+  auto transform = [&](int type) {
+    if (nmaps == 3) {
+      cmdr_sht_execute_iqu_dist(comm, type, ad, md, geom_T, geom_P, alm_info, SHARP_DP, st);
+    } else {
+      cmdr_sht_execute_dist(comm, type, 0, ad, md, geom_T, alm_info, SHARP_DP, st);
+    }
+  };
+  transform(SHARP_Y);
+  if (ef) CMDR_CUDA_CHECK(cudaStreamWaitEvent(st, ef, 0));
+  if (npix) {
+    int nsm = 148;
+    int dev = 0;
+    CMDR_CUDA_CHECK(cudaGetDevice(&dev));
+    CMDR_CUDA_CHECK(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
+    for (int c = 0; c < nmaps; ++c) {
+      scale_map_kernel<<<nsm * 8, 256, 0, st>>>(md[c], fd[c], npix);
+      count_launch(1);
+    }
+    CMDR_CUDA_CHECK(cudaGetLastError());
+  }
+  transform(SHARP_YtW);
+  if (!alm_on_dev) {
+    for (int c = 0; c < nmaps; ++c)
+      if (nalm_d) CMDR_CUDA_CHECK(cudaMemcpyAsync(alm[c], ad[c], sizeof(double) * nalm_d, cudaMemcpyDeviceToHost, st));
+    CMDR_CUDA_CHECK(cudaStreamSynchronize(st));
+  } else if (!f_on_dev) {
+    CMDR_CUDA_CHECK(cudaStreamSynchronize(st));     // the caller may free or rewrite the host F after return
+  }
 }
 
 // commander3/src/sharp.f90:96-104.  `comm` is the MPI_Fint; the group must have been

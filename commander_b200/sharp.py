@@ -34,7 +34,7 @@ ABI_SYMBOLS = [
     # part 2: additive
     "cmdr_sht_version", "cmdr_sht_execute_dev", "cmdr_sht_execute_iqu", "cmdr_sht_execute_iqu_batch", "cmdr_sht_get_unique_id",
     "cmdr_sht_comm_register", "cmdr_sht_comm_destroy", "cmdr_sht_execute_dist",
-    "cmdr_sht_execute_iqu_dist", "cmdr_sht_allreduce_sum", "cmdr_sht_launch_count",
+    "cmdr_sht_execute_iqu_dist", "cmdr_sht_mix", "cmdr_sht_allreduce_sum", "cmdr_sht_launch_count",
     "cmdr_sht_set_profiling", "cmdr_sht_last_legendre_ms", "cmdr_sht_nominal_flops",
     "cmdr_sht_release_caches", "cmdr_sht_measure_fp64_tflops", "cmdr_sht_measure_fp64_tflops_3op",
 ]
@@ -72,6 +72,7 @@ def lib() -> C.CDLL:
     L.cmdr_sht_comm_destroy.argtypes = [ci]
     L.cmdr_sht_execute_dist.argtypes = [ci, ci, ci, vp, vp, vp, vp, ci, vp]
     L.cmdr_sht_execute_iqu_dist.argtypes = [ci, ci, vp, vp, vp, vp, vp, ci, vp]
+    L.cmdr_sht_mix.argtypes = [ci, ci, vp, vp, vp, vp, vp, vp]
     L.cmdr_sht_allreduce_sum.argtypes = [ci, vp, ci, vp]
     L.cmdr_sht_launch_count.restype = C.c_ulonglong
     L.cmdr_sht_set_profiling.argtypes = [ci]
@@ -234,6 +235,20 @@ def execute_iqu_batch(type, alms, maps, geom_T: sharp_geom_info, geom_P: sharp_g
             mptr[3 * b + c] = pm[c]
     st = C.c_void_p(stream) if stream else None
     L.cmdr_sht_execute_iqu_batch(type, nb, aptr, mptr, geom_T.handle, geom_P.handle, alm_info.handle, flags, st)
+
+
+def mix(alm, F, geom_T: sharp_geom_info, geom_P: sharp_geom_info, alm_info: sharp_alm_info, nmaps=3,
+        stream=None, comm=None):
+    """alm <- YtW(F .* Y(alm)) with the map kept on the device (cmdr_sht_mix; the mixing step of
+    commander3/src/comm_diffuse_comp_mod.f90:2078-2080, 2148-2150).  alm (nmaps, n_alm) is updated
+    in place, F (nmaps, n_pix); host (numpy) or device (torch) arrays."""
+    L = lib()
+    alm_ptr, _a = _col_ptrs(alm, nmaps, alm_info.n_local)
+    f_ptr, _f = _col_ptrs(F, nmaps, geom_T.n_local)
+    st = C.c_void_p(stream) if stream else None
+    gp = geom_P.handle if geom_P is not None else None
+    L.cmdr_sht_mix(int(comm) if comm is not None else -1, nmaps, alm_ptr, f_ptr, geom_T.handle, gp,
+                   alm_info.handle, st)
 
 
 def launch_count() -> int:

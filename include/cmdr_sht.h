@@ -140,6 +140,18 @@ void cmdr_sht_execute_iqu_dist(int comm, int type, double *const *alm3, double *
                                const sharp_geom_info *geom_T, const sharp_geom_info *geom_P,
                                const sharp_alm_info *alm_info, int flags, void *stream);
 
+/* Pixel-space mixing, alm <- YtW( F .* Y(alm) ): the spatially varying branch of
+ * evalDiffuseBand / projectDiffuseBand (commander3/src/comm_diffuse_comp_mod.f90:2078-2080
+ * and :2148-2150 -- `call m%Y(); m%map = m%map * F%map; call m%YtW()`), which the reference
+ * runs as four sharp_execute calls with a host-side multiply in between.  Here the map stays
+ * on the device; only alm (and F, if it lives on the host) cross PCIe.
+ * nmaps = 1 (T, geom_P ignored) or 3 (I,Q,U); alm and F are arrays of nmaps pointers to
+ * n_alm / n_pix doubles, host or device.  comm: a registered communicator (collective call,
+ * layout as for sharp_execute_mpi_fortran) or any unregistered value for one GPU. */
+void cmdr_sht_mix(int comm, int nmaps, double *const *alm, const double *const *F,
+                  const sharp_geom_info *geom_T, const sharp_geom_info *geom_P,
+                  const sharp_alm_info *alm_info, void *stream);
+
 /* NCCL sum-allreduce of n doubles (device pointer) on the comm: the collective
  * behind mpi_dot_product (commander3/src/comm_utils.f90:599-614). */
 void cmdr_sht_allreduce_sum(int comm, double *dev_buf, int n, void *stream);
