@@ -15,10 +15,10 @@ two SHTs per A application are `comm_map%Y` and `comm_map%Yt` on device pointers
 per iteration go through `mpi_dot_product` = local dot + NCCL all-reduce
 (commander3/src/comm_utils.f90:599-614).
 
-Simplification (documented in DESIGN.md 7): the preconditioner's N^-1_{lm,lm} keeps only the
-monopole term of `compute_invN_lm` (commander3/src/comm_N_mod.f90:127-197), i.e. the sky mean of
-siN^2 times npix/4pi, instead of the full Wigner-3j sum.  Any SPD preconditioner gives the same
-solution; only the iteration count differs.
+The preconditioner's N^-1_{lm,lm} is `compute_invN_lm` (commander3/src/comm_N_mod.f90:127-197), on the GPU
+(`cmdr_sht_invN_diag`: the Wigner-3j sum of the reference evaluated as an exact quadrature).  `invN_lm="monopole"`
+keeps only its L = 0 term, the sky mean of siN^2 times npix/4pi (what round 1 started with).  Any SPD
+preconditioner gives the same solution; only the iteration count differs.
 """
 from __future__ import annotations
 
@@ -40,11 +40,37 @@ def gaussian_beam(lmax: int, fwhm_arcmin: float, nmaps: int = 3) -> np.ndarray:
     return bl
 
 
+def compute_invN_lm(invN_diag: comm_map) -> None:
+    """commander3/src/comm_N_mod.f90:127-197.  On entry invN_diag%map holds N^-1 per pixel (all columns treated
+    as scalars, :146); on exit invN_diag%alm holds N_lm: `YtW_scalar`, the m = 0 coefficients from the rank that
+    owns them to everybody (:147-152), then the 3j sum per local (l,m) (:154-184) -- here one GPU kernel."""
+    from . import sharp
+    info = invN_diag.info
+    invN_diag.YtW_scalar()
+    lmax, nm = info.lmax, info.nmaps
+    i0 = info.lm2i(0, 0)
+    if invN_diag.device is None:
+        a_l0 = np.zeros((nm, lmax + 1))
+        if i0 >= 0:
+            a_l0[:] = invN_diag.alm[:, i0:i0 + lmax + 1]
+        if info.dist and info.comm.size > 1:
+            raise NotImplementedError("host-resident comm_map on several ranks: use device maps")
+    else:
+        import torch
+        a = torch.zeros((nm, lmax + 1), dtype=torch.float64, device=invN_diag.alm.device)
+        if i0 >= 0:
+            a.copy_(invN_diag.alm[:, i0:i0 + lmax + 1])
+        if info.dist and info.comm.size > 1:
+            info.comm.allreduce_sum_(a)          # mpi_bcast from the owner of m = 0: zero everywhere else
+        a_l0 = a.cpu().numpy()
+    sharp.invN_diag(a_l0, float(info.npix), info.alm_info, invN_diag.alm)
+
+
 class cr_cmb_system:
     """One band, one component (CMB, F = 1) constrained-realisation system."""
 
     def __init__(self, info: comm_mapinfo, siN, b_l: np.ndarray, Cl: np.ndarray, mask=None, mb_eff: float = 1.0,
-                 precond: str = "diagonal"):
+                 precond: str = "diagonal", invN_lm: str = "wigner"):
         import torch
         self.torch = torch
         self.info = info
@@ -69,7 +95,17 @@ class cr_cmb_system:
         self._allreduce(mean_invN)
         mean_invN = mean_invN / float(info.npix)
         invN_diag = mean_invN * float(info.npix) / (4.0 * math.pi)
-        self.Minv = 1.0 / (1.0 + (self.sqrtS * self.bl) ** 2 * invN_diag[:, None])
+        if invN_lm == "wigner":
+            # P_cr%invM_diff for npre = 1 with the full N_lm (comm_diffuse_comp_mod.f90:1167-1252)
+            self.buf.map.copy_(self.invN)
+            compute_invN_lm(self.buf)
+            self.invN_lm = self.buf.alm.clone()
+            self.Minv = 1.0 / (1.0 + (self.sqrtS * self.bl) ** 2 * self.invN_lm)
+        elif invN_lm == "monopole":
+            self.invN_lm = None
+            self.Minv = 1.0 / (1.0 + (self.sqrtS * self.bl) ** 2 * invN_diag[:, None])
+        else:
+            raise ValueError("invN_lm must be 'wigner' or 'monopole'")
         # pseudo-inverse preconditioner (precond_type = 'pseudoinv')
         if precond not in ("diagonal", "pseudoinv"):
             raise ValueError("Preconditioner type not supported: " + precond)

@@ -34,7 +34,7 @@ ABI_SYMBOLS = [
     # part 2: additive
     "cmdr_sht_version", "cmdr_sht_execute_dev", "cmdr_sht_execute_iqu", "cmdr_sht_execute_iqu_batch", "cmdr_sht_get_unique_id",
     "cmdr_sht_comm_register", "cmdr_sht_comm_destroy", "cmdr_sht_execute_dist",
-    "cmdr_sht_execute_iqu_dist", "cmdr_sht_mix", "cmdr_sht_allreduce_sum", "cmdr_sht_launch_count",
+    "cmdr_sht_execute_iqu_dist", "cmdr_sht_mix", "cmdr_sht_invN_diag", "cmdr_sht_allreduce_sum", "cmdr_sht_launch_count",
     "cmdr_sht_set_profiling", "cmdr_sht_last_legendre_ms", "cmdr_sht_nominal_flops",
     "cmdr_sht_release_caches", "cmdr_sht_measure_fp64_tflops", "cmdr_sht_measure_fp64_tflops_3op",
 ]
@@ -73,6 +73,7 @@ def lib() -> C.CDLL:
     L.cmdr_sht_execute_dist.argtypes = [ci, ci, ci, vp, vp, vp, vp, ci, vp]
     L.cmdr_sht_execute_iqu_dist.argtypes = [ci, ci, vp, vp, vp, vp, vp, ci, vp]
     L.cmdr_sht_mix.argtypes = [ci, ci, vp, vp, vp, vp, vp, vp]
+    L.cmdr_sht_invN_diag.argtypes = [ci, vp, C.c_double, vp, vp, vp]
     L.cmdr_sht_allreduce_sum.argtypes = [ci, vp, ci, vp]
     L.cmdr_sht_launch_count.restype = C.c_ulonglong
     L.cmdr_sht_set_profiling.argtypes = [ci]
@@ -249,6 +250,18 @@ def mix(alm, F, geom_T: sharp_geom_info, geom_P: sharp_geom_info, alm_info: shar
     gp = geom_P.handle if geom_P is not None else None
     L.cmdr_sht_mix(int(comm) if comm is not None else -1, nmaps, alm_ptr, f_ptr, geom_T.handle, gp,
                    alm_info.handle, st)
+
+
+def invN_diag(a_l0, npix, alm_info: sharp_alm_info, out, stream=None) -> None:
+    """N_lm of compute_invN_lm (commander3/src/comm_N_mod.f90:127-197) from the m=0 coefficients a_l0
+    (nmaps, lmax+1; numpy, host) of YtW(N^-1 map); out (nmaps, n_alm), numpy or torch (device)."""
+    L = lib()
+    a_l0 = np.ascontiguousarray(a_l0, dtype=np.float64)
+    nmaps = a_l0.shape[0]
+    a_ptr, _a = _col_ptrs(a_l0, nmaps, a_l0.shape[1])
+    o_ptr, _o = _col_ptrs(out, nmaps, alm_info.n_local)
+    st = C.c_void_p(stream) if stream else None
+    L.cmdr_sht_invN_diag(nmaps, a_ptr, float(npix), alm_info.handle, o_ptr, st)
 
 
 def launch_count() -> int:

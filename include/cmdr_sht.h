@@ -152,6 +152,16 @@ void cmdr_sht_mix(int comm, int nmaps, double *const *alm, const double *const *
                   const sharp_geom_info *geom_T, const sharp_geom_info *geom_P,
                   const sharp_alm_info *alm_info, void *stream);
 
+/* Diagonal of the inverse noise covariance in harmonic space, the input of the diagonal CG
+ * preconditioner: replaces compute_invN_lm (commander3/src/comm_N_mod.f90:127-197) after its
+ * YtW_scalar and mpi_bcast.  a_l0[c] -> the lmax+1 m=0 coefficients of YtW(N^-1 map) of component c
+ * (host memory, identical on every rank); out[c] <- N_lm in the local real-packed order of alm_info
+ * (host or device), both entries of an m>0 pair equal (:176-181).  npix = 12 nside^2.  The 3j sum
+ * of the reference is evaluated as an exact Gauss-Legendre quadrature of lambda_lm^2 times the
+ * azimuthally averaged profile (see commander_b200/csrc/invn.cu); no collective. */
+void cmdr_sht_invN_diag(int nmaps, const double *const *a_l0, double npix,
+                        const sharp_alm_info *alm_info, double *const *out, void *stream);
+
 /* NCCL sum-allreduce of n doubles (device pointer) on the comm: the collective
  * behind mpi_dot_product (commander3/src/comm_utils.f90:599-614). */
 void cmdr_sht_allreduce_sum(int comm, double *dev_buf, int n, void *stream);
