@@ -16,7 +16,7 @@ per iteration go through `mpi_dot_product` = local dot + NCCL all-reduce
 (commander3/src/comm_utils.f90:599-614).
 
 The preconditioner's N^-1_{lm,lm} is `compute_invN_lm` (commander3/src/comm_N_mod.f90:127-197), on the GPU
-(`cmdr_sht_invN_diag`: the Wigner-3j sum of the reference evaluated as an exact quadrature).  `invN_lm="monopole"`
+(`cmdr_sht_invn_diag`: the Wigner-3j sum of the reference evaluated as an exact quadrature).  `invN_lm="monopole"`
 keeps only its L = 0 term, the sky mean of siN^2 times npix/4pi (what round 1 started with).  Any SPD
 preconditioner gives the same solution; only the iteration count differs.
 """

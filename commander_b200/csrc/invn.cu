@@ -34,7 +34,7 @@ struct InvNParams {
   const long long *mvstart, *cofs;
   const double *coef, *Kstart;
   const double *trig;      // nnodes * 4: cth, sth, sh, ch
-  const double *f;         // nmaps * nnodes: folded weight * profile, see cmdr_sht_invN_diag
+  const double *f;         // nmaps * nnodes: folded weight * profile, see cmdr_sht_invn_diag
   double *out[3];
   long long nalm;
 };
@@ -160,11 +160,11 @@ extern "C" {
 // a_l0[c] points at the lmax+1 m=0 coefficients of YtW(N^-1 map) for component c (host memory, the
 // same on every rank); out[c] receives N_lm in the local real-packed alm order of `alm_info` (both
 // entries of an m>0 pair get the same value, :176-181), host or device memory.  npix = 12 nside^2.
-void cmdr_sht_invN_diag(int nmaps, const double *const *a_l0, double npix, const sharp_alm_info *alm_info,
+void cmdr_sht_invn_diag(int nmaps, const double *const *a_l0, double npix, const sharp_alm_info *alm_info,
                         double *const *out, void *stream) {
-  if (nmaps < 1 || nmaps > 3) { fprintf(stderr, "cmdr_sht_invN_diag: nmaps %d unsupported (1..3)\n", nmaps); abort(); }
+  if (nmaps < 1 || nmaps > 3) { fprintf(stderr, "cmdr_sht_invn_diag: nmaps %d unsupported (1..3)\n", nmaps); abort(); }
   sharp_alm_info *a = const_cast<sharp_alm_info *>(alm_info);
-  if (!a->real_packed) { fprintf(stderr, "cmdr_sht_invN_diag: needs a real-packed alm_info\n"); abort(); }
+  if (!a->real_packed) { fprintf(stderr, "cmdr_sht_invn_diag: needs a real-packed alm_info\n"); abort(); }
   cudaStream_t st = (cudaStream_t)stream;
   const int lmax = a->lmax;
   const long long nalm = a->nalm;

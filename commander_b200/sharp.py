@@ -34,7 +34,7 @@ ABI_SYMBOLS = [
     # part 2: additive
     "cmdr_sht_version", "cmdr_sht_execute_dev", "cmdr_sht_execute_iqu", "cmdr_sht_execute_iqu_batch", "cmdr_sht_get_unique_id",
     "cmdr_sht_comm_register", "cmdr_sht_comm_destroy", "cmdr_sht_execute_dist",
-    "cmdr_sht_execute_iqu_dist", "cmdr_sht_mix", "cmdr_sht_invN_diag", "cmdr_sht_allreduce_sum", "cmdr_sht_launch_count",
+    "cmdr_sht_execute_iqu_dist", "cmdr_sht_mix", "cmdr_sht_invn_diag", "cmdr_sht_allreduce_sum", "cmdr_sht_launch_count",
     "cmdr_sht_set_profiling", "cmdr_sht_last_legendre_ms", "cmdr_sht_nominal_flops",
     "cmdr_sht_release_caches", "cmdr_sht_measure_fp64_tflops", "cmdr_sht_measure_fp64_tflops_3op",
 ]
@@ -73,7 +73,7 @@ def lib() -> C.CDLL:
     L.cmdr_sht_execute_dist.argtypes = [ci, ci, ci, vp, vp, vp, vp, ci, vp]
     L.cmdr_sht_execute_iqu_dist.argtypes = [ci, ci, vp, vp, vp, vp, vp, ci, vp]
     L.cmdr_sht_mix.argtypes = [ci, ci, vp, vp, vp, vp, vp, vp]
-    L.cmdr_sht_invN_diag.argtypes = [ci, vp, C.c_double, vp, vp, vp]
+    L.cmdr_sht_invn_diag.argtypes = [ci, vp, C.c_double, vp, vp, vp]
     L.cmdr_sht_allreduce_sum.argtypes = [ci, vp, ci, vp]
     L.cmdr_sht_launch_count.restype = C.c_ulonglong
     L.cmdr_sht_set_profiling.argtypes = [ci]
@@ -261,7 +261,7 @@ def invN_diag(a_l0, npix, alm_info: sharp_alm_info, out, stream=None) -> None:
     a_ptr, _a = _col_ptrs(a_l0, nmaps, a_l0.shape[1])
     o_ptr, _o = _col_ptrs(out, nmaps, alm_info.n_local)
     st = C.c_void_p(stream) if stream else None
-    L.cmdr_sht_invN_diag(nmaps, a_ptr, float(npix), alm_info.handle, o_ptr, st)
+    L.cmdr_sht_invn_diag(nmaps, a_ptr, float(npix), alm_info.handle, o_ptr, st)
 
 
 def launch_count() -> int:

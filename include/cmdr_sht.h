@@ -159,7 +159,7 @@ void cmdr_sht_mix(int comm, int nmaps, double *const *alm, const double *const *
  * (host or device), both entries of an m>0 pair equal (:176-181).  npix = 12 nside^2.  The 3j sum
  * of the reference is evaluated as an exact Gauss-Legendre quadrature of lambda_lm^2 times the
  * azimuthally averaged profile (see commander_b200/csrc/invn.cu); no collective. */
-void cmdr_sht_invN_diag(int nmaps, const double *const *a_l0, double npix,
+void cmdr_sht_invn_diag(int nmaps, const double *const *a_l0, double npix,
                         const sharp_alm_info *alm_info, double *const *out, void *stream);
 
 /* NCCL sum-allreduce of n doubles (device pointer) on the comm: the collective

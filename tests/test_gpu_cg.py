@@ -120,7 +120,7 @@ def test_cg_pseudoinv_preconditioner(shtlib):
 
 def test_cg_full_invN_lm_preconditioner(shtlib):
     """Diagonal preconditioner with the full compute_invN_lm (commander3/src/comm_N_mod.f90:127-197, GPU kernel
-    cmdr_sht_invN_diag) against its monopole-only approximation, for noise that varies with latitude (the term
+    cmdr_sht_invn_diag) against its monopole-only approximation, for noise that varies with latitude (the term
     the 3j sum captures): same solution, comparable iteration count (each run stops on its own preconditioned
     residual, so the counts are not ordered: 39 vs 36 here on B200)."""
     import torch

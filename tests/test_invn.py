@@ -1,5 +1,5 @@
 """compute_invN_lm (commander3/src/comm_N_mod.f90:127-197): the oracle's Wigner-3j restatement against
-independent references (CPU), and the GPU quadrature kernel `cmdr_sht_invN_diag` against the oracle and
+independent references (CPU), and the GPU quadrature kernel `cmdr_sht_invn_diag` against the oracle and
 closed forms.  Tolerance 1e-10 relative (FP64)."""
 import math
 
