@@ -34,7 +34,7 @@ ABI_SYMBOLS = [
     # part 2: additive
     "cmdr_sht_version", "cmdr_sht_execute_dev", "cmdr_sht_execute_iqu", "cmdr_sht_execute_iqu_batch", "cmdr_sht_get_unique_id",
     "cmdr_sht_comm_register", "cmdr_sht_comm_destroy", "cmdr_sht_execute_dist",
-    "cmdr_sht_execute_iqu_dist", "cmdr_sht_mix", "cmdr_sht_invn_diag", "cmdr_sht_allreduce_sum", "cmdr_sht_launch_count",
+    "cmdr_sht_execute_iqu_dist", "cmdr_sht_mix", "cmdr_sht_invn_diag", "cmdr_sht_conviqt_cube", "cmdr_sht_allreduce_sum", "cmdr_sht_launch_count",
     "cmdr_sht_set_profiling", "cmdr_sht_last_legendre_ms", "cmdr_sht_nominal_flops",
     "cmdr_sht_release_caches", "cmdr_sht_measure_fp64_tflops", "cmdr_sht_measure_fp64_tflops_3op",
 ]
@@ -74,6 +74,7 @@ def lib() -> C.CDLL:
     L.cmdr_sht_execute_iqu_dist.argtypes = [ci, ci, vp, vp, vp, vp, vp, ci, vp]
     L.cmdr_sht_mix.argtypes = [ci, ci, vp, vp, vp, vp, vp, vp]
     L.cmdr_sht_invn_diag.argtypes = [ci, vp, C.c_double, vp, vp, vp]
+    L.cmdr_sht_conviqt_cube.argtypes = [ci, ci, ci, vp, vp, vp, vp, vp, ci, vp]
     L.cmdr_sht_allreduce_sum.argtypes = [ci, vp, ci, vp]
     L.cmdr_sht_launch_count.restype = C.c_ulonglong
     L.cmdr_sht_set_profiling.argtypes = [ci]
@@ -262,6 +263,39 @@ def invN_diag(a_l0, npix, alm_info: sharp_alm_info, out, stream=None) -> None:
     o_ptr, _o = _col_ptrs(out, nmaps, alm_info.n_local)
     st = C.c_void_p(stream) if stream else None
     L.cmdr_sht_invn_diag(nmaps, a_ptr, float(npix), alm_info.handle, o_ptr, st)
+
+
+def conviqt_cube(sky_alm, beam, bmax, geom_T: sharp_geom_info, alm_info: sharp_alm_info, cube, stream=None,
+                 comm=None) -> None:
+    """cube <- the psi cube of comm_conviqt%precompute_sky (commander3/src/comm_conviqt_mod.f90:207-292).
+    sky_alm (nmaps, n_alm) float64; beam (ntri, nmaps) complex64 (alm_beam of the reference, transposed
+    into memory order); cube (2*bmax, n_pix) float32 or float64.  numpy (host) or torch (device) arrays."""
+    L = lib()
+    nmaps = sky_alm.shape[0]
+    alm_ptr, _a = _col_ptrs(sky_alm, nmaps, alm_info.n_local)
+    ntri = beam.shape[0]
+    if isinstance(beam, np.ndarray):
+        if beam.dtype != np.complex64 or not beam.flags.c_contiguous or beam.shape != (ntri, nmaps):
+            raise ValueError("beam must be a C-contiguous complex64 array of shape (ntri, nmaps)")
+        bptr = beam.ctypes.data
+    else:
+        import torch
+        if beam.dtype != torch.complex64 or not beam.is_contiguous() or tuple(beam.shape) != (ntri, nmaps):
+            raise ValueError("beam must be a contiguous complex64 tensor of shape (ntri, nmaps)")
+        bptr = beam.data_ptr()
+    shape = (2 * bmax, geom_T.n_local)
+    if isinstance(cube, np.ndarray):
+        if cube.dtype not in (np.float32, np.float64) or not cube.flags.c_contiguous or cube.shape != shape:
+            raise ValueError(f"cube must be a C-contiguous float32/float64 array of shape {shape}")
+        cptr, f64 = cube.ctypes.data, cube.dtype == np.float64
+    else:
+        import torch
+        if cube.dtype not in (torch.float32, torch.float64) or not cube.is_contiguous() or tuple(cube.shape) != shape:
+            raise ValueError(f"cube must be a contiguous float32/float64 tensor of shape {shape}")
+        cptr, f64 = cube.data_ptr(), cube.dtype == torch.float64
+    st = C.c_void_p(stream) if stream else None
+    L.cmdr_sht_conviqt_cube(int(comm) if comm is not None else -1, nmaps, int(bmax), alm_ptr, bptr,
+                            geom_T.handle, alm_info.handle, cptr, 1 if f64 else 0, st)
 
 
 def launch_count() -> int:

@@ -72,7 +72,7 @@ ptrdiff_t sharp_map_size(const sharp_geom_info *info);
  * pointers, one per component (spin 0: 1, spin>0: 2), each to a contiguous
  * double array.  The pointers may be host memory (pageable or pinned; the
  * Fortran case) or device memory (detected with cudaPointerGetAttributes).
- * spin must be 0 or 2.  `time` (seconds) and `opcnt` (nominal flops) are
+ * spin 0, or any spin 1..32 (two components; conviqt calls spin j, comm_conviqt_mod.f90:254).  `time` (seconds) and `opcnt` (nominal flops) are
  * optional outputs. */
 void sharp_execute(int type, int spin, void *alm, void *map, const sharp_geom_info *geom_info,
                    const sharp_alm_info *alm_info, int flags, double *time,
@@ -161,6 +161,19 @@ void cmdr_sht_mix(int comm, int nmaps, double *const *alm, const double *const *
  * azimuthally averaged profile (see commander_b200/csrc/invn.cu); no collective. */
 void cmdr_sht_invn_diag(int nmaps, const double *const *a_l0, double npix,
                         const sharp_alm_info *alm_info, double *const *out, void *stream);
+
+/* The convolution cube of conviqt: replaces comm_conviqt%precompute_sky together with get_alms
+ * (commander3/src/comm_conviqt_mod.f90:207-292 and :294-357), which the reference runs as bmax+1
+ * sharp_execute calls through host arrays (:247-258) plus one FFTW c2r of length 2*bmax per pixel
+ * (:267-282).  sky_alm: nmaps (1..3) pointers to the local real-packed a_lm of alm_info; beam: the
+ * shared beam table alm_beam%a(nmaps, (lmax+1)(lmax+2)/2) exactly as the reference holds it (:94-115) --
+ * single-precision complex, entry (l,m) at complex index (l(l+1)/2 + m)*nmaps + c; cube: 2*bmax rows
+ * of n_pix local pixels (c%a(pix, psi) in Fortran order), float when cube_f64 == 0 (the reference's
+ * real(sp) cube, :281) or double.  All three may be host or device memory.  1 <= bmax <= 32.
+ * comm: a registered communicator (collective) or any unregistered value for one GPU. */
+void cmdr_sht_conviqt_cube(int comm, int nmaps, int bmax, const double *const *sky_alm, const float *beam,
+                           const sharp_geom_info *geom_T, const sharp_alm_info *alm_info, void *cube,
+                           int cube_f64, void *stream);
 
 /* NCCL sum-allreduce of n doubles (device pointer) on the comm: the collective
  * behind mpi_dot_product (commander3/src/comm_utils.f90:599-614). */
