@@ -300,6 +300,7 @@ def run_ours(args):
     clocks = sampler.stop() if rank == 0 else None
     cg = run_cg_metric(args, comm, dev, world) if not args.no_cg else None
     batch = run_batch_metric(dev) if (world == 1 and not args.no_batch) else None
+    conviqt = run_conviqt_metric(dev) if (world == 1 and not args.no_conviqt) else None
     bytes_alm, bytes_map = 3 * info.nalm * 8, 3 * info.np * 8
 
     # ---- roofline of the dominant kernel (spin-2 Legendre), FP64 pipe
@@ -378,7 +379,7 @@ def run_ours(args):
                 "e2e": {"value": 1e3 / e2e_ms, "unit": UNIT, "ms_per_step": e2e_ms, "steps": e2e_steps,
                         "h2d_bytes_per_step": bytes_alm + bytes_map, "d2h_bytes_per_step": bytes_alm + bytes_map,
                         "host_buffers": "pinned", "api": "comm_map.Y(); comm_map.YtW()  (4 sharp_execute calls)"},
-                "roofline": roofline, "cpu_baseline": cpu, "cg": cg, "batch": batch}
+                "roofline": roofline, "cpu_baseline": cpu, "cg": cg, "batch": batch, "conviqt": conviqt}
         print(json.dumps(line))
     if world > 1:
         cdist.destroy(comm)
@@ -426,6 +427,36 @@ def run_batch_metric(dev, nbands=30, nside=512, lmax=1500):
             "sequential_abi_calls": round(out["sequential"], 2), "batched_entry_point": round(out["batched"], 2),
             "pcie_bytes_per_pair": nbytes, "bands": nbands, "host_buffers": "pinned",
             "api": "comm_map.Y()/YtW() per band  vs  comm_map.Y_batch()/YtW_batch() (cmdr_sht_execute_iqu_batch)"}
+
+
+def run_conviqt_metric(dev, nside=512, lmax=1000, bmax=8):
+    """the conviqt convolution cube (comm_conviqt%precompute_sky, commander3/src/comm_conviqt_mod.f90:207-292):
+    bmax+1 spin-j syntheses and the psi transform, sky a_lm / beam table / cube device resident."""
+    import numpy as np
+    import torch
+    from commander_b200 import comm_map, comm_mapinfo
+    from commander_b200.comm_conviqt import comm_conviqt
+    info = comm_mapinfo(None, nside, lmax, 3, True)
+    rng = np.random.default_rng(200)
+    sky = comm_map(info, device=dev)
+    sky.alm.copy_(torch.as_tensor(rng.standard_normal((3, info.nalm))))
+    beam = comm_map(info)
+    beam.alm[...] = rng.standard_normal(beam.alm.shape) / (1.0 + info.lm[0])
+    cv = comm_conviqt(nside, lmax, 3, bmax, beam, sky, device=dev)    # first call: plans, tables
+    torch.cuda.synchronize()
+    reps = 3
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    ev[0].record()
+    for _ in range(reps):
+        cv.precompute_sky(sky)
+    ev[1].record()
+    torch.cuda.synchronize()
+    ms = ev[0].elapsed_time(ev[1]) / reps
+    psi_bytes = info.np * (8 * (2 * bmax + 1) + 4 * 2 * bmax)
+    return {"metric": "conviqt cubes/sec (precompute_sky)", "value": round(1e3 / ms, 3), "unit": "cubes/s", "ms_per_cube": round(ms, 3),
+            "config": f"nside={nside} lmax={lmax} IQU sky x beam, bmax={bmax} (1 spin-0 + {bmax} spin-j syntheses, {2 * bmax} psi planes, "
+                      "float32 cube), device-resident",
+            "psi_kernel_algorithmic_bytes": psi_bytes}
 
 
 def run_cg_metric(args, comm, dev, world):
@@ -480,6 +511,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-cg", action="store_true", help="skip the secondary CG iters/s measurement")
     ap.add_argument("--no-batch", action="store_true", help="skip the 30-band batch measurement (config 5)")
+    ap.add_argument("--no-conviqt", action="store_true", help="skip the conviqt cube measurement (SURVEY 8f rank 4)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

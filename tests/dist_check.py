@@ -77,6 +77,27 @@ def main():
                 e4 = np.linalg.norm(outa - refa[:, gidx]) / np.linalg.norm(refa[:, gidx])
                 worst = max(worst, e3, e4)
                 assert e3 <= 1e-10 and e4 <= 1e-10, (spin, e3, e4)
+        # conviqt cube through the distributed entry point (beam table synchronised over ranks, spin-j syntheses
+        # with the fused exchange, psi transform on the local pixels)
+        if nside == 64:
+            from commander_b200.comm_conviqt import comm_conviqt
+            from oracle import conviqt as O
+            bmax = 3
+            beam_g = rng.standard_normal((3, nalm_g))
+            sky, beam = comm_map(infow), comm_map(infow)
+            sky.alm[:] = alm_g[:, gidx]
+            beam.alm[:] = beam_g[:, gidx]
+            cv = comm_conviqt(nside, lmax, 3, bmax, beam, sky, precompute=False)
+            assert cv.info.np == infow.np and cv.info.nalm == infow.nalm
+            c64 = np.zeros((2 * bmax, infow.np))
+            cv.precompute_sky(sky, cube=c64)
+            lm = O.lm_table(lmax)
+            tab = O.beam_table(lmax, 3, lm, beam_g)
+            assert np.array_equal(tab.view(np.float32), cv.alm_beam.view(np.float32))
+            refc = O.precompute_sky(S, nside, lmax, bmax, alm_g, tab)[:, infow.pix]
+            e5 = np.linalg.norm(c64 - refc) / np.linalg.norm(refc)
+            worst = max(worst, e5)
+            assert e5 <= 1e-10, ("conviqt", e5)
         infow.dealloc()
     # pinned host buffers at a size where the chunked pipeline (per-chunk exchange barriers, PCIe copies beside
     # the Legendre kernels) is taken

@@ -106,6 +106,24 @@ def _worker(rank, world, port, nside, lmax, q):
         ref = S.execute(S.YtW, spin, nside, lmax, map=full.numpy(), ms=info.ms)
         err = np.linalg.norm(mine - ref) / np.linalg.norm(ref)
         assert err < 1e-13, err
+    # 4. conviqt beam table: every rank contributes its own m's, all ranks end with the full single-precision table
+    #    (sync_shared_2d_spc_alm, commander3/src/comm_conviqt_mod.f90:124-125)
+    from commander_b200.comm_map import comm_map
+    from commander_b200.comm_conviqt import comm_conviqt
+    from oracle import conviqt as O
+    grng = np.random.default_rng(55)
+    lm_g = O.lm_table(lmax)
+    beam_g = grng.standard_normal((3, len(lm_g)))
+    pos = {t: i for i, t in enumerate(lm_g)}
+    gidx = np.array([pos[(int(info.lm[0, i]), int(info.lm[1, i]))] for i in range(info.nalm)])
+    sky, beam = comm_map(info), comm_map(info)
+    beam.alm[...] = beam_g[:, gidx]
+    cv = comm_conviqt(nside, lmax, 3, 2, beam, sky, precompute=False)
+    tab = O.beam_table(lmax, 3, lm_g, beam_g)
+    assert np.array_equal(cv.alm_beam.view(np.float32), tab.view(np.float32))
+    ref = O.get_alms(1, lmax, lm_g, beam_g, tab)[:, gidx]        # any a_lm serve as the sky
+    sky.alm[...] = beam_g[:, gidx]
+    assert np.allclose(cv.get_alms(1, sky), ref, rtol=0, atol=1e-14 * np.abs(ref).max())
     dist.barrier()
     dist.destroy_process_group()
     q.put((rank, "ok"))
