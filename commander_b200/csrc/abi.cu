@@ -326,6 +326,7 @@ void sharp_destroy_geom_info(sharp_geom_info *g) {
     cudaFree(g->d_ofsN); cudaFree(g->d_ofsS); cudaFree(g->d_zbase); cudaFree(g->d_zidx);
     cudaFree(g->d_znp); cudaFree(g->d_zlen); cudaFree(g->d_zblue);
     if (g->d_vtab) cudaFree(g->d_vtab);
+    if (g->d_vtab_br) cudaFree(g->d_vtab_br);
     for (auto &kv : g->mlim) cudaFree(kv.second);
   }
   delete g;

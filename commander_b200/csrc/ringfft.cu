@@ -14,7 +14,9 @@
 
 #include <cstdio>
 #include <cstdlib>
+#include <map>
 
+#include "blue_fft.cuh"
 #include "kernels.h"
 
 namespace cmdr {
@@ -74,15 +76,13 @@ __device__ __forceinline__ double2 fold_one(const FParams &p, const PhaseLayout 
   return make_double2(pn.x - ps.y, pn.y + ps.x);
 }
 
-__global__ void __launch_bounds__(256) fold_kernel(FParams p, int first_pair) {
-  __shared__ double2 part_sum[256];
-  const int pair = first_pair + blockIdx.x, c = blockIdx.y;
-  const int n = p.nph[pair], len = p.zlen[pair];
+template <int NT>
+__device__ __forceinline__ void fold_into(const FParams &p, int pair, int c, double2 *out, int len, double2 *part_sum) {
+  const int n = p.nph[pair];
   const bool blue = p.zblue[pair], shifted = p.shifted[pair];
-  double2 *out = p.buf + zoff(p, pair, c);
   const PhaseLayout &L = p.L;
   int parts = 1;
-  while (parts * 2 * n <= 256) parts *= 2;          // power of two, parts * n <= 256
+  while (parts * 2 * n <= NT) parts *= 2;           // power of two, parts * n <= NT
   if (parts > 1) {
     const int k = threadIdx.x % n, part = threadIdx.x / n;   // threads >= parts*n idle
     double2 acc = make_double2(0.0, 0.0);
@@ -100,7 +100,7 @@ __global__ void __launch_bounds__(256) fold_kernel(FParams p, int first_pair) {
     }
     part_sum[threadIdx.x] = acc;
     __syncthreads();
-    for (int kk = threadIdx.x; kk < len; kk += blockDim.x) {
+    for (int kk = threadIdx.x; kk < len; kk += NT) {
       double2 tot = make_double2(0.0, 0.0);
       if (kk < n) {
         for (int q = 0; q < parts; ++q) { tot.x += part_sum[kk + q * n].x; tot.y += part_sum[kk + q * n].y; }
@@ -110,7 +110,7 @@ __global__ void __launch_bounds__(256) fold_kernel(FParams p, int first_pair) {
     }
     return;
   }
-  for (int k = threadIdx.x; k < len; k += blockDim.x) {
+  for (int k = threadIdx.x; k < len; k += NT) {
     double2 acc = make_double2(0.0, 0.0);
     if (k < n) {
       for (int m = k; m <= L.mmax; m += n) {          // m == k (mod n): X_k += p_m
@@ -127,6 +127,12 @@ __global__ void __launch_bounds__(256) fold_kernel(FParams p, int first_pair) {
     }
     out[k] = acc;
   }
+}
+
+__global__ void __launch_bounds__(256) fold_kernel(FParams p, int first_pair) {
+  __shared__ double2 part_sum[256];
+  const int pair = first_pair + blockIdx.x, c = blockIdx.y;
+  fold_into<256>(p, pair, c, p.buf + zoff(p, pair, c), p.zlen[pair], part_sum);
 }
 
 // Rings without aliasing (n >= 2 mmax + 1, the belt at lmax <= 2 nside): every m owns the two
@@ -186,11 +192,9 @@ __global__ void __launch_bounds__(256) blue_filter_kernel(FParams p, int first_p
 }
 
 // ---- synthesis, after the FFT: write north = Re z, south = Im z into the map
-__global__ void __launch_bounds__(256) scatter_kernel(FParams p) {
-  const int pair = blockIdx.x, c = blockIdx.y;
+__device__ __forceinline__ void scatter_from(const FParams &p, int pair, int c, const double2 *in) {
   const int n = p.nph[pair], len = p.zlen[pair];
   const bool blue = p.zblue[pair];
-  const double2 *in = p.buf + zoff(p, pair, c);
   double *mp = map_ptr(p, c);
   const long long oN = p.ofsN[pair], oS = p.ofsS[pair];
   double w = p.weighted ? p.wgt[pair] : 1.0;
@@ -202,13 +206,15 @@ __global__ void __launch_bounds__(256) scatter_kernel(FParams p) {
     if (oS >= 0) { if (p.add) mp[oS + j] += w * z.y; else mp[oS + j] = w * z.y; }
   }
 }
+__global__ void __launch_bounds__(256) scatter_kernel(FParams p, int first_pair) {
+  const int pair = first_pair + blockIdx.x, c = blockIdx.y;
+  scatter_from(p, pair, c, p.buf + zoff(p, pair, c));
+}
 
 // ---- analysis, before the FFT: z = w (x_north + i x_south)
-__global__ void __launch_bounds__(256) gather_kernel(FParams p) {
-  const int pair = blockIdx.x, c = blockIdx.y;
+__device__ __forceinline__ void gather_into(const FParams &p, int pair, int c, double2 *out) {
   const int n = p.nph[pair], len = p.zlen[pair];
   const bool blue = p.zblue[pair];
-  double2 *out = p.buf + zoff(p, pair, c);
   const double *mp = map_ptr(p, c);
   const long long oN = p.ofsN[pair], oS = p.ofsS[pair];
   const double w = p.weighted ? p.wgt[pair] : 1.0;
@@ -223,13 +229,15 @@ __global__ void __launch_bounds__(256) gather_kernel(FParams p) {
     out[j] = z;
   }
 }
+__global__ void __launch_bounds__(256) gather_kernel(FParams p, int first_pair) {
+  const int pair = first_pair + blockIdx.x, c = blockIdx.y;
+  gather_into(p, pair, c, p.buf + zoff(p, pair, c));
+}
 
 // ---- analysis, after the FFT: phases ph_m = c_m e^{-i m phi0} X_{m mod n}
-__global__ void __launch_bounds__(256) unfold_kernel(FParams p) {
-  const int pair = blockIdx.x, c = blockIdx.y;
+__device__ __forceinline__ void unfold_from(const FParams &p, int pair, int c, const double2 *in) {
   const int n = p.nph[pair], len = p.zlen[pair];
   const bool blue = p.zblue[pair], shifted = p.shifted[pair];
-  const double2 *in = p.buf + zoff(p, pair, c);
   const PhaseLayout &L = p.L;
   const double inv = blue ? 1.0 / (double)len : 1.0;
   for (int e = threadIdx.x; e < L.nm_total; e += blockDim.x) {
@@ -250,6 +258,63 @@ __global__ void __launch_bounds__(256) unfold_kernel(FParams p) {
     p.ph[((size_t)(L.mlist_src[e] * L.ncomp_tot + L.comp0 + c) * L.NML + L.mlist_im[e]) * L.NPL + L.pair0 + pair] =
         make_double4(xn.x, xn.y, xs.x, xs.y);
   }
+}
+__global__ void __launch_bounds__(256) unfold_kernel(FParams p, int first_pair) {
+  const int pair = first_pair + blockIdx.x, c = blockIdx.y;
+  unfold_from(p, pair, c, p.buf + zoff(p, pair, c));
+}
+
+// ---- fused chirp-z ring transform for the Bluestein classes whose work length fits in shared memory
+// (M <= 8192: 128 KB): fold | gather -> FFT_M -> .* V -> IFFT_M -> scatter | unfold in ONE kernel, one CTA per
+// (ring pair, component).  The separate path moves the padded length-M array through HBM about 13 times (fold
+// write, two cuFFT passes, the multiply, two more cuFFT passes, scatter read); here HBM sees the phases, the
+// filter spectrum and the map once.  FFT pair: blue_fft.cuh (DIF forward, bit-reversed V, DIT inverse).
+template <int DIR, int NT>
+__global__ void __launch_bounds__(NT) blue_fused_kernel(FParams p, int first_pair, int M, const double2 *__restrict__ tw,
+                                                        const double2 *__restrict__ vbr) {
+  extern __shared__ double2 u_sm[];                 // M work elements, then the pass-major twiddle table
+  __shared__ double2 part_sum[DIR == 0 ? NT : 1];
+  const int pair = first_pair + blockIdx.x, c = blockIdx.y;
+  double2 *T = u_sm + M;
+  const int ntw = bf_tw_total(M);
+  for (int k = threadIdx.x; k < ntw; k += NT) T[k] = tw[k];
+  if (DIR == 0) fold_into<NT>(p, pair, c, u_sm, M, part_sum); else gather_into(p, pair, c, u_sm);
+  __syncthreads();
+  const int np = bf_num_passes(M);
+  for (int k = 0; k < np; ++k) {
+    int h, fused;
+    bf_pass(M, k, &h, &fused);
+    const double2 *Tk = T + bf_tw_offset(M, k);
+    if (fused) { for (int q = threadIdx.x; q < M / 4; q += NT) dif_item4(u_sm, h, Tk, q); }
+    else { for (int q = threadIdx.x; q < M / 2; q += NT) dif_item2(u_sm, q); }
+    __syncthreads();
+  }
+  const double2 *v = vbr + p.zbase[pair] + (size_t)p.zidx[pair] * M;
+  for (int k = threadIdx.x; k < M; k += NT) u_sm[k] = cmul(u_sm[k], v[k]);
+  __syncthreads();
+  for (int k = np - 1; k >= 0; --k) {
+    int h, fused;
+    bf_pass(M, k, &h, &fused);
+    const double2 *Tk = T + bf_tw_offset(M, k);
+    if (fused) { for (int q = threadIdx.x; q < M / 4; q += NT) dit_item4(u_sm, h, Tk, q); }
+    else { for (int q = threadIdx.x; q < M / 2; q += NT) dit_item2(u_sm, q); }
+    __syncthreads();
+  }
+  if (DIR == 0) scatter_from(p, pair, c, u_sm); else unfold_from(p, pair, c, u_sm);
+}
+
+// twiddles of one fused pass with leading half-size h: T[j] = exp(-i pi j / h), j < h/2 (blue_fft.cuh)
+__global__ void twiddle_kernel(double2 *T, int h) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < h / 2) { double2 e = expipi(j, h); T[j] = make_double2(e.x, -e.y); }
+}
+
+// filter spectra of the fused classes in bit-reversed order
+__global__ void __launch_bounds__(256) bitrev_filter_kernel(FParams p, int first_pair, int bits, double2 *vbr) {
+  const int pair = first_pair + blockIdx.x;
+  const int len = p.zlen[pair];
+  const size_t o = p.zbase[pair] + (size_t)p.zidx[pair] * len;
+  for (int k = threadIdx.x; k < len; k += blockDim.x) vbr[o + k] = p.vtab[o + bf_bitrev((unsigned)k, bits)];
 }
 
 // ---------------------------------------------------------------- host side
@@ -275,8 +340,71 @@ static FParams base_params(sharp_geom_info *g, int ncomp, const PhaseLayout &L, 
   return p;
 }
 
-static void run_ffts(sharp_geom_info *g, int ncomp, double2 *buf, int direct_dir, FParams &p, cudaStream_t st) {
-  for (size_t r = 0; r < g->regions.size(); ++r) {
+// Leading Bluestein regions that take the fused shared-memory kernel (work length <= 8192 complex = 128 KB):
+// returns the number of ring pairs they cover (they come first in pair order) and their count in *nregions.
+// Opt-in (CMDR_SHT_FUSED_BLUE=1) until it beats the cuFFT path on hardware; the default sends every class through cuFFT.
+static int fused_prefix(const sharp_geom_info *g, int *nregions) {
+  static const bool enabled = getenv("CMDR_SHT_FUSED_BLUE") && atoi(getenv("CMDR_SHT_FUSED_BLUE")) != 0;
+  int nr = 0, np = 0;
+  if (enabled)
+    for (const FftRegion &R : g->regions) {
+      if (!R.bluestein || R.len > 8192 || R.first != np) break;
+      ++nr; np += R.np;
+    }
+  *nregions = nr;
+  return np;
+}
+
+static const double2 *twiddle_table(int M, cudaStream_t st) {
+  static std::map<long long, double2 *> tabs;       // (device, M)
+  int dev = 0;
+  CMDR_CUDA_CHECK(cudaGetDevice(&dev));
+  const long long key = ((long long)dev << 32) | (unsigned)M;
+  auto it = tabs.find(key);
+  if (it != tabs.end()) return it->second;
+  double2 *t = nullptr;
+  CMDR_CUDA_CHECK(cudaMalloc(&t, sizeof(double2) * (size_t)(bf_tw_total(M) + 1)));
+  const int np = bf_num_passes(M);
+  for (int k = 0; k < np; ++k) {
+    int h, fused;
+    bf_pass(M, k, &h, &fused);
+    if (!fused) continue;
+    twiddle_kernel<<<(h / 2 + 255) / 256, 256, 0, st>>>(t + bf_tw_offset(M, k), h);
+    count_launch();
+  }
+  CMDR_CUDA_CHECK(cudaGetLastError());
+  tabs[key] = t;
+  return t;
+}
+
+// threads per CTA of the fused kernel by work length: a pass has M/4 work items
+template <int DIR>
+static void launch_fused(sharp_geom_info *g, int ncomp, int nregions, const FParams &p, cudaStream_t st) {
+  static bool attr_set = false;
+  const int max_smem = (int)(sizeof(double2) * (8192 + bf_tw_total(8192)));
+  if (!attr_set) {
+    attr_set = true;
+    CMDR_CUDA_CHECK(cudaFuncSetAttribute(blue_fused_kernel<DIR, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    CMDR_CUDA_CHECK(cudaFuncSetAttribute(blue_fused_kernel<DIR, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    CMDR_CUDA_CHECK(cudaFuncSetAttribute(blue_fused_kernel<DIR, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+  }
+  const double2 *vbr = reinterpret_cast<const double2 *>(g->d_vtab_br);
+  for (int r = 0; r < nregions; ++r) {
+    const FftRegion &R = g->regions[r];
+    if (R.np == 0) continue;
+    const double2 *tw = twiddle_table(R.len, st);
+    const size_t smem = sizeof(double2) * (size_t)(R.len + bf_tw_total(R.len));
+    if (R.len <= 2048) blue_fused_kernel<DIR, 256><<<dim3(R.np, ncomp), 256, smem, st>>>(p, R.first, R.len, tw, vbr);
+    else if (R.len <= 4096) blue_fused_kernel<DIR, 512><<<dim3(R.np, ncomp), 512, smem, st>>>(p, R.first, R.len, tw, vbr);
+    else blue_fused_kernel<DIR, 1024><<<dim3(R.np, ncomp), 1024, smem, st>>>(p, R.first, R.len, tw, vbr);
+    count_launch();
+  }
+  CMDR_CUDA_CHECK(cudaGetLastError());
+}
+
+static void run_ffts(sharp_geom_info *g, int ncomp, double2 *buf, int direct_dir, FParams &p, cudaStream_t st,
+                     size_t first_region = 0) {
+  for (size_t r = first_region; r < g->regions.size(); ++r) {
     const FftRegion &R = g->regions[r];
     if (R.np == 0) continue;
     cufftHandle h = get_plan(g, (int)r, ncomp);
@@ -312,6 +440,23 @@ static void ensure_vtab(sharp_geom_info *g, cudaStream_t st) {
     CMDR_CUFFT_CHECK(cufftExecZ2Z(h, d, d, CUFFT_FORWARD));
     count_launch(2);
   }
+  // the fused classes read their filter spectra in bit-reversed order (same offsets: they are the leading regions)
+  int nfr = 0;
+  fused_prefix(g, &nfr);
+  if (nfr > 0) {
+    const FftRegion &last = g->regions[nfr - 1];
+    const size_t flen = (size_t)last.base + (size_t)last.np * last.len;
+    CMDR_CUDA_CHECK(cudaMalloc(&g->d_vtab_br, sizeof(double2) * flen));
+    p.vtab = reinterpret_cast<const double2 *>(g->d_vtab);
+    for (int r = 0; r < nfr; ++r) {
+      const FftRegion &R = g->regions[r];
+      if (R.np == 0) continue;
+      int bits = 0;
+      while ((1 << bits) < R.len) ++bits;
+      bitrev_filter_kernel<<<R.np, 256, 0, st>>>(p, R.first, bits, reinterpret_cast<double2 *>(g->d_vtab_br));
+      count_launch();
+    }
+  }
   CMDR_CUDA_CHECK(cudaGetLastError());
 }
 
@@ -324,10 +469,14 @@ void ringfft_synth(sharp_geom_info *g, int ncomp, const PhaseLayout &L, const do
   p.ph = const_cast<double4 *>(ph);
   p.map0 = map[0]; p.map1 = ncomp > 1 ? map[1] : nullptr; p.map2 = ncomp > 2 ? map[2] : nullptr;
   p.weighted = weighted; p.add = add;
-  // all pairs that need the generic (aliasing) fold go in ONE launch: the blocks of short rings are
+  int nfr = 0;
+  const int nf = fused_prefix(g, &nfr);               // pairs [0, nf): fold + FFTs + scatter in one kernel per class
+  launch_fused<0>(g, ncomp, nfr, p, st);
+  if (nf == g->npairs) return;
+  // all remaining pairs that need the generic (aliasing) fold go in ONE launch: the blocks of short rings are
   // latency bound (long m chains per bin) and must overlap the big ones instead of queueing
   int gen_first = -1, gen_np = 0;
-  for (size_t r = 0; r < g->regions.size(); ++r) {
+  for (size_t r = nfr; r < g->regions.size(); ++r) {
     const FftRegion &R = g->regions[r];
     if (R.np == 0) continue;
     if (!R.bluestein && R.len >= 2 * L.mmax + 1) {      // no aliasing: coalesced transpose
@@ -347,8 +496,8 @@ void ringfft_synth(sharp_geom_info *g, int ncomp, const PhaseLayout &L, const do
     fold_kernel<<<dim3(gen_np, ncomp), 256, 0, st>>>(p, gen_first);
     count_launch();
   }
-  run_ffts(g, ncomp, buf, CUFFT_INVERSE, p, st);
-  scatter_kernel<<<dim3(g->npairs, ncomp), 256, 0, st>>>(p);
+  run_ffts(g, ncomp, buf, CUFFT_INVERSE, p, st, nfr);
+  scatter_kernel<<<dim3(g->npairs - nf, ncomp), 256, 0, st>>>(p, nf);
   count_launch();
   CMDR_CUDA_CHECK(cudaGetLastError());
 }
@@ -364,10 +513,14 @@ void ringfft_anal(sharp_geom_info *g, int ncomp, const PhaseLayout &L, double4 *
   p.map1 = ncomp > 1 ? const_cast<double *>(map[1]) : nullptr;
   p.map2 = ncomp > 2 ? const_cast<double *>(map[2]) : nullptr;
   p.weighted = weighted;
-  gather_kernel<<<dim3(g->npairs, ncomp), 256, 0, st>>>(p);
+  int nfr = 0;
+  const int nf = fused_prefix(g, &nfr);
+  launch_fused<1>(g, ncomp, nfr, p, st);
+  if (nf == g->npairs) return;
+  gather_kernel<<<dim3(g->npairs - nf, ncomp), 256, 0, st>>>(p, nf);
   count_launch();
-  run_ffts(g, ncomp, buf, CUFFT_FORWARD, p, st);
-  unfold_kernel<<<dim3(g->npairs, ncomp), 256, 0, st>>>(p);
+  run_ffts(g, ncomp, buf, CUFFT_FORWARD, p, st, nfr);
+  unfold_kernel<<<dim3(g->npairs - nf, ncomp), 256, 0, st>>>(p, nf);
   count_launch();
   CMDR_CUDA_CHECK(cudaGetLastError());
 }

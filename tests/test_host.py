@@ -149,3 +149,47 @@ def test_device_recurrence_math_arbitrary_spin(emul, spin):
                 rp, rm = float(D.slam(l, m, spin, cth, sth)), float(D.slam(l, m, -spin, cth, sth))
                 sc = max(abs(rp), abs(rm))
                 assert abs(P[l] - rp) <= 1e-11 * sc + 1e-19 and abs(M[l] - rm) <= 1e-11 * sc + 1e-19, (m, north, l)
+
+
+@pytest.fixture(scope="module")
+def emul_fft():
+    """tests/host_emul/emul_bluefft.cpp: the product's blue_fft.cuh executed on the host."""
+    src = os.path.join(ROOT, "tests", "host_emul", "emul_bluefft.cpp")
+    hdr = os.path.join(ROOT, "commander_b200", "csrc", "blue_fft.cuh")
+    out = os.path.join(ROOT, "tests", "host_emul", "_build")
+    os.makedirs(out, exist_ok=True)
+    so = os.path.join(out, "libemul_bluefft.so")
+    if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
+        subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-o", so, src])
+    L = C.CDLL(so)
+    L.emul_fft.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
+    L.emul_bitrev.argtypes = [C.c_uint, C.c_int]
+    L.emul_bitrev.restype = C.c_uint
+    return L
+
+
+@pytest.mark.parametrize("M", [4, 8, 16, 32, 1024, 2048, 4096, 8192])
+def test_blue_fft_pair_on_host(emul_fft, M):
+    """DIF forward = numpy FFT in bit-reversed order; DIT inverse of a bit-reversed spectrum = M * ifft; and the
+    circular convolution u -> DIT(DIF(u) .* V_bitrev) the fused Bluestein kernels rely on."""
+    rng = np.random.default_rng(M)
+    bits = M.bit_length() - 1
+    br = np.array([emul_fft.emul_bitrev(i, bits) for i in range(M)])
+    assert np.array_equal(br[br], np.arange(M))
+    x = rng.standard_normal(M) + 1j * rng.standard_normal(M)
+    for nthreads in (1, 7, 256):
+        y = x.copy()
+        emul_fft.emul_fft(y.ctypes.data, M, 0, nthreads)
+        ref = np.fft.fft(x)
+        assert np.abs(y - ref[br]).max() <= 1e-12 * np.abs(ref).max()
+        z = y.copy()
+        emul_fft.emul_fft(z.ctypes.data, M, 1, nthreads)
+        assert np.abs(z - M * x).max() <= 1e-12 * M * np.abs(x).max()
+    v = rng.standard_normal(M) + 1j * rng.standard_normal(M)
+    V = np.fft.fft(v)
+    u = x.copy()
+    emul_fft.emul_fft(u.ctypes.data, M, 0, 64)
+    u *= V[br]
+    emul_fft.emul_fft(u.ctypes.data, M, 1, 64)
+    conv = np.fft.ifft(np.fft.fft(x) * V) * M
+    assert np.abs(u - conv).max() <= 1e-11 * np.abs(conv).max()
