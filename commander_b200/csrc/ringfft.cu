@@ -342,9 +342,9 @@ static FParams base_params(sharp_geom_info *g, int ncomp, const PhaseLayout &L, 
 
 // Leading Bluestein regions that take the fused shared-memory kernel (work length <= 8192 complex = 128 KB):
 // returns the number of ring pairs they cover (they come first in pair order) and their count in *nregions.
-// Opt-in (CMDR_SHT_FUSED_BLUE=1) until it beats the cuFFT path on hardware; the default sends every class through cuFFT.
+// CMDR_SHT_FUSED_BLUE=0 sends every class through cuFFT instead (cross-check / tuning).
 static int fused_prefix(const sharp_geom_info *g, int *nregions) {
-  static const bool enabled = getenv("CMDR_SHT_FUSED_BLUE") && atoi(getenv("CMDR_SHT_FUSED_BLUE")) != 0;
+  static const bool enabled = !(getenv("CMDR_SHT_FUSED_BLUE") && atoi(getenv("CMDR_SHT_FUSED_BLUE")) == 0);
   int nr = 0, np = 0;
   if (enabled)
     for (const FftRegion &R : g->regions) {
@@ -377,9 +377,26 @@ static const double2 *twiddle_table(int M, cudaStream_t st) {
   return t;
 }
 
-// threads per CTA of the fused kernel by work length: a pass has M/4 work items
+// side streams of the fused classes: the classes are independent of each other and of the belt path, and the
+// small ones are latency bound (few CTAs, long m chains per bin), so all of them run concurrently
+static cudaStream_t class_stream(int k) {
+  static std::map<long long, cudaStream_t> cs;       // (device, k)
+  int dev = 0;
+  CMDR_CUDA_CHECK(cudaGetDevice(&dev));
+  const long long key = ((long long)dev << 8) | k;
+  auto it = cs.find(key);
+  if (it != cs.end()) return it->second;
+  cudaStream_t s;
+  CMDR_CUDA_CHECK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+  cs[key] = s;
+  return s;
+}
+
+// Launches the fused classes on side streams that fork from `st`; returns how many streams join_fused must
+// join back.  Threads per CTA by work length: a pass has M/4 work items.
 template <int DIR>
-static void launch_fused(sharp_geom_info *g, int ncomp, int nregions, const FParams &p, cudaStream_t st) {
+static int launch_fused(sharp_geom_info *g, int ncomp, int nregions, const FParams &p, cudaStream_t st) {
+  if (nregions == 0) return 0;
   static bool attr_set = false;
   const int max_smem = (int)(sizeof(double2) * (8192 + bf_tw_total(8192)));
   if (!attr_set) {
@@ -389,17 +406,29 @@ static void launch_fused(sharp_geom_info *g, int ncomp, int nregions, const FPar
     CMDR_CUDA_CHECK(cudaFuncSetAttribute(blue_fused_kernel<DIR, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
   }
   const double2 *vbr = reinterpret_cast<const double2 *>(g->d_vtab_br);
-  for (int r = 0; r < nregions; ++r) {
+  for (int r = 0; r < nregions; ++r) twiddle_table(g->regions[r].len, st);     // built on st before the fork
+  cudaEvent_t e0 = pooled_event(150);
+  CMDR_CUDA_CHECK(cudaEventRecord(e0, st));
+  int ns = 0;
+  for (int r = nregions - 1; r >= 0; --r) {                                   // longest class first
     const FftRegion &R = g->regions[r];
     if (R.np == 0) continue;
+    cudaStream_t cs = class_stream(ns);
+    CMDR_CUDA_CHECK(cudaStreamWaitEvent(cs, e0, 0));
     const double2 *tw = twiddle_table(R.len, st);
     const size_t smem = sizeof(double2) * (size_t)(R.len + bf_tw_total(R.len));
-    if (R.len <= 2048) blue_fused_kernel<DIR, 256><<<dim3(R.np, ncomp), 256, smem, st>>>(p, R.first, R.len, tw, vbr);
-    else if (R.len <= 4096) blue_fused_kernel<DIR, 512><<<dim3(R.np, ncomp), 512, smem, st>>>(p, R.first, R.len, tw, vbr);
-    else blue_fused_kernel<DIR, 1024><<<dim3(R.np, ncomp), 1024, smem, st>>>(p, R.first, R.len, tw, vbr);
+    if (R.len <= 2048) blue_fused_kernel<DIR, 256><<<dim3(R.np, ncomp), 256, smem, cs>>>(p, R.first, R.len, tw, vbr);
+    else if (R.len <= 4096) blue_fused_kernel<DIR, 512><<<dim3(R.np, ncomp), 512, smem, cs>>>(p, R.first, R.len, tw, vbr);
+    else blue_fused_kernel<DIR, 1024><<<dim3(R.np, ncomp), 1024, smem, cs>>>(p, R.first, R.len, tw, vbr);
     count_launch();
+    CMDR_CUDA_CHECK(cudaEventRecord(pooled_event(151 + ns), cs));
+    ++ns;
   }
   CMDR_CUDA_CHECK(cudaGetLastError());
+  return ns;
+}
+static void join_fused(int ns, cudaStream_t st) {
+  for (int k = 0; k < ns; ++k) CMDR_CUDA_CHECK(cudaStreamWaitEvent(st, pooled_event(151 + k), 0));
 }
 
 static void run_ffts(sharp_geom_info *g, int ncomp, double2 *buf, int direct_dir, FParams &p, cudaStream_t st,
@@ -471,8 +500,8 @@ void ringfft_synth(sharp_geom_info *g, int ncomp, const PhaseLayout &L, const do
   p.weighted = weighted; p.add = add;
   int nfr = 0;
   const int nf = fused_prefix(g, &nfr);               // pairs [0, nf): fold + FFTs + scatter in one kernel per class
-  launch_fused<0>(g, ncomp, nfr, p, st);
-  if (nf == g->npairs) return;
+  const int nside_streams = launch_fused<0>(g, ncomp, nfr, p, st);
+  if (nf == g->npairs) { join_fused(nside_streams, st); return; }
   // all remaining pairs that need the generic (aliasing) fold go in ONE launch: the blocks of short rings are
   // latency bound (long m chains per bin) and must overlap the big ones instead of queueing
   int gen_first = -1, gen_np = 0;
@@ -500,6 +529,7 @@ void ringfft_synth(sharp_geom_info *g, int ncomp, const PhaseLayout &L, const do
   scatter_kernel<<<dim3(g->npairs - nf, ncomp), 256, 0, st>>>(p, nf);
   count_launch();
   CMDR_CUDA_CHECK(cudaGetLastError());
+  join_fused(nside_streams, st);
 }
 
 void ringfft_anal(sharp_geom_info *g, int ncomp, const PhaseLayout &L, double4 *ph,
@@ -515,14 +545,15 @@ void ringfft_anal(sharp_geom_info *g, int ncomp, const PhaseLayout &L, double4 *
   p.weighted = weighted;
   int nfr = 0;
   const int nf = fused_prefix(g, &nfr);
-  launch_fused<1>(g, ncomp, nfr, p, st);
-  if (nf == g->npairs) return;
+  const int nside_streams = launch_fused<1>(g, ncomp, nfr, p, st);
+  if (nf == g->npairs) { join_fused(nside_streams, st); return; }
   gather_kernel<<<dim3(g->npairs - nf, ncomp), 256, 0, st>>>(p, nf);
   count_launch();
   run_ffts(g, ncomp, buf, CUFFT_FORWARD, p, st, nfr);
   unfold_kernel<<<dim3(g->npairs - nf, ncomp), 256, 0, st>>>(p, nf);
   count_launch();
   CMDR_CUDA_CHECK(cudaGetLastError());
+  join_fused(nside_streams, st);
 }
 
 void destroy_plans(sharp_geom_info *g) {
