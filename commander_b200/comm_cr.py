@@ -226,3 +226,241 @@ def solve_cr_eqn_by_CG(sys: cr_cmb_system, b, maxiter=300, cg_tol=1e-8, cg_conv_
         if verbose:
             print(f"  CG iter. {i:5d} -- res = {delta_new:13.5e}, tol = {lim_convergence:13.5e}")
     return x, it, hist
+
+
+# =====================================================================================================
+# General system: several diffuse components seen through several bands (cr_matmulA as written,
+# commander3/src/comm_cr_mod.f90:771-1024, diffuse components only)
+# =====================================================================================================
+
+class cr_component:
+    """What cr_matmulA needs of a `comm_diffuse_comp`: the amplitude layout x%info (nside, lmax_amp, nmaps), an
+    optional diagonal prior C_l (cltype /= 'none'), and per band either F_mean (nmaps scalars, spectral parameters
+    constant on the sky) or a per-pixel mixing map F (commander3/src/comm_diffuse_comp_mod.f90:2070-2083)."""
+
+    def __init__(self, x_info: comm_mapinfo, Cl=None, F_mean=None, F=None):
+        self.x_info = x_info
+        self.lmax_amp = x_info.lmax
+        self.nmaps = x_info.nmaps
+        self.Cl = None if Cl is None else np.asarray(Cl, dtype=np.float64)
+        self.F_mean = np.asarray(F_mean, dtype=np.float64)     # (numband, nmaps); also feeds the preconditioner
+        self.F = F                                             # None or a list (numband) of None / (nmaps, np) arrays
+
+
+class cr_band:
+    """One frequency band: data(i)%info, N%invN as siN^2 (x mask) per pixel, beam b_l(0:lmax, nmaps)."""
+
+    def __init__(self, info: comm_mapinfo, invN, b_l):
+        self.info, self.invN, self.b_l = info, invN, np.asarray(b_l, dtype=np.float64)
+
+
+class cr_system:
+    """A = P + sqrt(S) sum_nu F^t B^t Y^t N^-1 Y B F sqrt(S) over all diffuse components (P = 1 on components
+    with a prior, 0 on the others; sqrt(S) = 1 on the latter).  x is the flat vector of cr_extract_comp /
+    cr_insert_comp (:408-540): component after component, each (nmaps, nalm) in memory order."""
+
+    def __init__(self, comps, bands, device):
+        import torch
+        from .comm_diffuse_comp import diffuse_band
+        self.torch, self.dev = torch, device
+        self.comps, self.bands = list(comps), list(bands)
+        self.off = [0]
+        for c in self.comps:
+            self.off.append(self.off[-1] + c.nmaps * c.x_info.nalm)
+        self.ncr = self.off[-1]
+        self.lmax = max(max(c.lmax_amp for c in self.comps), 2)                 # :809
+        self.sqrtS = []
+        for c in self.comps:
+            if c.Cl is None:
+                self.sqrtS.append(None)
+                continue
+            l = c.x_info.lm[0].astype(np.int64)
+            sS = np.stack([np.sqrt(np.maximum(c.Cl[l, j], 0.0)) for j in range(c.nmaps)])
+            for j in range(1, c.nmaps):
+                sS[j, l < 2] = 0.0
+            self.sqrtS.append(torch.as_tensor(sS, device=device))
+        # (component, band) operators: re-pack + mixing + beam and its transpose
+        self.cb = []
+        for c in self.comps:
+            row = []
+            for q, b in enumerate(self.bands):
+                nm = min(b.info.nmaps, c.nmaps)
+                binfo = b.info if nm == b.info.nmaps else comm_mapinfo(b.info.comm, b.info.nside, b.info.lmax, nm, nm == 3)
+                Fq = None if c.F is None else c.F[q]
+                if Fq is not None and not hasattr(Fq, "device"):
+                    Fq = torch.as_tensor(np.ascontiguousarray(Fq[:nm]), device=device)
+                row.append(diffuse_band(c.x_info, binfo, b.b_l[:, :nm], F=Fq,
+                                        F_mean=None if Fq is not None else c.F_mean[q, :nm], device=device))
+            self.cb.append(row)
+        # one buffer pair per band: the band layout, and the synthesis layout at lmax = max lmax_amp (:877-882)
+        self.bmap = [comm_map(b.info, device=device) for b in self.bands]
+        self.ymap = [comm_map(comm_mapinfo(b.info.comm, b.info.nside, self.lmax, b.info.nmaps, b.info.nmaps == 3), device=device)
+                     for b in self.bands]
+        self.xbuf = [comm_map(c.x_info, device=device) for c in self.comps]
+        self.n_matmul = 0
+        self.Minv = None
+
+    # -- vector layout
+    def extract_comp(self, i, x):
+        """cr_extract_comp: view of component i as (nmaps, nalm)."""
+        c = self.comps[i]
+        return x[self.off[i]:self.off[i + 1]].view(c.nmaps, c.x_info.nalm)
+
+    def _comm(self):
+        return self.bands[0].info.comm
+
+    def _allreduce(self, t):
+        c = self._comm()
+        if self.bands[0].info.dist and c.size > 1:
+            c.allreduce_sum_(t)
+        return t
+
+    def mpi_dot_product(self, a, b):
+        s = self.torch.dot(a.reshape(-1), b.reshape(-1)).reshape(1)
+        self._allreduce(s)
+        return float(s.item())
+
+    # -- band passes
+    def _to_band(self, q, sx):
+        """sum over components of getBand(q, alm_out) (:858-864), then Y at lmax (:877-882); returns the band map."""
+        m = self.bmap[q]
+        m.alm.zero_()
+        for i, c in enumerate(self.comps):
+            xb = self.xbuf[i]
+            xb.alm.copy_(self.extract_comp(i, sx))
+            a = self.cb[i][q].evalDiffuseBand(xb, alm_out=True)
+            m.alm[:a.shape[0]] += a
+        y = self.ymap[q]
+        m.alm_equal(y)
+        y.Y()
+        return y
+
+    def _from_band(self, q, y, out):
+        """Yt at lmax (:913-918), then projectBand(q, alm_in) into every component, accumulated into `out` (:926-934)."""
+        m = self.bmap[q]
+        y.Yt()
+        y.alm_equal(m)
+        for i, c in enumerate(self.comps):
+            nm = self.cb[i][q].band_info.nmaps
+            sub = m if nm == m.info.nmaps else _view_maps(m, self.cb[i][q].band_info, nm)
+            self.extract_comp(i, out).add_(self.cb[i][q].projectDiffuseBand(sub, alm_in=True))
+
+    def matmulA(self, x):
+        torch = self.torch
+        sx = x.clone()
+        for i, sS in enumerate(self.sqrtS):
+            if sS is not None:
+                self.extract_comp(i, sx).mul_(sS)                               # :797-836
+        y = torch.zeros_like(x)
+        for q, b in enumerate(self.bands):
+            ym = self._to_band(q, sx)
+            ym.map.mul_(b.invN)                                                 # :905
+            self._from_band(q, ym, y)
+        for i, sS in enumerate(self.sqrtS):
+            if sS is not None:
+                yi = self.extract_comp(i, y)
+                yi.mul_(sS)                                                     # :957-1008
+                yi.add_(self.extract_comp(i, x))
+        self.n_matmul += 1
+        return y
+
+    def computeRHS(self, data, eta_pix=None, eta_alm=None):
+        """cr_computeRHS (:542-769): sum over bands of sqrt(S) F^t B^t Y^t (N^-1 d + N^-1/2 eta_nu), plus the prior
+        fluctuation eta_0 on the components that have a prior."""
+        torch = self.torch
+        rhs = torch.zeros(self.ncr, dtype=torch.float64, device=self.dev)
+        for q, b in enumerate(self.bands):
+            ym = self.ymap[q]
+            ym.map.copy_(data[q] * b.invN)
+            if eta_pix is not None:
+                ym.map.add_(torch.sqrt(b.invN) * eta_pix[q])
+            self._from_band(q, ym, rhs)
+        for i, sS in enumerate(self.sqrtS):
+            if sS is not None:
+                ri = self.extract_comp(i, rhs)
+                ri.mul_(sS)
+                if eta_alm is not None:
+                    ri.add_(self.extract_comp(i, eta_alm))
+        return rhs
+
+    # -- preconditioner
+    def initDiffPrecond_diagonal(self):
+        """initDiffPrecond_diagonal + updateDiffPrecond_diagonal, commander3/src/comm_diffuse_comp_mod.f90:1167-1252,
+        1313-1557: per (l, m, pol) the npre x npre matrix sqrt(S) [sum_nu N^-1_lm b_l^2 F_k1 F_k2] sqrt(S) + P on the
+        components that reach this l, inverted; N^-1_lm from compute_invN_lm on every band."""
+        torch = self.torch
+        npre = len(self.comps)
+        nmaps_pre = max(c.nmaps for c in self.comps)
+        b0 = self.bands[0].info
+        pre = comm_mapinfo(b0.comm, b0.nside, self.lmax, nmaps_pre, nmaps_pre == 3)
+        self.info_pre = pre
+        l, m = pre.lm[0].astype(np.int64), pre.lm[1].astype(np.int64)
+        mat = torch.zeros((nmaps_pre, pre.nalm, npre, npre), dtype=torch.float64, device=self.dev)
+        for q, b in enumerate(self.bands):
+            nd = comm_map(b.info, device=self.dev)
+            nd.map.copy_(b.invN)
+            compute_invN_lm(nd)                                                  # data(q)%N%invN_diag
+            i2 = b.info.lm2i_vec(l, m)
+            ok = torch.as_tensor(i2 >= 0, device=self.dev)
+            idx = torch.as_tensor(np.maximum(i2, 0), device=self.dev)
+            for j in range(min(nmaps_pre, b.info.nmaps)):
+                w = torch.where(ok, nd.alm[j, idx], torch.zeros((), dtype=torch.float64, device=self.dev))
+                w = w * torch.as_tensor(b.b_l[np.minimum(l, b.info.lmax), j] ** 2, device=self.dev)
+                for k1, c1 in enumerate(self.comps):
+                    if j >= c1.nmaps:
+                        continue
+                    r1 = torch.as_tensor((l <= c1.lmax_amp) * c1.F_mean[q, j], device=self.dev)
+                    for k2, c2 in enumerate(self.comps):
+                        if j >= c2.nmaps:
+                            continue
+                        r2 = torch.as_tensor((l <= c2.lmax_amp) * c2.F_mean[q, j], device=self.dev)
+                        mat[j, :, k1, k2] += w * r1 * r2
+        active = torch.diagonal(mat, dim1=2, dim2=3) > 0.0                       # comp2ind /= -1, :1232-1239
+        # sqrt(S) on both sides and the unit prior term for components with a C_l (:1350-1470)
+        for k, c in enumerate(self.comps):
+            if c.Cl is None:
+                continue
+            sS = np.zeros((nmaps_pre, pre.nalm))
+            for j in range(c.nmaps):
+                sS[j] = np.sqrt(np.maximum(c.Cl[np.minimum(l, c.lmax_amp), j], 0.0)) * (l <= c.lmax_amp)
+                if j > 0:
+                    sS[j, l < 2] = 0.0
+            sS = torch.as_tensor(sS, device=self.dev)
+            mat[:, :, k, :] *= sS[:, :, None]
+            mat[:, :, :, k] *= sS[:, :, None]
+            unit = torch.as_tensor((l <= c.lmax_amp).astype(np.float64), device=self.dev)[None, :] * active[:, :, k]
+            mat[:, :, k, k] += unit
+        # invert on the active set: inactive components pass through unchanged (applyDiffPrecond_diagonal, :2186-2235)
+        eye = torch.eye(npre, dtype=torch.float64, device=self.dev)
+        act2 = active[:, :, :, None] & active[:, :, None, :]
+        full = torch.where(act2, mat, torch.zeros_like(mat)) + eye * (~active)[:, :, :, None]
+        self.Minv = torch.linalg.inv(full)
+        # index maps between every component's layout and info_pre
+        self.pre_idx = []
+        for c in self.comps:
+            k = pre.lm2i_vec(c.x_info.lm[0], c.x_info.lm[1])
+            self.pre_idx.append(torch.as_tensor(k, device=self.dev))
+
+    def invM(self, r):
+        """applyDiffPrecond_diagonal, :2186-2235."""
+        torch = self.torch
+        if self.Minv is None:
+            self.initDiffPrecond_diagonal()
+        npre = len(self.comps)
+        nmaps_pre, nalm_pre = self.Minv.shape[0], self.Minv.shape[1]
+        yv = torch.zeros((nmaps_pre, nalm_pre, npre), dtype=torch.float64, device=self.dev)
+        for i, c in enumerate(self.comps):
+            yv[:c.nmaps, self.pre_idx[i], i] = self.extract_comp(i, r)
+        yv = torch.einsum("jakb,jab->jak", self.Minv, yv)
+        out = torch.empty_like(r)
+        for i, c in enumerate(self.comps):
+            self.extract_comp(i, out).copy_(yv[:c.nmaps, self.pre_idx[i], i])
+        return out
+
+
+def _view_maps(m: comm_map, info: comm_mapinfo, nm: int) -> comm_map:
+    """The first nm columns of m's a_lm as a comm_map on `info` (same nside / lmax, fewer maps)."""
+    v = comm_map.__new__(comm_map)
+    v.info, v.device = info, m.device
+    v.alm, v.map = m.alm[:nm], m.map[:nm]
+    return v

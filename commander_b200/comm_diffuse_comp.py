@@ -22,6 +22,9 @@ from . import sharp
 from .comm_map import comm_map, comm_mapinfo
 
 
+_conv_cache: dict = {}   # per (layout, beam, device): b_l expanded over the alm slots
+
+
 def mix(m: comm_map, F) -> None:
     """m%alm <- YtW(F .* Y(m%alm)); F has shape (nmaps, np), on the host (numpy) or the device (torch).
     commander3/src/comm_diffuse_comp_mod.f90:2078-2080 / :2148-2150."""
@@ -40,12 +43,16 @@ def _conv(m: comm_map, b_l) -> None:
     """B%conv, commander3/src/comm_B_bl_mod.f90:108-127: alm(l,m,j) *= b_l(l,j) (its own transpose)."""
     l = m.info.lm[0]
     nm = m.info.nmaps
-    fac = np.stack([np.asarray(b_l)[l, j] for j in range(nm)])
     if m.device is None:
-        m.alm *= fac
+        m.alm *= np.stack([np.asarray(b_l)[l, j] for j in range(nm)])
     else:
         import torch
-        m.alm *= torch.as_tensor(fac, device=m.alm.device)
+        key = (id(m.info), id(b_l), str(m.alm.device))
+        fac = _conv_cache.get(key)
+        if fac is None:
+            fac = (torch.as_tensor(np.stack([np.asarray(b_l)[l, j] for j in range(nm)]), device=m.alm.device), m.info, b_l)
+            _conv_cache[key] = fac
+        m.alm *= fac[0]
 
 
 class diffuse_band:

@@ -38,6 +38,7 @@ def _ring_start(nside: int, ring: int) -> int:
     return ofs if north == ring else npix - nph - ofs
 
 
+_repack_cache: dict = {}   # alm_equal index pairs for device-resident maps
 _mapinfos: list = []   # the `mapinfos` linked list, commander3/src/comm_map_mod.f90:157-169
 
 
@@ -298,17 +299,25 @@ class comm_map:
     # commander3/src/comm_map_mod.f90:1148-1211
     def alm_equal(self, other: "comm_map"):
         """other%alm = self%alm on the (l,m) both hold, zero elsewhere."""
-        j = self.info.lm2i_vec(other.info.lm[0], other.info.lm[1])
         q = min(self.info.nmaps, other.info.nmaps)
-        ok = j >= 0
         other.alm[...] = 0.0
         if self.device is None and other.device is None:
+            j = self.info.lm2i_vec(other.info.lm[0], other.info.lm[1])
+            ok = j >= 0
             other.alm[:q, ok] = self.alm[:q, j[ok]]
         else:
+            # the index pair is a function of the two layouts only: built once per (layout, layout, device)
+            # (the reference redoes the lm2i loop on every call, comm_cr_mod.f90:858-861 -- every CG iteration)
             import torch
-            oki = torch.as_tensor(np.nonzero(ok)[0], device=other.alm.device)
-            ji = torch.as_tensor(j[ok], device=self.alm.device)
-            other.alm[:q, oki] = self.alm[:q, ji]
+            key = (id(self.info), id(other.info), str(other.alm.device))
+            hit = _repack_cache.get(key)
+            if hit is None:
+                j = self.info.lm2i_vec(other.info.lm[0], other.info.lm[1])
+                ok = j >= 0
+                hit = (torch.as_tensor(np.nonzero(ok)[0], device=other.alm.device),
+                       torch.as_tensor(j[ok], device=self.alm.device), self.info, other.info)
+                _repack_cache[key] = hit
+            other.alm[:q, hit[0]] = self.alm[:q, hit[1]]
 
     def add_alm(self, alm, info: comm_mapinfo):
         j = self.info.lm2i_vec(info.lm[0], info.lm[1])
