@@ -481,3 +481,64 @@ def test_arbitrary_spin_vs_oracle(shtlib, cpu_oracle, nside, lmax, spin):
         assert rel(out, ref) <= TOL, (name, rel(out, ref))
     sharp.sharp_destroy_alm_info(ai)
     sharp.sharp_destroy_geom_info(gi)
+
+
+@pytest.mark.parametrize("nside,lmax", [(256, 300), (512, 200), (3, 8), (12, 30), (48, 100)])
+@pytest.mark.parametrize("spin", [0, 2])
+def test_midsize_and_odd_nside_vs_oracle(shtlib, cpu_oracle, nside, lmax, spin):
+    """Sizes whose polar caps use the longer chirp-z classes (work lengths 2048 and 4096 of the fused ring kernel), and
+    values of nside that are not powers of two (the ring scheme allows any nside): Y and YtW against the oracle."""
+    sharp, S = shtlib, cpu_oracle
+    rng = np.random.default_rng(17 * nside + lmax + spin)
+    nc = 1 if spin == 0 else 2
+    w = rng.uniform(0.9, 1.1, 2 * nside)
+    ai, gi = _handles(sharp, nside, lmax, weight=w)
+    alm = rng.standard_normal((nc, ai.n_local))
+    if spin == 2:
+        _zero_low_l(alm, lmax, None)
+    out = np.full((nc, gi.n_local), np.nan)
+    sharp.sharp_execute(sharp.SHARP_Y, spin, nc, alm.copy(), ai, out, gi)
+    ref = S.execute(S.Y, spin, nside, lmax, alm=alm, weight=w)
+    assert rel(out, ref) <= TOL, rel(out, ref)
+    mp = rng.standard_normal((nc, gi.n_local))
+    outa = np.full((nc, ai.n_local), np.nan)
+    sharp.sharp_execute(sharp.SHARP_YtW, spin, nc, outa, ai, mp.copy(), gi)
+    refa = S.execute(S.YtW, spin, nside, lmax, map=mp, weight=w)
+    assert rel(outa, refa) <= TOL, rel(outa, refa)
+    sharp.sharp_destroy_alm_info(ai)
+    sharp.sharp_destroy_geom_info(gi)
+
+
+def test_fused_and_cufft_ring_paths_agree(shtlib):
+    """The polar-cap classes go through the fused chirp-z kernel by default and through cuFFT with
+    CMDR_SHT_FUSED_BLUE=0 (read once per process, hence the subprocess): same maps and a_lm to rounding."""
+    import os
+    import subprocess
+    import sys
+    import tempfile
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = r"""
+import sys, numpy as np
+sys.path.insert(0, %r)
+from commander_b200 import comm_map, comm_mapinfo
+info = comm_mapinfo(None, 512, 700, 3, True)
+m = comm_map(info)
+rng = np.random.default_rng(8)
+m.alm[:] = rng.standard_normal(m.alm.shape)
+m.alm[1:3, info.lm[0] < 2] = 0
+m.Y(); mp = m.map.copy()
+m.map[:] = rng.standard_normal(m.map.shape)
+m.Yt()
+np.savez(sys.argv[1], map=mp, alm=m.alm)
+""" % root
+    res = {}
+    with tempfile.TemporaryDirectory() as td:
+        for flag in ("1", "0"):
+            out = os.path.join(td, f"r{flag}.npz")
+            env = dict(os.environ, CMDR_SHT_FUSED_BLUE=flag)
+            r = subprocess.run([sys.executable, "-c", code, out], env=env, capture_output=True, text=True, timeout=300)
+            assert r.returncode == 0, r.stderr[-2000:]
+            res[flag] = dict(np.load(out))
+    assert rel(res["1"]["map"], res["0"]["map"]) <= 1e-13
+    assert rel(res["1"]["alm"], res["0"]["alm"]) <= 1e-13
+    assert not np.array_equal(res["1"]["map"], res["0"]["map"])      # two different code paths did run

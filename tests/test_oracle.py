@@ -27,7 +27,7 @@ def _grid(nside):
 
 
 def test_ring_offsets_tile_the_sphere():
-    for nside in (1, 2, 4, 8, 16):
+    for nside in (1, 2, 3, 4, 6, 8, 12, 16):
         pos = 0
         for o, n in sorted((D.healpix_ring(nside, r)[4], D.healpix_ring(nside, r)[2]) for r in range(1, 4 * nside)):
             assert o == pos
@@ -111,7 +111,7 @@ def test_cpu_restatement_vs_golden(cpu_oracle, path):
         assert rel(S.execute(S.YtW, spin, nside, lmax, map=mp, **kw), g[f"s{spin}_YtW"]) < 1e-13
 
 
-@pytest.mark.parametrize("nside,lmax", [(1, 3), (2, 5), (4, 11), (4, 14), (8, 10)])
+@pytest.mark.parametrize("nside,lmax", [(1, 3), (2, 5), (4, 11), (4, 14), (8, 10), (3, 8), (6, 13)])
 def test_cpu_restatement_vs_dense(cpu_oracle, nside, lmax):
     S = cpu_oracle
     rng = np.random.default_rng(nside * 100 + lmax)
