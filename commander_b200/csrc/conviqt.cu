@@ -13,8 +13,8 @@
 //
 // The psi transform is a direct real DFT per pixel (2*bmax <= 64 points): each thread owns one pixel,
 // parks its 2*bmax+1 inputs in a private shared-memory column (coalesced loads, no barrier) and
-// writes 2*bmax coalesced outputs.  Algorithmic bytes per pixel: 8 (2 bmax + 1) read + 4 * 2 bmax
-// written (HBM bound for bmax <~ 16, FP64 bound above: 4 bmax (bmax-1) DFMA per pixel).
+// writes 2*bmax coalesced outputs, four planes per inner loop (the planes k, n-k, k+bmax, bmax-k share their
+// products).  Algorithmic bytes per pixel: 8 (2 bmax + 1) read + 4 * 2 bmax written.
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -91,17 +91,29 @@ __global__ void conviqt_psi_kernel(int bmax, long long np, const double *__restr
     if (p >= np) continue;
     for (int r = 0; r <= n; ++r) col[r * PSI_BLOCK] = marr[(long long)r * np + p];
     const double m0 = col[0], mb = col[(n - 1) * PSI_BLOCK];
-    for (int k = 0; k < n; ++k) {
-      double acc = 0.0;
+    // Planes k, n-k, k+bmax and bmax-k share their products: cos(2 pi j (n-k)/n) = cos(2 pi j k/n), the sine flips
+    // sign, and a shift by bmax multiplies both by (-1)^j.  Four partial sums (even / odd j, cosine / sine part)
+    // per k in [0, bmax/2] give all four planes: a quarter of the shared-memory loads of the plain double loop.
+    for (int k = 0; k <= bmax / 2; ++k) {
+      double ce = 0.0, co = 0.0, se = 0.0, so = 0.0;
       int t = 0;
-      for (int j = 1; j < bmax; ++j) {
-        t += k;
-        if (t >= n) t -= n;
-        acc = fma(col[(2 * j - 1) * PSI_BLOCK], twc[t], acc);
-        acc = fma(-col[(2 * j) * PSI_BLOCK], tws[t], acc);
+      for (int j = 1; j < bmax; j += 2) {
+        t += k; if (t >= n) t -= n;                          // t = j k mod n, j odd
+        co = fma(col[(2 * j - 1) * PSI_BLOCK], twc[t], co);
+        so = fma(col[(2 * j) * PSI_BLOCK], tws[t], so);
+        if (j + 1 < bmax) {
+          t += k; if (t >= n) t -= n;                        // j + 1, even
+          ce = fma(col[(2 * j + 1) * PSI_BLOCK], twc[t], ce);
+          se = fma(col[(2 * j + 2) * PSI_BLOCK], tws[t], se);
+        }
       }
-      const double v = m0 + ((k & 1) ? -mb : mb) + 2.0 * acc;
-      cube[(long long)k * np + p] = (OUT)v;
+      const double nyq0 = (k & 1) ? -mb : mb, nyq1 = ((k + bmax) & 1) ? -mb : mb;
+      const double c0 = ce + co, s0 = se + so, c1 = ce - co, s1 = se - so;
+      const int k1 = k + bmax, k2 = (n - k) % n, k3 = bmax - k;
+      cube[(long long)k * np + p] = (OUT)(m0 + nyq0 + 2.0 * (c0 - s0));
+      cube[(long long)k2 * np + p] = (OUT)(m0 + nyq0 + 2.0 * (c0 + s0));
+      cube[(long long)k1 * np + p] = (OUT)(m0 + nyq1 + 2.0 * (c1 - s1));
+      cube[(long long)k3 * np + p] = (OUT)(m0 + nyq1 + 2.0 * (c1 + s1));
     }
   }
 }
