@@ -89,6 +89,7 @@ class cr_cmb_system:
             sS[j, l < 2] = 0.0
         self.bl = torch.as_tensor(bl, device=dev)
         self.sqrtS = torch.as_tensor(sS, device=dev)
+        self.sSbl = self.sqrtS * self.bl      # sqrt(S) and the beam act on the same slots: one pass instead of two
         self.buf = comm_map(info, device=dev)
         # diagonal preconditioner: 1 + C_l b_l^2 N^-1_{lm,lm}, monopole term of compute_invN_lm
         mean_invN = self.invN.sum(dim=1)
@@ -129,7 +130,7 @@ class cr_cmb_system:
 
     def mpi_dot_product(self, a, b):
         """commander3/src/comm_utils.f90:599-614"""
-        s = (a * b).sum().reshape(1)
+        s = self.torch.dot(a.reshape(-1), b.reshape(-1)).reshape(1)
         self._allreduce(s)
         return float(s.item())
 
@@ -137,16 +138,12 @@ class cr_cmb_system:
     def matmulA(self, x):
         """cr_matmulA, commander3/src/comm_cr_mod.f90:771-1024 for one band / one diffuse component."""
         m = self.buf
-        m.alm.copy_(x)
-        m.alm.mul_(self.sqrtS)        # sqrtS_x, :797-836
-        m.alm.mul_(self.bl)           # evalDiffuseBand: F_mean = 1, beam :2089
+        self.torch.mul(x, self.sSbl, out=m.alm)   # sqrtS_x :797-836, then evalDiffuseBand: F_mean = 1, beam :2089
         m.Y()                         # :888-892
         m.map.mul_(self.invN)         # N%invN, :905
         m.Yt()                        # :913-918
-        m.alm.mul_(self.bl)           # projectDiffuseBand (B^T)
-        m.alm.mul_(self.sqrtS)        # :957-1008
         self.n_matmul += 1
-        return x + m.alm
+        return self.torch.addcmul(x, m.alm, self.sSbl)   # projectDiffuseBand (B^T), sqrtS :957-1008, + x
 
     def invM(self, r):
         """cr_invM, :1026-1077: 'diagonal' (default) or 'pseudoinv' preconditioner."""
@@ -198,6 +195,8 @@ def solve_cr_eqn_by_CG(sys: cr_cmb_system, b, maxiter=300, cg_tol=1e-8, cg_conv_
     x = torch.zeros_like(b) if x0 is None else x0.clone()
     r = b - sys.matmulA(x)
     d = sys.invM(r)
+    if d.data_ptr() == r.data_ptr():
+        d = d.clone()                             # an identity preconditioner may hand r back; d is updated in place
     delta_new = sys.mpi_dot_product(r, d)
     delta0 = sys.mpi_dot_product(b, sys.invM(b))
     if cg_conv_crit not in ("residual", "fixed_iter"):
@@ -214,13 +213,13 @@ def solve_cr_eqn_by_CG(sys: cr_cmb_system, b, maxiter=300, cg_tol=1e-8, cg_conv_
                 break
         q = sys.matmulA(d)
         alpha = delta_new / sys.mpi_dot_product(d, q)
-        x = x + alpha * d
-        r = r - alpha * q
+        x.add_(d, alpha=alpha)                    # x = x + alpha d   (in place: x, r, d are this routine's own)
+        r.add_(q, alpha=-alpha)                   # r = r - alpha q
         s = sys.invM(r)
         delta_old = delta_new
         delta_new = sys.mpi_dot_product(r, s)
         beta = delta_new / delta_old
-        d = s + beta * d
+        d.mul_(beta).add_(s)                      # d = s + beta d
         hist.append(delta_new)
         it = i
         if verbose:
