@@ -319,6 +319,31 @@ class comm_map:
                 _repack_cache[key] = hit
             other.alm[:q, hit[0]] = self.alm[:q, hit[1]]
 
+    # ---- the chain-file order of a_lm: global index l^2 + l + m, all (l, m) of the sphere, single precision on disk
+    def alm_to_chain_order(self, dtype=np.float32):
+        """This rank's contribution to the `alm` dataset writeFITS puts into the chain file
+        (commander3/src/comm_map_mod.f90:712-739): array ((lmax+1)^2, nmaps) with alm(l^2+l+m, :) = self%alm(j, :),
+        zero for the (l, m) other ranks own (the reference gathers them on the root with mpi_recv; summing the
+        ranks' arrays is the same thing), cast to real(sp) as `real(alm, sp)` does."""
+        info = self.info
+        l, m = info.lm[0].astype(np.int64), info.lm[1].astype(np.int64)
+        out = np.zeros(((info.lmax + 1) ** 2, info.nmaps))
+        a = self.alm if isinstance(self.alm, np.ndarray) else self.alm.cpu().numpy()
+        out[l * l + l + m, :] = a.T
+        return out.astype(dtype)
+
+    def alm_from_chain_order(self, alms):
+        """readHDF, commander3/src/comm_map_mod.f90:860-889: self%alm(i, :) = alms(l^2 + l + m, :) for the local (l, m);
+        `alms` is the full ((lmax+1)^2, nmaps) dataset every rank receives by mpi_bcast."""
+        info = self.info
+        l, m = info.lm[0].astype(np.int64), info.lm[1].astype(np.int64)
+        loc = np.ascontiguousarray(np.asarray(alms, dtype=np.float64)[l * l + l + m, :].T)
+        if isinstance(self.alm, np.ndarray):
+            self.alm[...] = loc
+        else:
+            import torch
+            self.alm.copy_(torch.as_tensor(loc))
+
     def add_alm(self, alm, info: comm_mapinfo):
         j = self.info.lm2i_vec(info.lm[0], info.lm[1])
         q = min(self.info.nmaps, info.nmaps)

@@ -193,3 +193,34 @@ def test_blue_fft_pair_on_host(emul_fft, M):
     emul_fft.emul_fft(u.ctypes.data, M, 1, 64)
     conv = np.fft.ifft(np.fft.fft(x) * V) * M
     assert np.abs(u - conv).max() <= 1e-11 * np.abs(conv).max()
+
+
+def test_chain_order_round_trip(shtlib):
+    """alm <-> chain-file order l^2+l+m (commander3/src/comm_map_mod.f90:712-739, 860-889), one rank and the two ranks of a
+    round-robin split: the ranks' arrays add up to the single-rank one."""
+    from commander_b200.comm_map import comm_map, comm_mapinfo
+    from commander_b200.dist import Comm
+    lmax, nside = 11, 4
+    rng = np.random.default_rng(0)
+    info = comm_mapinfo(None, nside, lmax, 3, True)
+    m = comm_map(info)
+    m.alm[...] = rng.standard_normal(m.alm.shape)
+    full = m.alm_to_chain_order(dtype=np.float64)
+    assert full.shape == ((lmax + 1) ** 2, 3)
+    for i in range(info.nalm):
+        l, mm = info.i2lm(i)
+        assert np.array_equal(full[l * l + l + mm], m.alm[:, i])
+    assert m.alm_to_chain_order().dtype == np.float32
+    parts = []
+    for r in range(2):
+        ir = comm_mapinfo(Comm(r, 2, 9), nside, lmax, 3, True)
+        mr = comm_map(ir)
+        mr.alm_from_chain_order(full)
+        for i in range(ir.nalm):
+            l, mm = ir.i2lm(i)
+            assert np.array_equal(mr.alm[:, i], full[l * l + l + mm])
+        parts.append(mr.alm_to_chain_order(dtype=np.float64))
+    assert np.array_equal(parts[0] + parts[1], full)
+    back = comm_map(info)
+    back.alm_from_chain_order(full)
+    assert np.array_equal(back.alm, m.alm)
