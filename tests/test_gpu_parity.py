@@ -542,3 +542,50 @@ np.savez(sys.argv[1], map=mp, alm=m.alm)
     assert rel(res["1"]["map"], res["0"]["map"]) <= 1e-13
     assert rel(res["1"]["alm"], res["0"]["alm"]) <= 1e-13
     assert not np.array_equal(res["1"]["map"], res["0"]["map"])      # two different code paths did run
+
+
+@pytest.mark.parametrize("spin", [0, 2])
+def test_empty_and_ragged_inputs(shtlib, cpu_oracle, spin):
+    """What a rank with nothing to do passes (commander3/src/sharp.f90:219-224: null pointers when n_local == 0): no m's ->
+    synthesis writes a zero map and analysis returns; no rings -> analysis writes zero a_lm and synthesis returns.  Plus
+    ragged geometries against the oracle: the equator alone (an unpaired ring), the two polar rings, a single m."""
+    sharp, S = shtlib, cpu_oracle
+    nside, lmax = 8, 20
+    nc = 1 if spin == 0 else 2
+    rng = np.random.default_rng(spin)
+    full_a = sharp.sharp_make_mmajor_real_packed_alm_info(lmax)
+    full_g = sharp.sharp_make_healpix_geom_info(nside)
+    no_a = sharp.sharp_make_mmajor_real_packed_alm_info(lmax, ms=np.zeros(0, dtype=np.int32))
+    no_g = sharp.sharp_make_healpix_geom_info(nside, rings=np.zeros(0, dtype=np.int32))
+    empty = np.zeros((nc, 0))
+    mp = np.full((nc, full_g.n_local), np.nan)
+    sharp.sharp_execute(sharp.SHARP_Y, spin, nc, empty, no_a, mp, full_g)
+    assert np.array_equal(mp, np.zeros_like(mp))
+    sharp.sharp_execute(sharp.SHARP_YtW, spin, nc, empty, no_a, rng.standard_normal(mp.shape), full_g)
+    alm = np.full((nc, full_a.n_local), np.nan)
+    sharp.sharp_execute(sharp.SHARP_Yt, spin, nc, alm, full_a, empty, no_g)
+    assert np.array_equal(alm, np.zeros_like(alm))
+    sharp.sharp_execute(sharp.SHARP_Y, spin, nc, rng.standard_normal(alm.shape), full_a, empty, no_g)
+    a_in = rng.standard_normal((nc, full_a.n_local))
+    if spin == 2:
+        _zero_low_l(a_in, lmax, None)
+    for rings in ([2 * nside], [1, 4 * nside - 1], [3, nside, 2 * nside, 3 * nside + 1]):
+        g = sharp.sharp_make_healpix_geom_info(nside, rings=np.array(rings, dtype=np.int32))
+        out = np.full((nc, g.n_local), np.nan)
+        sharp.sharp_execute(sharp.SHARP_Y, spin, nc, a_in.copy(), full_a, out, g)
+        ref = S.execute(S.Y, spin, nside, lmax, alm=a_in, rings=rings)
+        assert rel(out, ref) <= TOL, (rings, rel(out, ref))
+        back = np.full((nc, full_a.n_local), np.nan)
+        sharp.sharp_execute(sharp.SHARP_Yt, spin, nc, back, full_a, out.copy(), g)
+        refb = S.execute(S.Yt, spin, nside, lmax, map=ref, rings=rings)
+        assert rel(back, refb) <= TOL, (rings, rel(back, refb))
+        sharp.sharp_destroy_geom_info(g)
+    one = sharp.sharp_make_mmajor_real_packed_alm_info(lmax, ms=np.array([lmax], dtype=np.int32))
+    a1 = rng.standard_normal((nc, one.n_local))
+    out = np.full((nc, full_g.n_local), np.nan)
+    sharp.sharp_execute(sharp.SHARP_Y, spin, nc, a1.copy(), one, out, full_g)
+    assert rel(out, S.execute(S.Y, spin, nside, lmax, alm=a1, ms=[lmax])) <= TOL
+    for h in (full_a, no_a, one):
+        sharp.sharp_destroy_alm_info(h)
+    for h in (full_g, no_g):
+        sharp.sharp_destroy_geom_info(h)

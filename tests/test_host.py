@@ -224,3 +224,21 @@ def test_chain_order_round_trip(shtlib):
     back = comm_map(info)
     back.alm_from_chain_order(full)
     assert np.array_equal(back.alm, m.alm)
+
+
+def test_empty_and_single_ring_handles(shtlib):
+    """A rank may own no m or no ring at all (sharp_execute is then called with null pointers); handles for
+    empty lists and for a single unpaired ring are valid and report their sizes.  Host only: no compute call."""
+    sharp = shtlib
+    ai = sharp.sharp_make_mmajor_real_packed_alm_info(10, ms=np.zeros(0, dtype=np.int32))
+    gi = sharp.sharp_make_healpix_geom_info(4, rings=np.zeros(0, dtype=np.int32))
+    assert ai.n_local == 0 and gi.n_local == 0
+    eq = sharp.sharp_make_healpix_geom_info(4, rings=np.array([8], dtype=np.int32))      # the equator alone
+    cap = sharp.sharp_make_healpix_geom_info(4, rings=np.array([1, 15], dtype=np.int32))  # the two polar rings
+    assert eq.n_local == 16 and cap.n_local == 8
+    one_m = sharp.sharp_make_mmajor_real_packed_alm_info(10, ms=np.array([10], dtype=np.int32))
+    assert one_m.n_local == 2
+    for h in (ai, one_m):
+        sharp.sharp_destroy_alm_info(h)
+    for h in (gi, eq, cap):
+        sharp.sharp_destroy_geom_info(h)
