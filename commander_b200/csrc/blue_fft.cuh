@@ -95,6 +95,158 @@ BF_HD int bf_tw_offset(int M, int k) {
 }
 BF_HD int bf_tw_total(int M) { return bf_tw_offset(M, bf_num_passes(M)); }
 
+// ---------------------------------------------------------------------------------------------------------
+// Register-blocked variant: S radix-2 stages per pass on 2^S elements held in registers (the same butterfly
+// network, so the same bit-reversed spectrum order), with the array padded by one slot per 16 elements.
+//
+// Pass with leading half-size h: work item q in [0, M / 2^S) owns the elements i + r st, r < 2^S, st = h / 2^(S-1),
+// i = (q / st) 2h + (q mod st).  Stage s (half-size h / 2^s, register distance d = 2^(S-1-s)) multiplies the lower
+// output of the pair (r, r + d) by  W_{2h}^{j 2^s} * exp(-i pi (r mod d) / d):  a per-item factor obtained by
+// repeated squaring of T[j] = W_{2h}^j (one table load per item) times a compile-time root of unity.
+// Schedule (bf2_*): passes of 3 or 4 stages with st >= 16 down to half-size 16, then ONE pass of 4 stages on 16
+// consecutive elements per item (st = 1).  With the padding a thread's 16 consecutive elements are 17 slots from its
+// neighbour's, and every strided pass reads 8 consecutive slots per quarter warp: no bank conflicts in any pass.
+template <bool PAD>
+BF_HD int bf_pidx(int i) { return PAD ? i + (i >> 4) : i; }
+
+BF_HD double2 bf_root(int k, int d) {          // exp(-i pi k / d), d in {1, 2, 4, 8}, 0 <= k < d (constants after unrolling)
+  const double c8[8] = {1.0, 0.92387953251128675613, 0.70710678118654752440, 0.38268343236508977173,
+                        0.0, -0.38268343236508977173, -0.70710678118654752440, -0.92387953251128675613};
+  const double s8[8] = {0.0, 0.38268343236508977173, 0.70710678118654752440, 0.92387953251128675613,
+                        1.0, 0.92387953251128675613, 0.70710678118654752440, 0.38268343236508977173};
+  const int t = k * (8 / d);                   // exp(-i pi t / 8)
+  double2 r; r.x = c8[t]; r.y = -s8[t];
+  return r;
+}
+
+template <int S, bool PAD>
+BF_HD void dif_itemS(double2 *x, int h, const double2 *T, int q) {
+  constexpr int R = 1 << S;
+  const int st = h >> (S - 1);
+  const int j = q & (st - 1);
+  const int i = (q - j) * R + j;
+  double2 v[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) v[r] = x[bf_pidx<PAD>(i + r * st)];
+  double2 w = T[j];
+#pragma unroll
+  for (int s = 0; s < S; ++s) {
+    const int d = R >> (s + 1);
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      if (r & d) continue;
+      const int k = r & (d - 1);
+      const double2 a = v[r], b = v[r + d];
+      v[r] = bf_add(a, b);
+      double2 t = bf_mul(bf_sub(a, b), w);
+      if (k != 0) t = (2 * k == d) ? bf_mul_mi(t) : bf_mul(t, bf_root(k, d));
+      v[r + d] = t;
+    }
+    w = bf_mul(w, w);
+  }
+#pragma unroll
+  for (int r = 0; r < R; ++r) x[bf_pidx<PAD>(i + r * st)] = v[r];
+}
+
+template <int S, bool PAD>
+BF_HD void dit_itemS(double2 *x, int h, const double2 *T, int q) {
+  constexpr int R = 1 << S;
+  const int st = h >> (S - 1);
+  const int j = q & (st - 1);
+  const int i = (q - j) * R + j;
+  double2 v[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) v[r] = x[bf_pidx<PAD>(i + r * st)];
+  double2 wp[S];                                // T[j]^(2^s)
+  wp[0] = T[j];
+#pragma unroll
+  for (int s = 1; s < S; ++s) wp[s] = bf_mul(wp[s - 1], wp[s - 1]);
+#pragma unroll
+  for (int s = S - 1; s >= 0; --s) {
+    const int d = R >> (s + 1);
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      if (r & d) continue;
+      const int k = r & (d - 1);
+      double2 t = bf_mulc(v[r + d], wp[s]);
+      if (k != 0) t = (2 * k == d) ? bf_mul_pi(t) : bf_mulc(t, bf_root(k, d));
+      const double2 a = v[r];
+      v[r] = bf_add(a, t);
+      v[r + d] = bf_sub(a, t);
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < R; ++r) x[bf_pidx<PAD>(i + r * st)] = v[r];
+}
+
+// The middle of the convolution for the register-blocked variant: the last DIF pass (half-sizes 8, 4, 2, 1), the
+// multiplication by the bit-reversed filter spectrum and the first DIT pass all act on the 16 consecutive elements
+// [16 q, 16 q + 16) of one work item, so they are done in registers in one go: one shared-memory round trip and no
+// barrier instead of three passes.  No per-item twiddle (st = 1: T[j] = 1).
+template <bool PAD>
+BF_HD void conv_mid16(double2 *x, const double2 *v, int q) {
+  constexpr int R = 16;
+  const int i = q * R;
+  double2 u[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) u[r] = x[bf_pidx<PAD>(i + r)];
+#pragma unroll
+  for (int s = 0; s < 4; ++s) {
+    const int d = R >> (s + 1);
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      if (r & d) continue;
+      const int k = r & (d - 1);
+      const double2 a = u[r], b = u[r + d];
+      u[r] = bf_add(a, b);
+      double2 t = bf_sub(a, b);
+      if (k != 0) t = (2 * k == d) ? bf_mul_mi(t) : bf_mul(t, bf_root(k, d));
+      u[r + d] = t;
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < R; ++r) u[r] = bf_mul(u[r], v[i + r]);
+#pragma unroll
+  for (int s = 3; s >= 0; --s) {
+    const int d = R >> (s + 1);
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      if (r & d) continue;
+      const int k = r & (d - 1);
+      double2 t = u[r + d];
+      if (k != 0) t = (2 * k == d) ? bf_mul_pi(t) : bf_mulc(t, bf_root(k, d));
+      const double2 a = u[r];
+      u[r] = bf_add(a, t);
+      u[r + d] = bf_sub(a, t);
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < R; ++r) x[bf_pidx<PAD>(i + r)] = u[r];
+}
+
+// schedule of the register-blocked variant for M in {1024, 2048, 4096, 8192}: stage counts of the strided passes
+// (leading half-size M/2 downwards, ending at half-size 16); the final pass has 4 stages from half-size 8.
+BF_HD int bf2_num_strided(int M) { return M >= 8192 ? 3 : 2; }
+BF_HD int bf2_stages(int M, int k) {             // stages of strided pass k
+  if (M >= 8192) return 3;                       // 13 = 3 + 3 + 3 + 4
+  if (M >= 4096) return 4;                       // 12 = 4 + 4 + 4
+  if (M >= 2048) return k == 0 ? 4 : 3;          // 11 = 4 + 3 + 4
+  return 3;                                      // 10 = 3 + 3 + 4
+}
+BF_HD int bf2_half(int M, int k) {               // leading half-size of strided pass k
+  int h = M >> 1;
+  for (int i = 0; i < k; ++i) h >>= bf2_stages(M, i);
+  return h;
+}
+// twiddle table of the variant: pass k owns st_k = h_k / 2^(S_k - 1) entries T[j] = exp(-i pi j / h_k); the final
+// pass has st = 1 and T = {1}
+BF_HD int bf2_tw_offset(int M, int k) {
+  int o = 0;
+  for (int i = 0; i < k; ++i) o += bf2_half(M, i) >> (bf2_stages(M, i) - 1);
+  return o;
+}
+BF_HD int bf2_tw_total(int M) { return bf2_tw_offset(M, bf2_num_strided(M)) + 1; }
+
 BF_HD unsigned bf_bitrev(unsigned v, int bits) {
   unsigned r = 0;
   for (int b = 0; b < bits; ++b) { r = (r << 1) | (v & 1u); v >>= 1; }

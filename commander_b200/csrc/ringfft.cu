@@ -76,7 +76,7 @@ __device__ __forceinline__ double2 fold_one(const FParams &p, const PhaseLayout 
   return make_double2(pn.x - ps.y, pn.y + ps.x);
 }
 
-template <int NT>
+template <int NT, bool PAD = false>
 __device__ __forceinline__ void fold_into(const FParams &p, int pair, int c, double2 *out, int len, double2 *part_sum) {
   const int n = p.nph[pair];
   const bool blue = p.zblue[pair], shifted = p.shifted[pair];
@@ -106,7 +106,7 @@ __device__ __forceinline__ void fold_into(const FParams &p, int pair, int c, dou
         for (int q = 0; q < parts; ++q) { tot.x += part_sum[kk + q * n].x; tot.y += part_sum[kk + q * n].y; }
         if (blue) tot = cmul(tot, expipi((long long)kk * kk, n));
       }
-      out[kk] = tot;
+      out[bf_pidx<PAD>(kk)] = tot;
     }
     return;
   }
@@ -125,7 +125,7 @@ __device__ __forceinline__ void fold_into(const FParams &p, int pair, int c, dou
       }
       if (blue) acc = cmul(acc, expipi((long long)k * k, n));
     }
-    out[k] = acc;
+    out[bf_pidx<PAD>(k)] = acc;
   }
 }
 
@@ -192,6 +192,7 @@ __global__ void __launch_bounds__(256) blue_filter_kernel(FParams p, int first_p
 }
 
 // ---- synthesis, after the FFT: write north = Re z, south = Im z into the map
+template <bool PAD = false>
 __device__ __forceinline__ void scatter_from(const FParams &p, int pair, int c, const double2 *in) {
   const int n = p.nph[pair], len = p.zlen[pair];
   const bool blue = p.zblue[pair];
@@ -200,7 +201,7 @@ __device__ __forceinline__ void scatter_from(const FParams &p, int pair, int c, 
   double w = p.weighted ? p.wgt[pair] : 1.0;
   if (blue) w /= (double)len;
   for (int j = threadIdx.x; j < n; j += blockDim.x) {
-    double2 z = in[j];
+    double2 z = in[bf_pidx<PAD>(j)];
     if (blue) z = cmul(z, expipi((long long)j * j, n));
     if (oN >= 0) { if (p.add) mp[oN + j] += w * z.x; else mp[oN + j] = w * z.x; }
     if (oS >= 0) { if (p.add) mp[oS + j] += w * z.y; else mp[oS + j] = w * z.y; }
@@ -212,6 +213,7 @@ __global__ void __launch_bounds__(256) scatter_kernel(FParams p, int first_pair)
 }
 
 // ---- analysis, before the FFT: z = w (x_north + i x_south)
+template <bool PAD = false>
 __device__ __forceinline__ void gather_into(const FParams &p, int pair, int c, double2 *out) {
   const int n = p.nph[pair], len = p.zlen[pair];
   const bool blue = p.zblue[pair];
@@ -226,7 +228,7 @@ __device__ __forceinline__ void gather_into(const FParams &p, int pair, int c, d
       // Bluestein computes DFT+ ; DFT-(z) = conj(DFT+(conj z))
       if (blue) z = cmul(make_double2(z.x, -z.y), expipi((long long)j * j, n));
     }
-    out[j] = z;
+    out[bf_pidx<PAD>(j)] = z;
   }
 }
 __global__ void __launch_bounds__(256) gather_kernel(FParams p, int first_pair) {
@@ -235,6 +237,7 @@ __global__ void __launch_bounds__(256) gather_kernel(FParams p, int first_pair) 
 }
 
 // ---- analysis, after the FFT: phases ph_m = c_m e^{-i m phi0} X_{m mod n}
+template <bool PAD = false>
 __device__ __forceinline__ void unfold_from(const FParams &p, int pair, int c, const double2 *in) {
   const int n = p.nph[pair], len = p.zlen[pair];
   const bool blue = p.zblue[pair], shifted = p.shifted[pair];
@@ -243,7 +246,7 @@ __device__ __forceinline__ void unfold_from(const FParams &p, int pair, int c, c
   for (int e = threadIdx.x; e < L.nm_total; e += blockDim.x) {
     const int m = L.mlist[e];
     const int k = m % n, k2 = (n - k) % n;
-    double2 a = in[k], b = in[k2];
+    double2 a = in[bf_pidx<PAD>(k)], b = in[bf_pidx<PAD>(k2)];
     if (blue) {
       a = cmul(a, expipi((long long)k * k, n));   a = make_double2(a.x * inv, -a.y * inv);
       b = cmul(b, expipi((long long)k2 * k2, n)); b = make_double2(b.x * inv, -b.y * inv);
@@ -303,10 +306,47 @@ __global__ void __launch_bounds__(NT) blue_fused_kernel(FParams p, int first_pai
   if (DIR == 0) scatter_from(p, pair, c, u_sm); else unfold_from(p, pair, c, u_sm);
 }
 
+// Register-blocked variant of the fused kernel (blue_fft.cuh, bf2_* schedule): 3-4 stages per pass on 8 or 16 elements
+// held in registers, the array padded by one slot per 16 elements so that no pass has shared-memory bank conflicts, and
+// the last DIF pass, the filter multiplication and the first DIT pass done in registers in one go.  An 8192-point
+// convolution makes 6 shared-memory round trips and 7 barriers instead of 15 and 16.  EXPERIMENTAL: selected with
+// CMDR_SHT_FFT_BLOCKED=1; verified on the host (tests/host_emul) and against the cuFFT path, not yet the default.
+template <int DIR, int NT>
+__global__ void __launch_bounds__(NT) blue_fused2_kernel(FParams p, int first_pair, int M, const double2 *__restrict__ tw,
+                                                         const double2 *__restrict__ vbr) {
+  extern __shared__ double2 u_sm[];                 // M + M/16 work slots, then the twiddle table
+  __shared__ double2 part_sum[DIR == 0 ? NT : 1];
+  const int pair = first_pair + blockIdx.x, c = blockIdx.y;
+  double2 *T = u_sm + M + (M >> 4);
+  const int ntw = bf2_tw_total(M);
+  for (int k = threadIdx.x; k < ntw; k += NT) T[k] = tw[k];
+  if (DIR == 0) fold_into<NT, true>(p, pair, c, u_sm, M, part_sum); else gather_into<true>(p, pair, c, u_sm);
+  __syncthreads();
+  const int ns = bf2_num_strided(M);
+  for (int k = 0; k < ns; ++k) {
+    const int S = bf2_stages(M, k), h = bf2_half(M, k);
+    const double2 *Tk = T + bf2_tw_offset(M, k);
+    if (S == 3) { for (int q = threadIdx.x; q < (M >> 3); q += NT) dif_itemS<3, true>(u_sm, h, Tk, q); }
+    else { for (int q = threadIdx.x; q < (M >> 4); q += NT) dif_itemS<4, true>(u_sm, h, Tk, q); }
+    __syncthreads();
+  }
+  const double2 *v = vbr + p.zbase[pair] + (size_t)p.zidx[pair] * M;
+  for (int q = threadIdx.x; q < (M >> 4); q += NT) conv_mid16<true>(u_sm, v, q);
+  __syncthreads();
+  for (int k = ns - 1; k >= 0; --k) {
+    const int S = bf2_stages(M, k), h = bf2_half(M, k);
+    const double2 *Tk = T + bf2_tw_offset(M, k);
+    if (S == 3) { for (int q = threadIdx.x; q < (M >> 3); q += NT) dit_itemS<3, true>(u_sm, h, Tk, q); }
+    else { for (int q = threadIdx.x; q < (M >> 4); q += NT) dit_itemS<4, true>(u_sm, h, Tk, q); }
+    __syncthreads();
+  }
+  if (DIR == 0) scatter_from<true>(p, pair, c, u_sm); else unfold_from<true>(p, pair, c, u_sm);
+}
+
 // twiddles of one fused pass with leading half-size h: T[j] = exp(-i pi j / h), j < h/2 (blue_fft.cuh)
-__global__ void twiddle_kernel(double2 *T, int h) {
+__global__ void twiddle_kernel(double2 *T, int h, int count) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j < h / 2) { double2 e = expipi(j, h); T[j] = make_double2(e.x, -e.y); }
+  if (j < count) { double2 e = expipi(j, h); T[j] = make_double2(e.x, -e.y); }
 }
 
 // filter spectra of the fused classes in bit-reversed order
@@ -369,9 +409,32 @@ static const double2 *twiddle_table(int M, cudaStream_t st) {
     int h, fused;
     bf_pass(M, k, &h, &fused);
     if (!fused) continue;
-    twiddle_kernel<<<(h / 2 + 255) / 256, 256, 0, st>>>(t + bf_tw_offset(M, k), h);
+    twiddle_kernel<<<(h / 2 + 255) / 256, 256, 0, st>>>(t + bf_tw_offset(M, k), h, h / 2);
     count_launch();
   }
+  CMDR_CUDA_CHECK(cudaGetLastError());
+  tabs[key] = t;
+  return t;
+}
+
+// twiddles of the register-blocked variant (bf2_* schedule): per strided pass st entries exp(-i pi j / h), then {1}
+static const double2 *twiddle_table2(int M, cudaStream_t st) {
+  static std::map<long long, double2 *> tabs;       // (device, M)
+  int dev = 0;
+  CMDR_CUDA_CHECK(cudaGetDevice(&dev));
+  const long long key = ((long long)dev << 32) | (unsigned)M;
+  auto it = tabs.find(key);
+  if (it != tabs.end()) return it->second;
+  double2 *t = nullptr;
+  const int ntw = bf2_tw_total(M);
+  CMDR_CUDA_CHECK(cudaMalloc(&t, sizeof(double2) * (size_t)ntw));
+  for (int k = 0; k < bf2_num_strided(M); ++k) {
+    const int h = bf2_half(M, k), cnt = h >> (bf2_stages(M, k) - 1);
+    twiddle_kernel<<<(cnt + 255) / 256, 256, 0, st>>>(t + bf2_tw_offset(M, k), h, cnt);
+    count_launch();
+  }
+  twiddle_kernel<<<1, 32, 0, st>>>(t + ntw - 1, 1, 1);        // exp(0) = 1
+  count_launch();
   CMDR_CUDA_CHECK(cudaGetLastError());
   tabs[key] = t;
   return t;
@@ -406,6 +469,37 @@ static int launch_fused(sharp_geom_info *g, int ncomp, int nregions, const FPara
     CMDR_CUDA_CHECK(cudaFuncSetAttribute(blue_fused_kernel<DIR, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
   }
   const double2 *vbr = reinterpret_cast<const double2 *>(g->d_vtab_br);
+  static const bool blocked = getenv("CMDR_SHT_FFT_BLOCKED") && atoi(getenv("CMDR_SHT_FFT_BLOCKED")) != 0;
+  if (blocked) {
+    static bool attr2_set = false;
+    if (!attr2_set) {
+      attr2_set = true;
+      const int smem2 = (int)(sizeof(double2) * (8192 + 512 + bf2_tw_total(8192)));
+      CMDR_CUDA_CHECK(cudaFuncSetAttribute(blue_fused2_kernel<DIR, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2));
+      CMDR_CUDA_CHECK(cudaFuncSetAttribute(blue_fused2_kernel<DIR, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2));
+      CMDR_CUDA_CHECK(cudaFuncSetAttribute(blue_fused2_kernel<DIR, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2));
+    }
+    for (int r = 0; r < nregions; ++r) twiddle_table2(g->regions[r].len, st);
+    cudaEvent_t e0 = pooled_event(150);
+    CMDR_CUDA_CHECK(cudaEventRecord(e0, st));
+    int ns = 0;
+    for (int r = nregions - 1; r >= 0; --r) {
+      const FftRegion &R = g->regions[r];
+      if (R.np == 0) continue;
+      cudaStream_t cs = class_stream(ns);
+      CMDR_CUDA_CHECK(cudaStreamWaitEvent(cs, e0, 0));
+      const double2 *tw = twiddle_table2(R.len, st);
+      const size_t smem = sizeof(double2) * (size_t)(R.len + (R.len >> 4) + bf2_tw_total(R.len));
+      if (R.len <= 2048) blue_fused2_kernel<DIR, 128><<<dim3(R.np, ncomp), 128, smem, cs>>>(p, R.first, R.len, tw, vbr);
+      else if (R.len <= 4096) blue_fused2_kernel<DIR, 256><<<dim3(R.np, ncomp), 256, smem, cs>>>(p, R.first, R.len, tw, vbr);
+      else blue_fused2_kernel<DIR, 512><<<dim3(R.np, ncomp), 512, smem, cs>>>(p, R.first, R.len, tw, vbr);
+      count_launch();
+      CMDR_CUDA_CHECK(cudaEventRecord(pooled_event(151 + ns), cs));
+      ++ns;
+    }
+    CMDR_CUDA_CHECK(cudaGetLastError());
+    return ns;
+  }
   for (int r = 0; r < nregions; ++r) twiddle_table(g->regions[r].len, st);     // built on st before the fork
   cudaEvent_t e0 = pooled_event(150);
   CMDR_CUDA_CHECK(cudaEventRecord(e0, st));
