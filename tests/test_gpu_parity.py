@@ -533,15 +533,19 @@ np.savez(sys.argv[1], map=mp, alm=m.alm)
 """ % root
     res = {}
     with tempfile.TemporaryDirectory() as td:
-        for flag in ("1", "0"):
-            out = os.path.join(td, f"r{flag}.npz")
-            env = dict(os.environ, CMDR_SHT_FUSED_BLUE=flag)
+        for flag, blocked in (("1", "0"), ("0", "0"), ("1", "1")):
+            out = os.path.join(td, f"r{flag}{blocked}.npz")
+            env = dict(os.environ, CMDR_SHT_FUSED_BLUE=flag, CMDR_SHT_FFT_BLOCKED=blocked)
             r = subprocess.run([sys.executable, "-c", code, out], env=env, capture_output=True, text=True, timeout=300)
             assert r.returncode == 0, r.stderr[-2000:]
-            res[flag] = dict(np.load(out))
-    assert rel(res["1"]["map"], res["0"]["map"]) <= 1e-13
-    assert rel(res["1"]["alm"], res["0"]["alm"]) <= 1e-13
-    assert not np.array_equal(res["1"]["map"], res["0"]["map"])      # two different code paths did run
+            res[flag + blocked] = dict(np.load(out))
+    assert rel(res["10"]["map"], res["00"]["map"]) <= 1e-13
+    assert rel(res["10"]["alm"], res["00"]["alm"]) <= 1e-13
+    assert not np.array_equal(res["10"]["map"], res["00"]["map"])      # two different code paths did run
+    # the register-blocked variant of the fused kernel (opt-in, CMDR_SHT_FFT_BLOCKED=1)
+    assert rel(res["11"]["map"], res["00"]["map"]) <= 1e-13
+    assert rel(res["11"]["alm"], res["00"]["alm"]) <= 1e-13
+    assert not np.array_equal(res["11"]["map"], res["10"]["map"])
 
 
 @pytest.mark.parametrize("spin", [0, 2])
