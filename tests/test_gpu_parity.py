@@ -543,8 +543,8 @@ np.savez(sys.argv[1], map=mp, alm=m.alm)
     assert rel(res["10"]["alm"], res["00"]["alm"]) <= 1e-13
     assert not np.array_equal(res["10"]["map"], res["00"]["map"])      # two different code paths did run
     # the register-blocked variant of the fused kernel (opt-in, CMDR_SHT_FFT_BLOCKED=1)
-    assert rel(res["11"]["map"], res["00"]["map"]) <= 1e-13
-    assert rel(res["11"]["alm"], res["00"]["alm"]) <= 1e-13
+    assert rel(res["11"]["map"], res["00"]["map"]) <= 1e-12
+    assert rel(res["11"]["alm"], res["00"]["alm"]) <= 1e-12
     assert not np.array_equal(res["11"]["map"], res["10"]["map"])
 
 
