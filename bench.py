@@ -65,7 +65,11 @@ def workload(args):
             "nside": args.nside, "lmax": args.lmax, "nmaps": 3,
             "l2_policy": "inputs larger than L2 (alm 0.38 GB, map 1.2 GB, phases 1.6 GB per direction)",
             "parallelism": "m-distributed alm / ring-distributed map; m<->ring exchange fused into the Legendre kernels over NVLink "
-                           "(NCCL all-to-all as fallback)"}
+                           "(NCCL all-to-all as fallback)",
+            "ring_fft": ("cuFFT for every ring class" if os.environ.get("CMDR_SHT_FUSED_BLUE", "1") == "0" else
+                         "fused chirp-z kernel for the polar-cap classes with work length <= 8192"
+                         + (" (register-blocked variant)" if os.environ.get("CMDR_SHT_FFT_BLOCKED", "0") not in ("", "0") else "")
+                         + ", cuFFT for the belt and the 16384 classes")}
 
 
 # ------------------------------------------------------------------ CPU baseline / reference arm
