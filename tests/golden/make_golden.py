@@ -60,7 +60,35 @@ def scipy_columns(nside, lmax):
             "slots": np.array([idx.index(p) for p in picks], dtype=np.int32), "cols": np.array(cols)}
 
 
+def conviqt_case(nside, lmax, bmax, seed):
+    """The conviqt cube (commander3/src/comm_conviqt_mod.f90:207-357) with the spin-j syntheses done by the DENSE
+    definitional matrices (not by the fast CPU path): sky and beam a_lm in, double-precision cube out."""
+    from oracle import conviqt as O
+    rng = np.random.default_rng(seed)
+    lm = O.lm_table(lmax)
+    sky = rng.standard_normal((3, len(lm)))
+    beam = rng.standard_normal((3, len(lm))) / (1.0 + np.array([t[0] for t in lm]))
+    tab = O.beam_table(lmax, 3, lm, beam)
+    npix = D.map_size(nside, list(range(1, 4 * nside)))
+    marr = {}
+    for j in range(bmax + 1):
+        alm = O.get_alms(j, lmax, lm, sky, tab)
+        if j == 0:
+            marr[0] = D.Y_matrix(nside, lmax, 0) @ alm[0]
+        else:
+            mm = (D.Y_matrix(nside, lmax, j) @ alm.ravel()).reshape(2, npix)
+            marr[j], marr[-j] = mm[0], mm[1]
+    n = 2 * bmax
+    cube = np.empty((n, npix))
+    for i in range(npix):
+        dv = np.array([marr[0][i]] + [marr[j][i] + 1j * marr[-j][i] for j in range(1, bmax + 1)])
+        cube[:, i] = O.c2r(dv, n)
+    return {"nside": nside, "lmax": lmax, "bmax": bmax, "sky_alm": sky, "beam_alm": beam, "cube": cube}
+
+
 if __name__ == "__main__":
+    np.savez_compressed(os.path.join(OUT, "conviqt_n2_l5_b2.npz"), **conviqt_case(2, 5, 2, 21))
+    np.savez_compressed(os.path.join(OUT, "conviqt_n4_l6_b3.npz"), **conviqt_case(4, 6, 3, 22))
     np.savez_compressed(os.path.join(OUT, "dense_n4_l9.npz"), **case(4, 9, 11))
     np.savez_compressed(os.path.join(OUT, "dense_n2_l7.npz"), **case(2, 7, 12))        # lmax > 3 nside - 1
     np.savez_compressed(os.path.join(OUT, "dense_n4_l8_rank1of3.npz"), **case(4, 8, 13, rank=1, nprocs=3))

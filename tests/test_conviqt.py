@@ -107,3 +107,24 @@ def test_mirror_host_logic_matches_oracle(shtlib):
         got = cv.interp(pix, psi)
         ref = np.array([O.interp(cv.c, cv.psisteps, int(p), float(a), optim) for p, a in zip(pix, psi)], dtype=np.float32)
         assert got.dtype == np.float32 and np.array_equal(got, ref, equal_nan=True)
+
+
+import glob
+import os
+
+import pytest
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLD, "conviqt_*.npz"))))
+def test_oracle_cube_vs_golden(cpu_oracle, path):
+    """The committed cubes were made with the dense definitional spin-j matrices (tests/golden/make_golden.py);
+    the restatement with the fast CPU transforms must reproduce them."""
+    g = np.load(path)
+    nside, lmax, bmax = int(g["nside"]), int(g["lmax"]), int(g["bmax"])
+    lm = O.lm_table(lmax)
+    tab = O.beam_table(lmax, 3, lm, g["beam_alm"])
+    for vec in (True, False):
+        cube = O.precompute_sky(cpu_oracle, nside, lmax, bmax, g["sky_alm"], tab, vectorised=vec)
+        assert np.linalg.norm(cube - g["cube"]) <= 1e-12 * np.linalg.norm(g["cube"])

@@ -115,3 +115,25 @@ def test_beam_rotation_shifts_psi(shtlib):
     want = torch.roll(c0, -shift, dims=0)
     assert float((c1 - want).norm() / want.norm()) <= 1e-12
     assert float(c0.norm()) > 0 and float((c1 - c0).norm() / c0.norm()) > 1e-3
+
+
+def test_cube_vs_golden(shtlib):
+    """The committed conviqt cubes (dense definitional spin-j matrices, tests/golden/make_golden.py) through the C ABI."""
+    import glob
+    import os
+    from commander_b200 import comm_map, comm_mapinfo
+    from commander_b200.comm_conviqt import comm_conviqt
+    gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    paths = sorted(glob.glob(os.path.join(gold, "conviqt_*.npz")))
+    assert paths
+    for path in paths:
+        g = np.load(path)
+        nside, lmax, bmax = int(g["nside"]), int(g["lmax"]), int(g["bmax"])
+        info = comm_mapinfo(None, nside, lmax, 3, True)
+        sky, beam = comm_map(info), comm_map(info)
+        sky.alm[...] = g["sky_alm"]
+        beam.alm[...] = g["beam_alm"]
+        cv = comm_conviqt(nside, lmax, 3, bmax, beam, sky, precompute=False)
+        c64 = np.zeros((2 * bmax, info.np))
+        cv.precompute_sky(sky, cube=c64)
+        assert rel(c64, g["cube"]) <= TOL, (path, rel(c64, g["cube"]))
