@@ -23,6 +23,7 @@ namespace cmdr {
 
 void destroy_plans(sharp_geom_info *g);
 void forget_layout(const sharp_alm_info *a);
+void dist_forget_handle(const void *h);   // dist.cu: drops every cached distributed plan built for this handle
 
 static std::atomic<unsigned long long> g_launches{0};
 void count_launch(int n) { g_launches += (unsigned long long)n; }
@@ -271,6 +272,7 @@ ptrdiff_t sharp_alm_count(const sharp_alm_info *self) { return (ptrdiff_t)self->
 
 void sharp_destroy_alm_info(sharp_alm_info *a) {
   if (!a) return;
+  dist_forget_handle(a);
   if (a->device >= 0) {
     forget_layout(a);
     cudaFree(a->d_mval); cudaFree(a->d_mvstart); cudaFree(a->d_m2im);
@@ -318,6 +320,7 @@ void sharp_make_subset_healpix_geom_info(int nside, int stride, int nrings, cons
 
 void sharp_destroy_geom_info(sharp_geom_info *g) {
   if (!g) return;
+  dist_forget_handle(g);
   for (sharp_geom_info *sub : g->subs) sharp_destroy_geom_info(sub);
   g->subs.clear();
   if (g->device >= 0) {
@@ -570,9 +573,11 @@ static bool try_pipelined(int type, int spin, double *const *alm, double *const 
   const int ncomp = spin == 0 ? 1 : 2;
   if (disabled || (flags & SHARP_ADD) || g->npix < (1 << 21) || a->nm == 0 || spin < 0 || spin > CMDR_MAX_SPIN) return false;
   if (type < 0 || type > 3) return false;
-  for (int c = 0; c < ncomp; ++c) if (!is_pinned_host(alm[c]) || !is_pinned_host(map[c])) return false;
-  static const bool nocopy = getenv("CMDR_SHT_PIPE_NOCOPY") != nullptr;   // tuning aid: time the chunked kernels alone (results are garbage)
-#define PIPE_COPY(...) do { if (!nocopy) CMDR_CUDA_CHECK(cudaMemcpyAsync(__VA_ARGS__)); } while (0)
+  // host arrays of either kind: pinned ones are copied in place, pageable ones (what sharp.f90:219-224 passes)
+  // go through the library's pinned arena and the copy threads (hostio.cu)
+  for (int c = 0; c < ncomp; ++c)
+    if (host_kind(alm[c]) == HostKind::Device || host_kind(map[c]) == HostKind::Device) return false;
+  HostIO ioA, ioM;
   // tuning aid: CMDR_SHT_PIPE_TRACE=1 prints a timeline (ms since the call started) of the stream markers below
   static const bool trace = getenv("CMDR_SHT_PIPE_TRACE") != nullptr;
   std::vector<std::pair<std::string, cudaEvent_t>> marks;
@@ -606,6 +611,8 @@ static bool try_pipelined(int type, int spin, double *const *alm, double *const 
   double *alm_buf = static_cast<double *>(scratch_get("stage_alm", sizeof(double) * (size_t)nalm_d * ncomp));
   double *map_buf = static_cast<double *>(scratch_get("stage_map", sizeof(double) * (size_t)g->npix * ncomp));
   double4 *ph = static_cast<double4 *>(scratch_get("phase", sizeof(double4) * (size_t)ncomp * a->nm * g->npairs));
+  ioA.init("hstage_alm", alm, ncomp, nalm_d);
+  ioM.init("hstage_map", map, ncomp, g->npix);
   long long maxz = 0;
   for (sharp_geom_info *sub : g->subs) { ensure_geom_device(sub); maxz = std::max(maxz, sub->zlen_total); }
   scratch_get("fftbuf", sizeof(double2) * (size_t)maxz * ncomp);
@@ -627,16 +634,14 @@ static bool try_pipelined(int type, int spin, double *const *alm, double *const 
     std::vector<int> mcut;
     const int nmch = alm_m_chunks(a, nalm_d, NMCH, mstart, mcut) ? NMCH : 1;
     if (nmch == 1) {
-      for (int c = 0; c < ncomp; ++c)
-        PIPE_COPY(alm_dev[c], alm[c], sizeof(double) * nalm_d, cudaMemcpyHostToDevice, st);
+      for (int c = 0; c < ncomp; ++c) ioA.h2d(alm_dev[c], c, 0, nalm_d, st);
     } else {
       cudaEvent_t e0 = pooled_event(ns + 1);               // earlier work on `st` may still read the staging buffer
       CMDR_CUDA_CHECK(cudaEventRecord(e0, st));
       CMDR_CUDA_CHECK(cudaStreamWaitEvent(cs, e0, 0));
       for (int j = 0; j < nmch; ++j) {
         const long long b = mstart[mcut[j]], e = mstart[mcut[j + 1]];
-        for (int c = 0; c < ncomp; ++c)
-          if (e > b) PIPE_COPY(alm_dev[c] + b, alm[c] + b, sizeof(double) * (e - b), cudaMemcpyHostToDevice, cs);
+        for (int c = 0; c < ncomp; ++c) ioA.h2d(alm_dev[c] + b, c, b, e - b, cs);
         CMDR_CUDA_CHECK(cudaEventRecord(pooled_event(ns + 2 + j), cs));
         mark("up", j, cs);
       }
@@ -657,10 +662,10 @@ static bool try_pipelined(int type, int spin, double *const *alm, double *const 
       long long nb, ne, sb, se;
       sub_ranges(sub, nb, ne, sb, se);
       for (int c = 0; c < ncomp; ++c) {
-        PIPE_COPY(map[c] + nb, map_dev[c] + nb, sizeof(double) * (ne - nb), cudaMemcpyDeviceToHost, cs);
-        if (se > sb)
-          PIPE_COPY(map[c] + sb, map_dev[c] + sb, sizeof(double) * (se - sb), cudaMemcpyDeviceToHost, cs);
+        ioM.d2h(map_dev[c] + nb, c, nb, ne - nb, cs);
+        ioM.d2h(map_dev[c] + sb, c, sb, se - sb, cs);
       }
+      ioM.commit(cs);
       mark("down", i, cs);
     };
     if (nmch > 1) {
@@ -689,6 +694,7 @@ static bool try_pipelined(int type, int spin, double *const *alm, double *const 
       launch_legendre_synth(spin, G, A, alm_dev, ph, st, nmch == 1 && i == ns - 1);
       finish_chunk(i);
     }
+    ioM.drain();                                   // pageable caller map: rows leave the arena as their chunks land
     CMDR_CUDA_CHECK(cudaStreamSynchronize(cs));
     CMDR_CUDA_CHECK(cudaStreamSynchronize(st));
   } else {
@@ -707,9 +713,8 @@ static bool try_pipelined(int type, int spin, double *const *alm, double *const 
       long long nb, ne, sb, se;
       sub_ranges(sub, nb, ne, sb, se);
       for (int c = 0; c < ncomp; ++c) {
-        PIPE_COPY(map_dev[c] + nb, map[c] + nb, sizeof(double) * (ne - nb), cudaMemcpyHostToDevice, cs);
-        if (se > sb)
-          PIPE_COPY(map_dev[c] + sb, map[c] + sb, sizeof(double) * (se - sb), cudaMemcpyHostToDevice, cs);
+        ioM.h2d(map_dev[c] + nb, c, nb, ne - nb, cs);
+        ioM.h2d(map_dev[c] + sb, c, sb, se - sb, cs);
       }
       cudaEvent_t e = pooled_event(i);
       CMDR_CUDA_CHECK(cudaEventRecord(e, cs));
@@ -742,20 +747,20 @@ static bool try_pipelined(int type, int spin, double *const *alm, double *const 
         mark("legm", j, sj);
         CMDR_CUDA_CHECK(cudaStreamWaitEvent(cs, e, 0));
         const long long b = mstart[mcut[j]], e2 = mstart[mcut[j + 1]];
-        for (int c = 0; c < ncomp; ++c)
-          if (e2 > b) PIPE_COPY(alm[c] + b, alm_dev[c] + b, sizeof(double) * (e2 - b), cudaMemcpyDeviceToHost, cs);
+        for (int c = 0; c < ncomp; ++c) ioA.d2h(alm_dev[c] + b, c, b, e2 - b, cs);
+        ioA.commit(cs);
         mark("down", j, cs);
       }
     }
     if (nmch == 1) {
-      for (int c = 0; c < ncomp; ++c)
-        PIPE_COPY(alm[c], alm_dev[c], sizeof(double) * nalm_d, cudaMemcpyDeviceToHost, st);
+      for (int c = 0; c < ncomp; ++c) ioA.d2h(alm_dev[c], c, 0, nalm_d, st);
+      ioA.commit(st);
     }
+    ioA.drain();
     CMDR_CUDA_CHECK(cudaStreamSynchronize(cs));
     if (as != st) CMDR_CUDA_CHECK(cudaStreamSynchronize(as));
     CMDR_CUDA_CHECK(cudaStreamSynchronize(st));
   }
-#undef PIPE_COPY
   dump_marks();
   return true;
 }
@@ -884,7 +889,10 @@ void cmdr_sht_execute_iqu_batch(int type, int nbatch, double *const *alm3, doubl
     if (b >= 2) CMDR_CUDA_CHECK(cudaStreamWaitEvent(cin, done[b - 2], 0));
     for (int c = 0; c < 3; ++c)
       CMDR_CUDA_CHECK(cudaMemcpyAsync(in_dev + (size_t)c * nin, in_host[3 * b + c], sizeof(double) * nin, cudaMemcpyHostToDevice, cin));
-    if (add)   // accumulate into the caller's output: it has to come up too
+    // accumulate into the caller's output: it has to come up too -- into the staging set whose previous content
+    // (the result of band b-2) may still be on its way down on `cout`
+    if (add && b >= 2) CMDR_CUDA_CHECK(cudaStreamWaitEvent(cin, down[b - 2], 0));
+    if (add)
       for (int c = 0; c < 3; ++c)
         CMDR_CUDA_CHECK(cudaMemcpyAsync(out_dev + (size_t)c * nout, out_host[3 * b + c], sizeof(double) * nout, cudaMemcpyHostToDevice, cin));
     CMDR_CUDA_CHECK(cudaEventRecord(up[b], cin));
@@ -921,6 +929,6 @@ int cmdr_sht_last_legendre_ms(double *entries3, int max) {
 unsigned long long cmdr_sht_nominal_flops(const sharp_geom_info *g, const sharp_alm_info *a, int spin) {
   return nominal_flops(g, a, spin);
 }
-void cmdr_sht_release_caches(void) { scratch_release(); }
+void cmdr_sht_release_caches(void) { scratch_release(); pinned_release(); }
 
 }  // extern "C"

@@ -21,6 +21,7 @@
 #include <nccl.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cstring>
 #include <map>
 #include <tuple>
@@ -108,6 +109,7 @@ struct DistPlan {
   std::vector<int> lcut;                      // this rank's local pair boundaries, size nchunk + 1
   std::vector<sharp_geom_info *> subs;        // per chunk (nullptr when this rank has no pair in it)
   bool subs_built = false;
+  int pipe_ok = -1;                           // chunked host pipeline usable on EVERY rank (agreed once; -1 = not yet)
 };
 
 struct PeerBuf {                       // one receive buffer per rank, mapped by every rank
@@ -130,6 +132,55 @@ static std::map<int, DistComm *> g_comms;
 static DistComm *find_comm(int comm) {
   auto it = g_comms.find(comm);
   return it == g_comms.end() ? nullptr : it->second;
+}
+
+static void free_plan(DistPlan *P) {
+  cudaFree(P->d_trig); cudaFree(P->d_wslot); cudaFree(P->d_m2src); cudaFree(P->d_m2im); cudaFree(P->d_mlist);
+  cudaFree(P->d_mlist_src); cudaFree(P->d_mlist_im);
+  for (auto &m : P->d_mlim) cudaFree(m.second);
+  for (sharp_geom_info *sub : P->subs) if (sub) sharp_destroy_geom_info(sub);
+  delete P;
+}
+
+// Called by sharp_destroy_geom_info / sharp_destroy_alm_info (abi.cu): every cached plan that was built for the
+// handle goes with it, so that a later handle that happens to get the same heap address (comm_mapinfo%dealloc
+// followed by a new comm_mapinfo, commander3/src/comm_map_mod.f90:419-431) can never hit a stale plan.
+void dist_forget_handle(const void *h) {
+  for (auto &kc : g_comms) {
+    DistComm *C = kc.second;
+    for (auto it = C->plans.begin(); it != C->plans.end();) {
+      if ((const void *)std::get<0>(it->first) == h || (const void *)std::get<1>(it->first) == h) {
+        DistPlan *P = it->second;
+        it = C->plans.erase(it);
+        CMDR_CUDA_CHECK(cudaDeviceSynchronize());       // the plan's tables may still be in use by queued kernels
+        free_plan(P);
+      } else {
+        ++it;
+      }
+    }
+  }
+}
+
+// An unknown communicator handle must never run silently as a local transform: under `mpirun -np 8` every rank
+// holds a strict subset of the rings and m's and the result would be wrong without a message.  The only
+// communicator-less case that is well defined is a group of one, where the handles cover the whole sphere.
+constexpr int CMDR_COMM_SELF = -1;
+static bool covers_sphere(const sharp_geom_info *g, const sharp_alm_info *a) {
+  if (g->nrings != 4 * g->nside - 1 || a->nm != a->lmax + 1) return false;
+  std::vector<char> seen(a->lmax + 1, 0);
+  for (int m : a->mval) seen[m] = 1;
+  for (char c : seen) if (!c) return false;
+  return true;
+}
+static DistComm *comm_or_local(int comm, const sharp_geom_info *g, const sharp_alm_info *a, const char *who) {
+  DistComm *C = find_comm(comm);
+  if (C) return C->nranks == 1 ? nullptr : C;
+  if (comm == CMDR_COMM_SELF || covers_sphere(g, a)) return nullptr;     // a group of one
+  fprintf(stderr, "cmdr_sht: %s called with communicator %d that was never registered with cmdr_sht_comm_register, and the "
+          "handles hold only part of the sphere (%d of %d rings, %d of %d m's): refusing to run a local transform.  "
+          "Register every communicator that reaches sharp_execute (INTEGRATION.md section 2).\n",
+          who, comm, g->nrings, 4 * g->nside - 1, a->nm, a->lmax + 1);
+  abort();
 }
 
 // all-gather a vector of ints padded to `n` entries per rank
@@ -471,15 +522,30 @@ static bool try_dist_pipelined(DistComm *C, int type, int spin, double *const *a
   static const bool disabled = getenv("CMDR_SHT_NO_PIPELINE") != nullptr;
   const int ncomp = spin == 0 ? 1 : 2;
   if (disabled || (flags & SHARP_ADD) || !use_p2p(C) || type < 0 || type > 3) return false;
-  // every rank must take the same decision: it depends only on properties that are equal on all ranks
-  // (global sizes) or that the caller keeps symmetric (pinned buffers on all ranks or on none)
+  // Every rank must take the same decision (the chunked path has K + 1 exchange barriers, the plain one 2).
+  // Global sizes are equal everywhere by construction; host-versus-device buffers is a property of the call
+  // site, the same on all ranks of a collective call (pinned or pageable does not matter: both take this
+  // path).  What can differ from rank to rank -- a rank without rings or m's, a ring list that is not
+  // contiguous -- is agreed once per plan with an all-reduce (min) and cached there.
   if ((long long)g->nside * g->nside * 12 < (1LL << 20) * C->nranks) return false;
-  for (int c = 0; c < ncomp; ++c) if (!is_pinned_host(alm[c]) || !is_pinned_host(map[c])) return false;
-  if (g->npairs == 0 || a->nm == 0 || !pairs_contiguous(g)) return false;
+  for (int c = 0; c < ncomp; ++c)
+    if (host_kind(alm[c]) == HostKind::Device || host_kind(map[c]) == HostKind::Device) return false;
   const bool synth = (type == SHARP_Y || type == SHARP_WY);
   ensure_geom_device(g);
   ensure_alm_device(a);
   DistPlan *P = get_plan(C, g, a, st);
+  if (P->pipe_ok < 0) {
+    int ok = (g->npairs > 0 && a->nm > 0 && pairs_contiguous(g)) ? 1 : 0;
+    int *d_ok = nullptr;
+    CMDR_CUDA_CHECK(cudaMalloc(&d_ok, sizeof(int)));
+    CMDR_CUDA_CHECK(cudaMemcpyAsync(d_ok, &ok, sizeof(int), cudaMemcpyHostToDevice, st));
+    CMDR_NCCL_CHECK(nccl_api()->AllReduce(d_ok, d_ok, 1, ncclInt32, ncclMin, C->nccl, st));
+    CMDR_CUDA_CHECK(cudaMemcpyAsync(&ok, d_ok, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CMDR_CUDA_CHECK(cudaStreamSynchronize(st));
+    cudaFree(d_ok);
+    P->pipe_ok = ok;
+  }
+  if (!P->pipe_ok) return false;
   const int K = (int)P->wcut.size() - 1;
   if (!P->subs_built) {
     P->subs_built = true;
@@ -509,9 +575,11 @@ static bool try_dist_pipelined(DistComm *C, int type, int spin, double *const *a
   LegAlm A = make_legalm(a, spin);
   cudaStream_t cs = copy_stream();
   const size_t ev0 = 32;                                  // events 0..31 belong to the single-GPU pipeline
+  HostIO ioA, ioM;                                        // pageable caller arrays go through the pinned arena (hostio.cu)
+  ioA.init("hstage_alm", alm, ncomp, nalm_d);
+  ioM.init("hstage_map", map, ncomp, g->npix);
   if (synth) {
-    for (int c = 0; c < ncomp; ++c)
-      CMDR_CUDA_CHECK(cudaMemcpyAsync(alm_dev[c], alm[c], sizeof(double) * nalm_d, cudaMemcpyHostToDevice, st));
+    for (int c = 0; c < ncomp; ++c) ioA.h2d(alm_dev[c], c, 0, nalm_d, st);
     stream_barrier(C, st);                                 // every rank has finished reading its buffer
     for (int c = K - 1; c >= 0; --c) {                     // belt first, polar caps last
       G.slot_begin = P->wcut[c]; G.slot_end = P->wcut[c + 1];
@@ -527,11 +595,12 @@ static bool try_dist_pipelined(DistComm *C, int type, int spin, double *const *a
       long long nb, ne, sb, se;
       sub_ranges(sub, nb, ne, sb, se);
       for (int k = 0; k < ncomp; ++k) {
-        CMDR_CUDA_CHECK(cudaMemcpyAsync(map[k] + nb, map_dev[k] + nb, sizeof(double) * (ne - nb), cudaMemcpyDeviceToHost, cs));
-        if (se > sb)
-          CMDR_CUDA_CHECK(cudaMemcpyAsync(map[k] + sb, map_dev[k] + sb, sizeof(double) * (se - sb), cudaMemcpyDeviceToHost, cs));
+        ioM.d2h(map_dev[k] + nb, k, nb, ne - nb, cs);
+        ioM.d2h(map_dev[k] + sb, k, sb, se - sb, cs);
       }
+      ioM.commit(cs);
     }
+    ioM.drain();
     CMDR_CUDA_CHECK(cudaStreamSynchronize(cs));
     CMDR_CUDA_CHECK(cudaStreamSynchronize(st));
   } else {
@@ -546,9 +615,8 @@ static bool try_dist_pipelined(DistComm *C, int type, int spin, double *const *a
         long long nb, ne, sb, se;
         sub_ranges(sub, nb, ne, sb, se);
         for (int k = 0; k < ncomp; ++k) {
-          CMDR_CUDA_CHECK(cudaMemcpyAsync(map_dev[k] + nb, map[k] + nb, sizeof(double) * (ne - nb), cudaMemcpyHostToDevice, cs));
-          if (se > sb)
-            CMDR_CUDA_CHECK(cudaMemcpyAsync(map_dev[k] + sb, map[k] + sb, sizeof(double) * (se - sb), cudaMemcpyHostToDevice, cs));
+          ioM.h2d(map_dev[k] + nb, k, nb, ne - nb, cs);
+          ioM.h2d(map_dev[k] + sb, k, sb, se - sb, cs);
         }
         cudaEvent_t e = pooled_event(ev0 + c);
         CMDR_CUDA_CHECK(cudaEventRecord(e, cs));
@@ -560,8 +628,9 @@ static bool try_dist_pipelined(DistComm *C, int type, int spin, double *const *a
       G.slot_begin = P->wcut[c]; G.slot_end = P->wcut[c + 1];
       launch_legendre_anal(spin, G, A, alm_dev, reinterpret_cast<const double4 *>(B.mine), st);
     }
-    for (int c = 0; c < ncomp; ++c)
-      CMDR_CUDA_CHECK(cudaMemcpyAsync(alm[c], alm_dev[c], sizeof(double) * nalm_d, cudaMemcpyDeviceToHost, st));
+    for (int c = 0; c < ncomp; ++c) ioA.d2h(alm_dev[c], c, 0, nalm_d, st);
+    ioA.commit(st);
+    ioA.drain();
     CMDR_CUDA_CHECK(cudaStreamSynchronize(st));
   }
   return true;
@@ -627,14 +696,10 @@ int cmdr_sht_comm_register(int comm, int rank, int nranks, const void *id128) {
 void cmdr_sht_comm_destroy(int comm) {
   DistComm *C = find_comm(comm);
   if (!C) return;
-  for (auto &kv : C->plans) {
-    DistPlan *P = kv.second;
-    cudaFree(P->d_trig); cudaFree(P->d_wslot); cudaFree(P->d_m2src); cudaFree(P->d_m2im); cudaFree(P->d_mlist);
-    cudaFree(P->d_mlist_src); cudaFree(P->d_mlist_im);
-    for (auto &m : P->d_mlim) cudaFree(m.second);
-    for (sharp_geom_info *sub : P->subs) if (sub) sharp_destroy_geom_info(sub);
-    delete P;
-  }
+  std::vector<DistPlan *> plans;
+  for (auto &kv : C->plans) plans.push_back(kv.second);
+  C->plans.clear();                      // free_plan destroys sub-geometries, whose destructor walks the plan maps
+  for (DistPlan *P : plans) free_plan(P);
   close_peerbuf(C, C->pb[0]); close_peerbuf(C, C->pb[1]);
   if (C->d_flag) cudaFree(C->d_flag);
   if (C->nccl) nccl_api()->CommDestroy(C->nccl);
@@ -642,12 +707,19 @@ void cmdr_sht_comm_destroy(int comm) {
   delete C;
 }
 
+void cmdr_sht_comm_set_exchange(int comm, int mode) {
+  DistComm *C = find_comm(comm);
+  if (!C) return;
+  CMDR_CUDA_CHECK(cudaDeviceSynchronize());
+  C->p2p = mode < 0 ? -1 : ((mode && C->nranks <= CMDR_MAX_PEERS) ? 1 : 0);
+}
+
 void cmdr_sht_execute_dist(int comm, int type, int spin, void *alm, void *map, const sharp_geom_info *geom_info,
                            const sharp_alm_info *alm_info, int flags, void *stream) {
-  DistComm *C = find_comm(comm);
   sharp_geom_info *g = const_cast<sharp_geom_info *>(geom_info);
   sharp_alm_info *a = const_cast<sharp_alm_info *>(alm_info);
-  if (!C || C->nranks == 1) {
+  DistComm *C = comm_or_local(comm, g, a, "cmdr_sht_execute_dist");
+  if (!C) {
     execute_any(type, spin, alm, map, g, a, flags, nullptr, nullptr, (cudaStream_t)stream);
     return;
   }
@@ -658,8 +730,8 @@ void cmdr_sht_execute_dist(int comm, int type, int spin, void *alm, void *map, c
 void cmdr_sht_execute_iqu_dist(int comm, int type, double *const *alm3, double *const *map3,
                                const sharp_geom_info *geom_T, const sharp_geom_info *geom_P,
                                const sharp_alm_info *alm_info, int flags, void *stream) {
-  DistComm *C = find_comm(comm);
-  if (!C || C->nranks == 1) {
+  DistComm *C = comm_or_local(comm, geom_T, alm_info, "cmdr_sht_execute_iqu_dist");
+  if (!C) {
     cmdr_sht_execute_iqu(type, alm3, map3, geom_T, geom_P, alm_info, flags, stream);
     return;
   }
@@ -671,6 +743,11 @@ void cmdr_sht_execute_iqu_dist(int comm, int type, double *const *alm3, double *
 
 void cmdr_sht_allreduce_sum(int comm, double *dev_buf, int n, void *stream) {
   DistComm *C = find_comm(comm);
+  if (!C && comm != CMDR_COMM_SELF) {
+    fprintf(stderr, "cmdr_sht_allreduce_sum: communicator %d was never registered (cmdr_sht_comm_register); a silent no-op "
+            "would leave every rank with its local partial sum\n", comm);
+    abort();
+  }
   if (!C || C->nranks == 1) return;
   CMDR_NCCL_CHECK(nccl_api()->AllReduce(dev_buf, dev_buf, n, ncclDouble, ncclSum, C->nccl, (cudaStream_t)stream));
   count_launch(1);
@@ -761,17 +838,18 @@ void cmdr_sht_mix(int comm, int nmaps, double *const *alm, const double *const *
 void sharp_execute_mpi_fortran(int comm, int type, int spin, void *alm, void *map,
                                const sharp_geom_info *geom_info, const sharp_alm_info *alm_info, int flags,
                                double *time, unsigned long long *opcnt) {
-  DistComm *C = find_comm(comm);
   sharp_geom_info *g = const_cast<sharp_geom_info *>(geom_info);
   sharp_alm_info *a = const_cast<sharp_alm_info *>(alm_info);
-  if (!C || C->nranks == 1) {
+  DistComm *C = comm_or_local(comm, g, a, "sharp_execute_mpi_fortran");
+  if (!C) {
     execute_any(type, spin, alm, map, g, a, flags, time, opcnt, (cudaStream_t)0);
     return;
   }
+  auto t0 = std::chrono::steady_clock::now();
   execute_dist_any(C, type, 1, &spin, static_cast<double *const *>(alm), static_cast<double *const *>(map), &g, a,
                    flags, (cudaStream_t)0);
   if (time || opcnt) CMDR_CUDA_CHECK(cudaStreamSynchronize(0));
-  if (time) *time = 0.0;
+  if (time) *time = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();   // wall seconds, as libsharp2 reports
   if (opcnt) *opcnt = cmdr_sht_nominal_flops(geom_info, alm_info, spin);
 }
 

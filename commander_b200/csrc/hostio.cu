@@ -1,0 +1,198 @@
+// hostio.cu -- host-side staging for the buffers the reference really passes.
+//
+// commander3/src/sharp.f90:219-224 hands sharp_execute `c_loc` of ordinary (pageable) Fortran arrays.
+// DMA needs page-locked memory; registering the caller's arrays (cudaHostRegister) would be the obvious
+// route, but Commander allocates and frees its comm_map arrays all the time (cr_matmulA builds temporary
+// comm_map objects in every CG iteration, commander3/src/comm_cr_mod.f90:877-918) and a registration that
+// outlives a free()/munmap silently points the DMA engine at stale physical pages.  So the library owns a
+// pinned staging arena instead and moves the data between the caller's pages and the arena with a small pool
+// of copy threads, chunk by chunk inside the same pipeline that overlaps PCIe with the kernels:
+//
+//   upload   : worker threads copy chunk c+1 caller -> arena while chunk c is in flight over PCIe / in the kernels
+//   download : the D2H of a chunk lands in the arena; once its event completes the workers copy it to the caller
+//              while the GPU already works on the next chunk
+//
+// Pinned caller buffers (cudaMallocHost / cudaHostRegister done by the application) bypass the arena.
+#include <atomic>
+#include <condition_variable>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <thread>
+
+#include "kernels.h"
+
+namespace cmdr {
+
+// ---------------------------------------------------------------- pinned arena (grow-only, per tag and device)
+struct PinnedBuf { void *ptr = nullptr; size_t bytes = 0; };
+static std::map<std::string, PinnedBuf> g_pinned;
+static std::mutex g_pin_mu;
+
+void *pinned_get(const char *name, size_t bytes) {
+  int dev = 0;
+  CMDR_CUDA_CHECK(cudaGetDevice(&dev));
+  std::string key = std::string(name) + "@" + std::to_string(dev);
+  std::lock_guard<std::mutex> lk(g_pin_mu);
+  PinnedBuf &b = g_pinned[key];
+  if (b.bytes < bytes) {
+    if (b.ptr) { CMDR_CUDA_CHECK(cudaDeviceSynchronize()); CMDR_CUDA_CHECK(cudaFreeHost(b.ptr)); }
+    size_t want = bytes + bytes / 16 + 4096;
+    CMDR_CUDA_CHECK(cudaHostAlloc(&b.ptr, want, cudaHostAllocDefault));
+    b.bytes = want;
+  }
+  return b.ptr;
+}
+
+void pinned_release() {
+  std::lock_guard<std::mutex> lk(g_pin_mu);
+  for (auto &kv : g_pinned) if (kv.second.ptr) cudaFreeHost(kv.second.ptr);
+  g_pinned.clear();
+}
+
+// ---------------------------------------------------------------- copy-thread pool
+// One job at a time: memcpy(dst, src, n) cut into equal slices, one per worker plus the calling thread.
+class CopyPool {
+ public:
+  explicit CopyPool(int nworkers) : nw_(nworkers) {
+    for (int i = 0; i < nw_; ++i) std::thread([this, i] { run(i); }).detach();   // live until the process exits
+  }
+  void copy(void *dst, const void *src, size_t n) {
+    if (n < (size_t)(1 << 20) || nw_ == 0) { memcpy(dst, src, n); return; }
+    const int parts = nw_ + 1;
+    const size_t slice = ((n / parts) + 4095) & ~(size_t)4095;
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      dst_ = static_cast<char *>(dst); src_ = static_cast<const char *>(src); n_ = n; slice_ = slice;
+      pending_ = nw_;
+      ++gen_;
+    }
+    cv_.notify_all();
+    do_slice(nw_);                                  // the caller takes the last slice
+    std::unique_lock<std::mutex> lk(mu_);
+    done_.wait(lk, [this] { return pending_ == 0; });
+  }
+  int workers() const { return nw_; }
+
+ private:
+  void do_slice(int i) {
+    const size_t b = slice_ * (size_t)i;
+    if (b >= n_) return;
+    const size_t e = b + slice_ < n_ ? b + slice_ : n_;
+    memcpy(dst_ + b, src_ + b, e - b);
+  }
+  void run(int i) {
+    unsigned long long seen = 0;
+    for (;;) {
+      {
+        std::unique_lock<std::mutex> lk(mu_);
+        cv_.wait(lk, [&] { return gen_ != seen; });
+        seen = gen_;
+      }
+      do_slice(i);
+      {
+        std::lock_guard<std::mutex> lk(mu_);
+        if (--pending_ == 0) done_.notify_one();
+      }
+    }
+  }
+  int nw_;
+  std::mutex mu_;
+  std::condition_variable cv_, done_;
+  char *dst_ = nullptr;
+  const char *src_ = nullptr;
+  size_t n_ = 0, slice_ = 0;
+  int pending_ = 0;
+  unsigned long long gen_ = 0;
+};
+
+static CopyPool *copy_pool() {
+  static CopyPool *pool = [] {
+    int n = 0;
+    if (const char *e = getenv("CMDR_SHT_COPY_THREADS")) n = atoi(e);
+    if (n <= 0) {
+      // the threads this process may run on (respects taskset / cgroup / mpirun binding), at most 8
+      cpu_set_t set;
+      int avail = (sched_getaffinity(0, sizeof(set), &set) == 0) ? CPU_COUNT(&set) : (int)std::thread::hardware_concurrency();
+      n = avail / 2;
+      if (n > 8) n = 8;
+      if (n < 1) n = 1;
+    }
+    return new CopyPool(n - 1);                     // leaked on purpose: detached workers, no exit-order hazards
+  }();
+  return pool;
+}
+
+void host_copy(void *dst, const void *src, size_t bytes) { copy_pool()->copy(dst, src, bytes); }
+int host_copy_threads() { return copy_pool()->workers() + 1; }
+
+// ---------------------------------------------------------------- pointer classes
+HostKind host_kind(const void *p) {
+  if (!p) return HostKind::Device;                  // null columns (n_local == 0) never get dereferenced
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return HostKind::Pageable; }
+  if (at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged) return HostKind::Device;
+  if (at.type == cudaMemoryTypeHost) return HostKind::Pinned;
+  return HostKind::Pageable;
+}
+
+// ---------------------------------------------------------------- HostIO
+void HostIO::init(const char *tag, double *const *cols, int ncols, long long count) {
+  ncols_ = ncols; count_ = count;
+  pageable_ = false;
+  for (int c = 0; c < ncols; ++c) { user_[c] = cols[c]; pageable_ = pageable_ || host_kind(cols[c]) == HostKind::Pageable; }
+  stage_ = pageable_ ? static_cast<double *>(pinned_get(tag, sizeof(double) * (size_t)count * ncols)) : nullptr;
+}
+
+void HostIO::h2d(double *dev, int c, long long ofs, long long n, cudaStream_t s) {
+  if (n <= 0) return;
+  const double *src = user_[c] + ofs;
+  if (pageable_) {
+    double *sp = stage_ + (size_t)c * count_ + ofs;
+    host_copy(sp, src, sizeof(double) * (size_t)n);
+    src = sp;
+  }
+  CMDR_CUDA_CHECK(cudaMemcpyAsync(dev, src, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, s));
+}
+
+void HostIO::d2h(const double *dev, int c, long long ofs, long long n, cudaStream_t s) {
+  if (n <= 0) return;
+  double *dst = user_[c] + ofs;
+  if (pageable_) {
+    double *sp = stage_ + (size_t)c * count_ + ofs;
+    CMDR_CUDA_CHECK(cudaMemcpyAsync(sp, dev, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, s));
+    drains_.push_back(Drain{nullptr, dst, sp, sizeof(double) * (size_t)n});
+    return;
+  }
+  CMDR_CUDA_CHECK(cudaMemcpyAsync(dst, dev, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, s));
+}
+
+void HostIO::commit(cudaStream_t s) {
+  if (!pageable_) return;
+  cudaEvent_t e = nullptr;
+  for (Drain &d : drains_)
+    if (!d.ev && !d.done) {
+      if (!e) {
+        CMDR_CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        CMDR_CUDA_CHECK(cudaEventRecord(e, s));
+        events_.push_back(e);
+      }
+      d.ev = e;
+    }
+}
+
+void HostIO::drain() {
+  for (Drain &d : drains_) {
+    if (d.done) continue;
+    if (d.ev) CMDR_CUDA_CHECK(cudaEventSynchronize(d.ev));
+    else CMDR_CUDA_CHECK(cudaDeviceSynchronize());     // never committed: wait for everything
+    host_copy(d.dst, d.src, d.bytes);
+    d.done = true;
+  }
+  drains_.clear();
+  for (cudaEvent_t e : events_) cudaEventDestroy(e);
+  events_.clear();
+}
+
+}  // namespace cmdr

@@ -99,6 +99,35 @@ void sub_ranges(const sharp_geom_info *s, long long &nb, long long &ne, long lon
 bool is_pinned_host(const void *p);
 cudaStream_t copy_stream();
 cudaEvent_t pooled_event(size_t i);
+// host staging for pageable caller arrays (hostio.cu)
+enum class HostKind { Device, Pinned, Pageable };
+HostKind host_kind(const void *p);
+void *pinned_get(const char *name, size_t bytes);
+void pinned_release();
+void host_copy(void *dst, const void *src, size_t bytes);   // multi-threaded memcpy (blocking)
+int host_copy_threads();
+// The columns of one caller array (alm or map) as the pipelined paths move them: pinned columns are copied in
+// place; pageable columns go through the library's pinned arena (same offsets), uploads staged by the copy
+// threads before the H2D is queued, downloads landing in the arena and moved to the caller by drain().
+class HostIO {
+ public:
+  void init(const char *tag, double *const *cols, int ncols, long long count);
+  bool pageable() const { return pageable_; }
+  void h2d(double *dev, int c, long long ofs, long long n, cudaStream_t s);
+  void d2h(const double *dev, int c, long long ofs, long long n, cudaStream_t s);
+  void commit(cudaStream_t s);   // marks the downloads queued so far on `s` as one completion group
+  void drain();                  // waits for the groups in order and hands the data to the caller (call before returning)
+ private:
+  struct Drain { cudaEvent_t ev; double *dst; const double *src; size_t bytes; bool done = false; };
+  double *user_[4] = {};
+  double *stage_ = nullptr;
+  int ncols_ = 0;
+  long long count_ = 0;
+  bool pageable_ = false;
+  std::vector<Drain> drains_;
+  std::vector<cudaEvent_t> events_;
+};
+
 struct Staged {
   std::vector<double *> dev;
   std::vector<double *> host;

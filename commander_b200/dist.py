@@ -30,6 +30,12 @@ class Comm:
                                                C.c_void_p(torch.cuda.current_stream().cuda_stream))
         return t
 
+    def set_exchange(self, mode: int) -> None:
+        """Collective: 1 = phase exchange fused into the Legendre kernels (peer stores over NVLink), 0 = NCCL
+        all-to-all, -1 = automatic (cmdr_sht_comm_set_exchange)."""
+        if self.size > 1:
+            sharp.lib().cmdr_sht_comm_set_exchange(self.handle, int(mode))
+
 
 _next_handle = [1]
 

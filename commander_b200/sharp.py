@@ -33,7 +33,7 @@ ABI_SYMBOLS = [
     "sharp_map_size", "sharp_execute", "sharp_execute_mpi_fortran",
     # part 2: additive
     "cmdr_sht_version", "cmdr_sht_execute_dev", "cmdr_sht_execute_iqu", "cmdr_sht_execute_iqu_batch", "cmdr_sht_get_unique_id",
-    "cmdr_sht_comm_register", "cmdr_sht_comm_destroy", "cmdr_sht_execute_dist",
+    "cmdr_sht_comm_register", "cmdr_sht_comm_destroy", "cmdr_sht_comm_set_exchange", "cmdr_sht_execute_dist",
     "cmdr_sht_execute_iqu_dist", "cmdr_sht_mix", "cmdr_sht_invn_diag", "cmdr_sht_conviqt_cube", "cmdr_sht_allreduce_sum", "cmdr_sht_launch_count",
     "cmdr_sht_set_profiling", "cmdr_sht_last_legendre_ms", "cmdr_sht_nominal_flops",
     "cmdr_sht_release_caches", "cmdr_sht_measure_fp64_tflops", "cmdr_sht_measure_fp64_tflops_3op",
@@ -70,6 +70,7 @@ def lib() -> C.CDLL:
     L.cmdr_sht_comm_register.argtypes = [ci, ci, ci, vp]
     L.cmdr_sht_comm_register.restype = ci
     L.cmdr_sht_comm_destroy.argtypes = [ci]
+    L.cmdr_sht_comm_set_exchange.argtypes = [ci, ci]
     L.cmdr_sht_execute_dist.argtypes = [ci, ci, ci, vp, vp, vp, vp, ci, vp]
     L.cmdr_sht_execute_iqu_dist.argtypes = [ci, ci, vp, vp, vp, vp, vp, ci, vp]
     L.cmdr_sht_mix.argtypes = [ci, ci, vp, vp, vp, vp, vp, vp]

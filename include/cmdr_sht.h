@@ -11,6 +11,13 @@
  * All data is FP64.  There is no CPU fallback: every execute call runs CUDA
  * kernels on the current device and aborts with a message if that is impossible
  * (libsharp2 has no error channel either; it aborts on internal assertions).
+ *
+ * Threading: calls on one device must be serialised -- one calling thread and one
+ * in-flight stream per process (Commander calls sharp_execute from the single main
+ * thread of each MPI rank).  The work buffers (phases, FFT work area,
+ * staging, event pool) are per process and device, not per stream: two transforms
+ * enqueued concurrently on different streams of one device would share them.  One
+ * process drives one GPU.
  */
 #ifndef CMDR_SHT_H
 #define CMDR_SHT_H
@@ -80,8 +87,13 @@ void sharp_execute(int type, int spin, void *alm, void *map, const sharp_geom_in
 
 /* commander3/src/sharp.f90:96-104 (called at :227).  `comm` is an MPI_Fint.  This
  * library does not link MPI: the communicator is looked up in the table filled by
- * cmdr_sht_comm_register() (part 2); an unregistered comm of a 1-rank run falls
- * through to sharp_execute.  See INTEGRATION.md for the MPI bootstrap stub. */
+ * cmdr_sht_comm_register() (part 2) -- EVERY communicator that reaches this call must
+ * have been registered (comm_map passes info%comm, comm_conviqt its own self%comm,
+ * commander3/src/comm_conviqt_mod.f90:234-239).  An unknown communicator is accepted
+ * only when the handles cover the whole sphere (all 4 nside - 1 rings and all m: a
+ * group of one rank); otherwise the call aborts with a message instead of silently
+ * transforming local m's onto local rings.  `time` receives the wall seconds of the
+ * call in both modes.  See INTEGRATION.md for the MPI bootstrap stub. */
 void sharp_execute_mpi_fortran(int comm, int type, int spin, void *alm, void *map,
                                const sharp_geom_info *geom_info, const sharp_alm_info *alm_info,
                                int flags, double *time, unsigned long long *opcnt);
@@ -130,6 +142,17 @@ void cmdr_sht_get_unique_id(void *id128);
 int cmdr_sht_comm_register(int comm, int rank, int nranks, const void *id128);
 void cmdr_sht_comm_destroy(int comm);
 
+/* The communicator-less handle of the part-2 entry points below that take a `comm`: one GPU,
+ * no collective.  Any other value must be a registered communicator, or the handles must
+ * cover the whole sphere (same rule as sharp_execute_mpi_fortran). */
+#define CMDR_SHT_COMM_SELF (-1)
+
+/* Collective (every rank, same value).  How the m <-> ring transpose of later transforms on `comm`
+ * travels: 1 = fused into the Legendre kernels as peer stores / loads over NVLink (default where
+ * CUDA IPC works and nranks <= 8), 0 = NCCL all-to-all between a send and a receive buffer,
+ * -1 = back to the automatic choice ($CMDR_SHT_P2P).  For tests and benchmarks that compare the two. */
+void cmdr_sht_comm_set_exchange(int comm, int mode);
+
 /* Collective distributed transform on a registered comm.  geometry/alm handles
  * describe this rank's local rings and m's exactly as comm_mapinfo builds them.
  * Every rank must pass the same nside/lmax and the round-robin layout. */
@@ -147,7 +170,7 @@ void cmdr_sht_execute_iqu_dist(int comm, int type, double *const *alm3, double *
  * on the device; only alm (and F, if it lives on the host) cross PCIe.
  * nmaps = 1 (T, geom_P ignored) or 3 (I,Q,U); alm and F are arrays of nmaps pointers to
  * n_alm / n_pix doubles, host or device.  comm: a registered communicator (collective call,
- * layout as for sharp_execute_mpi_fortran) or any unregistered value for one GPU. */
+ * layout as for sharp_execute_mpi_fortran) or CMDR_SHT_COMM_SELF for one GPU. */
 void cmdr_sht_mix(int comm, int nmaps, double *const *alm, const double *const *F,
                   const sharp_geom_info *geom_T, const sharp_geom_info *geom_P,
                   const sharp_alm_info *alm_info, void *stream);
@@ -170,13 +193,15 @@ void cmdr_sht_invn_diag(int nmaps, const double *const *a_l0, double npix,
  * single-precision complex, entry (l,m) at complex index (l(l+1)/2 + m)*nmaps + c; cube: 2*bmax rows
  * of n_pix local pixels (c%a(pix, psi) in Fortran order), float when cube_f64 == 0 (the reference's
  * real(sp) cube, :281) or double.  All three may be host or device memory.  1 <= bmax <= 32.
- * comm: a registered communicator (collective) or any unregistered value for one GPU. */
+ * comm: a registered communicator (collective) or CMDR_SHT_COMM_SELF for one GPU. */
 void cmdr_sht_conviqt_cube(int comm, int nmaps, int bmax, const double *const *sky_alm, const float *beam,
                            const sharp_geom_info *geom_T, const sharp_alm_info *alm_info, void *cube,
                            int cube_f64, void *stream);
 
 /* NCCL sum-allreduce of n doubles (device pointer) on the comm: the collective
- * behind mpi_dot_product (commander3/src/comm_utils.f90:599-614). */
+ * behind mpi_dot_product (commander3/src/comm_utils.f90:599-614).  No-op for CMDR_SHT_COMM_SELF
+ * or a registered group of one; an unregistered communicator aborts (a silent no-op would leave
+ * every rank with its partial sum). */
 void cmdr_sht_allreduce_sum(int comm, double *dev_buf, int n, void *stream);
 
 /* ---- introspection for benchmarks/tests */

@@ -316,6 +316,60 @@ def test_full_size_properties(shtlib, nside, lmax):
     assert rt < 0.1, rt
 
 
+def _red_alm(rng, info, lmax):
+    """alm ~ N(0, C_l), C_l = 1 / (l (l + 1) + 1): a red spectrum exercises the dynamic range."""
+    l = info.lm[0].astype(np.float64)
+    a = rng.standard_normal((3, info.nalm)) / np.sqrt(l * (l + 1) + 1.0)
+    a[1:3, info.lm[0] < 2] = 0.0
+    return a
+
+
+@pytest.mark.parametrize("nside,lmax", [(1024, 2048), (1024, 2000), (2048, 4000), (512, 1500)])
+def test_full_size_vs_oracle(shtlib, cpu_oracle, nside, lmax):
+    """BASELINE.json configs[1] (1024 / 2048), [2]-size (1024 / 2000), [3] (2048 / 4000) and [4] (512 / 1500, one band)
+    compared IN FULL with the oracle: Y, WY, Yt, YtW for T (spin 0) and Q,U (spin 2) through comm_map on
+    ordinary numpy arrays -- pageable host memory, exactly what commander3/src/sharp.f90:219-224 passes (at these sizes
+    that is the chunked PCIe pipeline through the pinned arena).  WY and YtW are checked against the oracle's Y / Yt
+    with the ring weights applied in numpy (WY = diag(w) Y, YtW = Yt diag(w)), which halves the oracle time."""
+    from commander_b200 import comm_map, comm_mapinfo
+    S = cpu_oracle
+    rng = np.random.default_rng(3 + nside + lmax)
+    w = rng.uniform(0.9, 1.1, (2, 2 * nside))
+    info = comm_mapinfo(None, nside, lmax, 3, True, weights=w)
+    north = np.minimum(info.rings, 4 * nside - info.rings)
+    counts = np.where(north < nside, 4 * north, 4 * nside)
+    wpix = np.stack([np.repeat(4 * np.pi / (12 * nside ** 2) * w[k, north - 1], counts) for k in (0, 1, 1)])   # T, Q, U
+    m = comm_map(info)
+    alm0 = _red_alm(rng, info, lmax)
+    # ---- synthesis
+    refY = np.concatenate([S.execute(S.Y, 0, nside, lmax, alm=alm0[0:1]), S.execute(S.Y, 2, nside, lmax, alm=alm0[1:3])])
+    m.alm[:] = alm0
+    m.Y()
+    for c in range(3):
+        assert rel(m.map[c], refY[c]) <= TOL, ("Y", c, rel(m.map[c], refY[c]))
+    m.map[:] = np.nan
+    m.WY()
+    for c in range(3):
+        assert rel(m.map[c], wpix[c] * refY[c]) <= TOL, ("WY", c, rel(m.map[c], wpix[c] * refY[c]))
+    del refY
+    # ---- analysis
+    x = rng.standard_normal((3, info.np))
+    refA = np.concatenate([S.execute(S.Yt, 0, nside, lmax, map=x[0:1]), S.execute(S.Yt, 2, nside, lmax, map=x[1:3])])
+    m.map[:] = x
+    m.alm[:] = np.nan
+    m.Yt()
+    for c in range(3):
+        assert rel(m.alm[c], refA[c]) <= TOL, ("Yt", c, rel(m.alm[c], refA[c]))
+    xw = x * wpix
+    refA = np.concatenate([S.execute(S.Yt, 0, nside, lmax, map=xw[0:1]), S.execute(S.Yt, 2, nside, lmax, map=xw[1:3])])
+    m.map[:] = x
+    m.alm[:] = np.nan
+    m.YtW()
+    for c in range(3):
+        assert rel(m.alm[c], refA[c]) <= TOL, ("YtW", c, rel(m.alm[c], refA[c]))
+    info.dealloc()
+
+
 def test_full_size_m_column_vs_oracle(shtlib, cpu_oracle):
     """nside 2048 / lmax 4000: a_lm restricted to a few m (incl. the largest) against the oracle on
     every ring -- exercises the deep-underflow starts and the m cut-off at the target size."""

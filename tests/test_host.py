@@ -275,3 +275,42 @@ def test_blue_fft_register_blocked_variant_on_host(emul_fft, M):
     emul_fft.emul_conv2(buf.ctypes.data, vbr.ctypes.data, M, 33)
     conv = np.fft.ifft(np.fft.fft(x) * V) * M
     assert np.abs(buf[idx] - conv).max() <= 1e-11 * np.abs(conv).max()
+
+
+def test_add_alm_set_alm_loops(shtlib):
+    """add_alm / set_alm (commander3/src/comm_map_mod.f90:1167-1211) against the Fortran loops written out:
+    for i in info: (l,m) = info%i2lm(i); j = self%info%lm2i(l,m); skip j == -1; q <= min(nmaps)."""
+    from commander_b200 import comm_map, comm_mapinfo
+    rng = np.random.default_rng(17)
+    big = comm_mapinfo(None, 4, 11, 3, True)
+    small = comm_mapinfo(None, 4, 6, 1, False)
+    for self_info, other in ((big, small), (small, big)):
+        m = comm_map(self_info)
+        m.alm[:] = rng.standard_normal(m.alm.shape)
+        alm = rng.standard_normal((other.nmaps, other.nalm))
+        q = min(self_info.nmaps, other.nmaps)
+        want_add, want_set = m.alm.copy(), m.alm.copy()
+        for i in range(other.nalm):
+            l, mm = other.i2lm(i)
+            j = self_info.lm2i(l, mm)
+            if j == -1:
+                continue
+            want_add[:q, j] += alm[:q, i]
+            want_set[:q, j] = alm[:q, i]
+        a = comm_map(self_info); a.alm[:] = m.alm
+        a.add_alm(alm, other)
+        assert np.array_equal(a.alm, want_add)
+        s = comm_map(self_info); s.alm[:] = m.alm
+        s.set_alm(alm, other)
+        assert np.array_equal(s.alm, want_set)
+        # alm_equal, :1148-1165
+        o = comm_map(other)
+        o.alm[:] = 7.0
+        m.alm_equal(o)
+        want = np.zeros_like(o.alm)
+        for i in range(other.nalm):
+            l, mm = other.i2lm(i)
+            j = self_info.lm2i(l, mm)
+            if j != -1:
+                want[:q, i] = m.alm[:q, j]
+        assert np.array_equal(o.alm, want)
