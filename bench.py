@@ -149,6 +149,13 @@ def run_reference(args):
             ests.append(r["seconds_full_est"])
     mean_t = sum(ests) / len(ests)
     value = 1.0 / mean_t
+    cg = None
+    if not args.no_cg:
+        sec, nth = cpu_cg_sample(CG_NSIDE, CG_LMAX, 2)
+        cg = {"metric": "CR CG iters/sec", "value": 1.0 / sec, "unit": "iter/s", "ms_per_iter": 1e3 * sec, "cores": nth,
+              "sample": f"2 iterations of solve_cr_eqn_by_CG at nside={CG_NSIDE} lmax={CG_LMAX} IQU (1 band, CMB only, diagonal N^-1, "
+                        "10' beam): oracle/sht_cpu.c as SHT engine, numpy vector passes",
+              "kind": "port"}
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * mean_t, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -157,7 +164,7 @@ def run_reference(args):
                              "sample": "each step: " + cpu_sample_text(r, stride), "simd": r["simd"],
                              "note": "oracle/sht_cpu.c (OpenMP restatement of the libsharp2 algorithm); libsharp2 "
                                      "itself is not in /root/reference and cannot be built offline"},
-            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "cg": cg}
     print(json.dumps(line))
 
 
@@ -626,42 +633,111 @@ def run_conviqt_metric(dev, nside=512, lmax=1000, bmax=8):
             "psi_kernel_algorithmic_bytes": psi_bytes}
 
 
+CG_NSIDE, CG_LMAX, CG_ITERS = 1024, 2000, 50
+
+
+def _cg_inputs(nside, lmax):
+    import numpy as np
+    l = np.arange(lmax + 1, dtype=np.float64)
+    Cl = np.stack([1.0 / (l * (l + 1) + 1.0)] * 3, axis=1)
+    sigma0 = float(np.sqrt(Cl[min(1000, lmax // 2), 0] * 12 * nside ** 2 / (4 * np.pi)))
+    return Cl, sigma0
+
+
 def run_cg_metric(args, comm, dev, world):
-    """Second half of BASELINE.json's metric: CR CG iterations/s on configs[2] (nside 1024, lmax 2000,
-    IQU, diagonal N^-1 + Gaussian beam, CMB only), criterion fixed_iter as shipped
-    (parameter_files/param_BP8.1_v1.txt:40-47), all vectors device resident."""
+    """Second half of BASELINE.json's metric: CR CG iterations/s on configs[2] (nside 1024, lmax 2000, IQU, diagonal
+    N^-1 + Gaussian beam, CMB only), criterion fixed_iter with 50 iterations as shipped
+    (parameter_files/param_BP8.1_v1.txt:40-47), through the C ABI (cmdr_cr_solve): vectors device resident, sqrt(S) / beam /
+    N^-1 fused into the transform kernels, dot products reduced on the device, no host synchronisation in the loop."""
     import numpy as np
     import torch
     from commander_b200 import comm_mapinfo
-    from commander_b200.comm_cr import cr_cmb_system, gaussian_beam, solve_cr_eqn_by_CG
-    nside, lmax, iters = 1024, 2000, 10
+    from commander_b200.comm_cr import cr_cmb_system, cr_native_system, gaussian_beam, solve_cr_eqn_by_CG
+    nside, lmax, iters = CG_NSIDE, CG_LMAX, CG_ITERS
     info = comm_mapinfo(comm, nside, lmax, 3, True)
-    l = np.arange(lmax + 1, dtype=np.float64)
-    Cl = np.stack([1.0 / (l * (l + 1) + 1.0)] * 3, axis=1)
+    Cl, sigma0 = _cg_inputs(nside, lmax)
     g = torch.Generator(device=dev).manual_seed(5 + (comm.rank if comm else 0))
     pix = torch.as_tensor(info.pix, device=dev).double()
     z = 1.0 - 2.0 * (pix + 0.5) / (12 * nside ** 2)            # ~cos(theta) of the pixel in ring order
-    sigma0 = float(np.sqrt(Cl[1000, 0] * 12 * nside ** 2 / (4 * np.pi)))
     siN = (1.0 / (sigma0 * (1.0 + 0.5 * (1.0 - z * z)))).expand(3, -1).contiguous()
-    sysm = cr_cmb_system(info, siN, gaussian_beam(lmax, 10.0), Cl)
+    bl = gaussian_beam(lmax, 10.0)
+    sysn = cr_native_system(info, [siN * siN], [bl], Cl)
     data = torch.empty((3, info.np), dtype=torch.float64, device=dev).normal_(generator=g) / siN
-    b = sysm.computeRHS(data)
-    solve_cr_eqn_by_CG(sysm, b, maxiter=2, cg_conv_crit="fixed_iter")       # warm-up / plans
+    b = sysn.computeRHS([data])
+    sysn.solve(b, maxiter=2, cg_conv_crit="fixed_iter")       # warm-up / plans
     torch.cuda.synchronize()
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
-    ev[0].record()
-    x, it, hist = solve_cr_eqn_by_CG(sysm, b, maxiter=iters, cg_conv_crit="fixed_iter")
-    ev[1].record()
-    torch.cuda.synchronize()
-    ms = torch.tensor([ev[0].elapsed_time(ev[1])], dtype=torch.float64, device=dev)
     if world > 1:
         import torch.distributed as dist
+        dist.barrier()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    t0 = time.perf_counter()
+    ev[0].record()
+    x, it, hist = sysn.solve(b, maxiter=iters, cg_conv_crit="fixed_iter")
+    ev[1].record()
+    torch.cuda.synchronize()
+    wall = (time.perf_counter() - t0) * 1e3
+    ms = torch.tensor([max(ev[0].elapsed_time(ev[1]), wall)], dtype=torch.float64, device=dev)
+    if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms = float(ms.item())
-    return {"metric": "CR CG iters/sec", "value": (iters + 1) / (ms * 1e-3), "unit": "iter/s",
-            "config": f"nside={nside} lmax={lmax} IQU, 1 band, CMB only, diagonal N^-1, 10' Gaussian beam, diagonal preconditioner, "
-                      f"fixed_iter x{iters} (+1 initial A.x), device-resident vectors",
-            "ms_per_iter": ms / (iters + 1), "residual_drop": hist[-1] / hist[0]}
+    # the round-1 torch mirror of the same system (eager element-wise passes, two host syncs per iteration), for comparison
+    sysm = cr_cmb_system(info, siN, bl, Cl)
+    bm = sysm.computeRHS(data)
+    solve_cr_eqn_by_CG(sysm, bm, maxiter=2, cg_conv_crit="fixed_iter")
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    xm, itm, histm = solve_cr_eqn_by_CG(sysm, bm, maxiter=10, cg_conv_crit="fixed_iter")
+    torch.cuda.synchronize()
+    ms_m = torch.tensor([(time.perf_counter() - t0) * 1e3], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms_m, op=dist.ReduceOp.MAX)
+    agree = float(abs(hist[10] - histm[10]) / abs(histm[10]))
+    return {"metric": "CR CG iters/sec", "value": it / (ms * 1e-3), "unit": "iter/s",
+            "config": f"nside={nside} lmax={lmax} IQU, 1 band, CMB only, diagonal N^-1, 10' Gaussian beam, diagonal preconditioner "
+                      f"(full N_lm), fixed_iter x{iters} (x0 = 0: one A application per iteration), cmdr_cr_solve through the C ABI",
+            "ms_per_iter": ms / it, "iterations": it, "residual_drop": hist[-1] / hist[0],
+            "torch_mirror_iters_per_s": 11.0 / (float(ms_m.item()) * 1e-3),
+            "native_vs_mirror_residual_after_10_iterations_rel": agree}
+
+
+def cpu_cg_sample(nside, lmax, iters, nthreads=0):
+    """The reference's CG iteration on the host cores: cr_matmulA (commander3/src/comm_cr_mod.f90:771-1024) with the CPU
+    restatement as SHT engine and numpy for the vector passes, `iters` iterations of solve_cr_eqn_by_CG (:201-348).
+    Returns seconds per iteration (what the reference prints at :326-335)."""
+    import numpy as np
+    from oracle import sht_cpu as S
+    S.build()
+    if nthreads == 0:
+        nthreads = len(os.sched_getaffinity(0))
+    Cl, sigma0 = _cg_inputs(nside, lmax)
+    npix = 12 * nside * nside
+    z = 1.0 - 2.0 * (np.arange(npix) + 0.5) / npix
+    invN = np.stack([(1.0 / (sigma0 * (1.0 + 0.5 * (1.0 - z * z)))) ** 2] * 3)
+    sigma = 10.0 * np.pi / 180.0 / 60.0 / np.sqrt(8.0 * np.log(2.0))
+    lo = np.concatenate([np.repeat(np.arange(m, lmax + 1), 1 if m == 0 else 2) for m in range(lmax + 1)])
+    blT = np.exp(-0.5 * lo * (lo + 1.0) * sigma ** 2)
+    f = np.stack([blT, blT * np.exp(2 * sigma ** 2), blT * np.exp(2 * sigma ** 2)]) * np.sqrt(1.0 / (lo * (lo + 1.0) + 1.0))
+    f[1:, lo < 2] = 0.0
+
+    def A(v):
+        w = f * v
+        mp = np.concatenate([S.execute(S.Y, 0, nside, lmax, alm=w[0:1], nthreads=nthreads, mlim_skip=True),
+                             S.execute(S.Y, 2, nside, lmax, alm=w[1:3], nthreads=nthreads, mlim_skip=True)])
+        mp *= invN
+        a = np.concatenate([S.execute(S.Yt, 0, nside, lmax, map=mp[0:1], nthreads=nthreads, mlim_skip=True),
+                            S.execute(S.Yt, 2, nside, lmax, map=mp[1:3], nthreads=nthreads, mlim_skip=True)])
+        return v + f * a
+    rng = np.random.default_rng(5)
+    b = rng.standard_normal(f.shape)
+    Minv = 1.0 / (1.0 + f * f * float(invN.mean()) * npix / (4 * np.pi))
+    A(b)                                                      # warm-up: FFT plans, page faults
+    x = np.zeros_like(b); r = b.copy(); d = Minv * r
+    dn = float(np.sum(r * d))
+    t0 = time.perf_counter()
+    for _ in range(iters):
+        q = A(d); alpha = dn / float(np.sum(d * q)); x += alpha * d; r -= alpha * q
+        s = Minv * r; do = dn; dn = float(np.sum(r * s)); d = s + dn / do * d
+    return (time.perf_counter() - t0) / iters, nthreads
 
 
 def main():

@@ -463,3 +463,124 @@ def _view_maps(m: comm_map, info: comm_mapinfo, nm: int) -> comm_map:
     v.info, v.device = info, m.device
     v.alm, v.map = m.alm[:nm], m.map[:nm]
     return v
+
+
+# =====================================================================================================
+# The same CMB system behind the C ABI (cmdr_cr_*, commander_b200/csrc/cr.cu): no torch in the operator, the
+# sqrt(S) / beam / N^-1 passes fused into the transform kernels, dot products reduced on the device.
+# =====================================================================================================
+
+def _ptrs(arrs):
+    """Array of column pointers over a list of 1-D views (numpy or torch); returns (ctypes array, keep-alive)."""
+    import ctypes as C
+    p = (C.c_void_p * len(arrs))()
+    for i, a in enumerate(arrs):
+        if isinstance(a, np.ndarray):
+            if a.dtype != np.float64 or not a.flags.c_contiguous:
+                raise ValueError("expected contiguous float64 columns")
+            p[i] = a.ctypes.data
+        else:
+            import torch
+            if a.dtype != torch.float64 or not a.is_contiguous():
+                raise ValueError("expected contiguous float64 columns")
+            p[i] = a.data_ptr()
+    return p, arrs
+
+
+class cr_native_system:
+    """One signal component with a diagonal prior C_l (or none) seen through `nbands` bands that share `info`:
+    handle of cmdr_cr_setup.  invN: list (per band) of (nmaps, np) arrays, numpy or torch; b_l: list (per band) of
+    (lmax+1, nmaps) beams (times mb_eff and F_mean); Cl: (lmax+1, nmaps) or None; precond 'diagonal' | 'none'."""
+
+    def __init__(self, info: comm_mapinfo, invN, b_l, Cl=None, precond: str = "diagonal"):
+        from . import sharp
+        self.info = info
+        self.nbands, self.nmaps = len(invN), info.nmaps
+        if len(b_l) != self.nbands:
+            raise ValueError("one beam per band")
+        if precond not in ("diagonal", "none"):
+            raise ValueError("Preconditioner type not supported: " + precond)
+        nm = self.nmaps
+        icols = [invN[b][c] for b in range(self.nbands) for c in range(nm)]
+        self._bl = [np.ascontiguousarray(np.asarray(b_l[b], dtype=np.float64)[:, c]) for b in range(self.nbands) for c in range(nm)]
+        self._sS = None
+        if Cl is not None:
+            self._sS = [np.ascontiguousarray(np.sqrt(np.maximum(np.asarray(Cl, dtype=np.float64)[:, c], 0.0))) for c in range(nm)]
+        ip, _k1 = _ptrs(icols)
+        bp, _k2 = _ptrs(self._bl)
+        sp = None
+        if self._sS is not None:
+            sp, _k3 = _ptrs(self._sS)
+        c = info.comm
+        comm = c.handle if (info.dist and c.size > 1) else -1
+        gp = info.geom_info_P.handle if info.geom_info_P is not None else None
+        self.handle = sharp.lib().cmdr_cr_setup(comm, self.nbands, nm, info.geom_info_T.handle, gp, info.alm_info.handle,
+                                                ip, bp, sp, 1 if precond == "diagonal" else 0)
+        self.L = sharp.lib()
+
+    def __del__(self):
+        if getattr(self, "handle", None):
+            self.L.cmdr_cr_destroy(self.handle)
+            self.handle = None
+
+    def _like(self, v):
+        if isinstance(v, np.ndarray):
+            return np.empty((self.nmaps, self.info.nalm))
+        import torch
+        return torch.empty((self.nmaps, self.info.nalm), dtype=torch.float64, device=v.device)
+
+    @property
+    def n_matmul(self):
+        return int(self.L.cmdr_cr_matmul_count(self.handle))
+
+    def matmulA(self, x):
+        """cr_matmulA, commander3/src/comm_cr_mod.f90:771-1024"""
+        y = self._like(x)
+        xp, _a = _ptrs([x[c] for c in range(self.nmaps)])
+        yp, _b = _ptrs([y[c] for c in range(self.nmaps)])
+        self.L.cmdr_cr_matmulA(self.handle, xp, yp, None)
+        return y
+
+    def invM(self, r):
+        """cr_invM, commander3/src/comm_cr_mod.f90:1026-1077 (diagonal)"""
+        z = self._like(r)
+        rp, _a = _ptrs([r[c] for c in range(self.nmaps)])
+        zp, _b = _ptrs([z[c] for c in range(self.nmaps)])
+        self.L.cmdr_cr_invM(self.handle, rp, zp, None)
+        return z
+
+    def Minv(self):
+        out = np.empty((self.nmaps, self.info.nalm))
+        op, _a = _ptrs([out[c] for c in range(self.nmaps)])
+        self.L.cmdr_cr_get_precond_diag(self.handle, op)
+        return out
+
+    def computeRHS(self, data, eta_pix=None, eta_alm=None):
+        """cr_computeRHS, commander3/src/comm_cr_mod.f90:542-769; data / eta_pix: lists (per band) of (nmaps, np) arrays."""
+        nm = self.nmaps
+        b = self._like(data[0])
+        dp, _a = _ptrs([data[q][c] for q in range(self.nbands) for c in range(nm)])
+        ep = None
+        if eta_pix is not None:
+            ep, _b = _ptrs([eta_pix[q][c] for q in range(self.nbands) for c in range(nm)])
+        ap = None
+        if eta_alm is not None:
+            ap, _c = _ptrs([eta_alm[c] for c in range(nm)])
+        bp, _d = _ptrs([b[c] for c in range(nm)])
+        self.L.cmdr_cr_compute_rhs(self.handle, dp, ep, ap, bp, None)
+        return b
+
+    def solve(self, b, x0=None, maxiter=300, cg_tol=1e-8, cg_conv_crit="residual", cg_miniter=5, cg_check_conv_freq=1):
+        """solve_cr_eqn_by_CG, commander3/src/comm_cr_mod.f90:201-348.  Returns (x, iterations done, residual history)."""
+        import ctypes as C
+        if cg_conv_crit not in ("residual", "fixed_iter"):
+            raise ValueError("Unsupported convergence criterion = " + cg_conv_crit)
+        x = self._like(b)
+        if x0 is not None:
+            x[...] = x0
+        bp, _a = _ptrs([b[c] for c in range(self.nmaps)])
+        xp, _b = _ptrs([x[c] for c in range(self.nmaps)])
+        hist = (C.c_double * (maxiter + 1))()
+        it = self.L.cmdr_cr_solve(self.handle, bp, xp, 1 if x0 is not None else 0, int(maxiter), float(cg_tol),
+                                  0 if cg_conv_crit == "residual" else 1, int(cg_miniter), int(cg_check_conv_freq), hist, None)
+        return x, int(it), [float(hist[i]) for i in range(it + 1)]

@@ -418,8 +418,8 @@ LegAlm make_legalm(sharp_alm_info *a, int spin) {
 
 // Single-GPU transform with device pointers.  `ph` holds ncomp_tot components; this call
 // handles components [comp0, comp0+ncomp) of it.
-static void run_single(int type, int spin, double *const *alm, double *const *map, sharp_geom_info *g,
-                       sharp_alm_info *a, int flags, cudaStream_t st) {
+void run_single(int type, int spin, double *const *alm, double *const *map, sharp_geom_info *g,
+                sharp_alm_info *a, int flags, cudaStream_t st, const XformOpts *opts, int comp_off) {
   if (spin < 0 || spin > CMDR_MAX_SPIN) { fprintf(stderr, "cmdr_sht: spin %d unsupported (0..%d)\n", spin, CMDR_MAX_SPIN); abort(); }
   if (type < 0 || type > 3) { fprintf(stderr, "cmdr_sht: job type %d unsupported\n", type); abort(); }
   if (flags & SHARP_NO_FFT) { fprintf(stderr, "cmdr_sht: SHARP_NO_FFT unsupported\n"); abort(); }
@@ -428,6 +428,9 @@ static void run_single(int type, int spin, double *const *alm, double *const *ma
   const bool add = (flags & SHARP_ADD) != 0;
   ensure_geom_device(g);
   LegAlm A = make_legalm(a, spin);
+  const double *pixscale[2] = {nullptr, nullptr};
+  if (opts)
+    for (int c = 0; c < ncomp; ++c) { A.lscale[c] = opts->lscale[comp_off + c]; pixscale[c] = opts->pixscale[comp_off + c]; }
   if (g->npairs == 0 || a->nm == 0) {
     if (!add) {
       if (synth) { for (int c = 0; c < ncomp; ++c) if (g->npix) CMDR_CUDA_CHECK(cudaMemsetAsync(map[c], 0, sizeof(double) * g->npix, st)); }
@@ -445,7 +448,7 @@ static void run_single(int type, int spin, double *const *alm, double *const *ma
     launch_legendre_synth(spin, G, A, alm, ph, st);
     prof_end(st);
     prof_begin(100 + spin, 0, st);
-    ringfft_synth(g, ncomp, L, ph, map, type == SHARP_WY, add, st);
+    ringfft_synth(g, ncomp, L, ph, map, type == SHARP_WY, add, st, opts ? pixscale : nullptr);
     prof_end(st);
   } else {
     prof_begin(100 + spin, 1, st);
@@ -738,9 +741,9 @@ static bool try_pipelined(int type, int spin, double *const *alm, double *const 
     for (int j = 0; j < nmch && nj > 0; ++j) {
       cudaStream_t sj = (j & 1) ? as : st;
       LegAlm Aj = A;
-      Aj.im_begin = mcut[j]; Aj.im_end = mcut[j + 1];
+      if (nmch > 1) { Aj.im_begin = mcut[j]; Aj.im_end = mcut[j + 1]; }    // (mcut is empty when the m's are not chunkable)
       G.slot_begin = g->subs[ns - nj]->pair0; G.slot_end = g->subs[ns - 1]->pair0 + g->subs[ns - 1]->npairs;
-      launch_legendre_anal(spin, G, nmch > 1 ? Aj : A, alm_dev, ph, sj);   // merged slot range of the last nj chunks
+      launch_legendre_anal(spin, G, Aj, alm_dev, ph, sj);   // merged slot range of the last nj chunks
       if (nmch > 1) {
         cudaEvent_t e = pooled_event(ns + 2 + j);
         CMDR_CUDA_CHECK(cudaEventRecord(e, sj));

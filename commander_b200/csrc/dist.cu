@@ -371,7 +371,11 @@ static void alltoall_blocks(DistComm *C, const double *send, double *recv, size_
   count_launch(1);
 }
 
-struct Part { int spin, comp0, ncomp; sharp_geom_info *g; double *const *alm; double *const *map; };
+struct Part {
+  int spin, comp0, ncomp; sharp_geom_info *g; double *const *alm; double *const *map;
+  const double *lscale[2] = {nullptr, nullptr}, *pixscale[2] = {nullptr, nullptr};   // fused factors (XformOpts)
+  bool has_ps() const { return pixscale[0] || pixscale[1]; }
+};
 
 // Distributed transform over `parts` (one part = one spin with its geometry); all parts
 // share one phase buffer of ncomp_tot components and one exchange.
@@ -410,6 +414,7 @@ static void run_dist(DistComm *C, int type, const Part *parts, int nparts, int n
     for (int i = 0; i < nparts; ++i) {
       const Part &p = parts[i];
       LegAlm A = make_legalm(a, p.spin);
+      A.lscale[0] = p.lscale[0]; A.lscale[1] = p.lscale[1];
       G.comp0 = p.comp0; G.mlim = plan_mlim(P, a->lmax, p.spin);
       prof_begin(p.spin, 0, st);
       launch_legendre_synth(p.spin, G, A, p.alm, reinterpret_cast<double4 *>(B.mine), st);
@@ -423,7 +428,8 @@ static void run_dist(DistComm *C, int type, const Part *parts, int nparts, int n
       L.comp0 = p.comp0;
       if (p.g->npairs == 0) continue;
       prof_begin(100 + p.spin, 0, st);
-      ringfft_synth(p.g, p.ncomp, L, reinterpret_cast<double4 *>(B.mine), p.map, type == SHARP_WY, add, st);
+      ringfft_synth(p.g, p.ncomp, L, reinterpret_cast<double4 *>(B.mine), p.map, type == SHARP_WY, add, st,
+                    p.has_ps() ? p.pixscale : nullptr);
       prof_end(st);
     }
     return;
@@ -451,6 +457,7 @@ static void run_dist(DistComm *C, int type, const Part *parts, int nparts, int n
     for (int i = 0; i < nparts; ++i) {
       const Part &p = parts[i];
       LegAlm A = make_legalm(a, p.spin);
+      A.lscale[0] = p.lscale[0]; A.lscale[1] = p.lscale[1];
       G.comp0 = p.comp0; G.mlim = plan_mlim(P, a->lmax, p.spin);
       const size_t nd = (size_t)a->nalm * (a->real_packed ? 1 : 2);
       if (!add && nd)
@@ -470,6 +477,7 @@ static void run_dist(DistComm *C, int type, const Part *parts, int nparts, int n
     for (int i = 0; i < nparts; ++i) {
       const Part &p = parts[i];
       LegAlm A = make_legalm(a, p.spin);
+      A.lscale[0] = p.lscale[0]; A.lscale[1] = p.lscale[1];
       G.comp0 = p.comp0; G.mlim = plan_mlim(P, a->lmax, p.spin);
       prof_begin(p.spin, 0, st);
       launch_legendre_synth(p.spin, G, A, p.alm, reinterpret_cast<double4 *>(bufA), st);
@@ -483,7 +491,8 @@ static void run_dist(DistComm *C, int type, const Part *parts, int nparts, int n
       L.comp0 = p.comp0;
       if (p.g->npairs == 0) continue;
       prof_begin(100 + p.spin, 0, st);
-      ringfft_synth(p.g, p.ncomp, L, reinterpret_cast<double4 *>(bufB), p.map, type == SHARP_WY, add, st);
+      ringfft_synth(p.g, p.ncomp, L, reinterpret_cast<double4 *>(bufB), p.map, type == SHARP_WY, add, st,
+                    p.has_ps() ? p.pixscale : nullptr);
       prof_end(st);
     }
   } else {
@@ -502,6 +511,7 @@ static void run_dist(DistComm *C, int type, const Part *parts, int nparts, int n
     for (int i = 0; i < nparts; ++i) {
       const Part &p = parts[i];
       LegAlm A = make_legalm(a, p.spin);
+      A.lscale[0] = p.lscale[0]; A.lscale[1] = p.lscale[1];
       G.comp0 = p.comp0; G.mlim = plan_mlim(P, a->lmax, p.spin);
       const size_t nd = (size_t)a->nalm * (a->real_packed ? 1 : 2);
       if (!add && nd)
@@ -638,13 +648,13 @@ static bool try_dist_pipelined(DistComm *C, int type, int spin, double *const *a
 
 static void execute_dist_any(DistComm *C, int type, int nparts, const int *spins, double *const *alm,
                              double *const *map, sharp_geom_info *const *geoms, sharp_alm_info *a, int flags,
-                             cudaStream_t st) {
+                             cudaStream_t st, const XformOpts *opts = nullptr) {
   const bool synth = (type == SHARP_Y || type == SHARP_WY);
   const bool add = (flags & SHARP_ADD) != 0;
   int ncomp_tot = 0;
   for (int i = 0; i < nparts; ++i) ncomp_tot += spins[i] == 0 ? 1 : 2;
   const long long nalm_d = a->nalm * (a->real_packed ? 1 : 2);
-  if (nparts == 1 && try_dist_pipelined(C, type, spins[0], alm, map, geoms[0], a, flags, st)) return;
+  if (nparts == 1 && !opts && try_dist_pipelined(C, type, spins[0], alm, map, geoms[0], a, flags, st)) return;
   Staged sa = stage_in("stage_alm", alm, ncomp_tot, nalm_d, synth || add, st);
   Staged sm = stage_in("stage_map", map, ncomp_tot, geoms[0]->npix, !synth || add, st);
   Part parts[4];
@@ -653,11 +663,34 @@ static void execute_dist_any(DistComm *C, int type, int nparts, const int *spins
     int nc = spins[i] == 0 ? 1 : 2;
     if (spins[i] < 0 || spins[i] > CMDR_MAX_SPIN) { fprintf(stderr, "cmdr_sht: spin %d unsupported\n", spins[i]); abort(); }
     parts[i] = Part{spins[i], c0, nc, geoms[i], sa.dev.data() + c0, sm.dev.data() + c0};
+    if (opts)
+      for (int c = 0; c < nc; ++c) { parts[i].lscale[c] = opts->lscale[c0 + c]; parts[i].pixscale[c] = opts->pixscale[c0 + c]; }
     c0 += nc;
   }
   run_dist(C, type, parts, nparts, ncomp_tot, a, flags, st);
   if (synth) stage_out(sm, geoms[0]->npix, st); else stage_out(sa, nalm_d, st);
   if (sa.staged || sm.staged) CMDR_CUDA_CHECK(cudaStreamSynchronize(st));
+}
+
+// the communicator a component should keep using: `comm` when it is a registered group of several ranks, else
+// CMDR_COMM_SELF (aborts for an unknown communicator whose handles hold only part of the sphere)
+int effective_comm(int comm, const sharp_geom_info *g, const sharp_alm_info *a, const char *who) {
+  return comm_or_local(comm, g, a, who) ? comm : CMDR_COMM_SELF;
+}
+
+// T (nmaps = 1) or IQU (nmaps = 3) transform on device pointers with fused factors, on one GPU or collectively
+// on a registered communicator (cr.cu)
+void execute_iqu_opts(int comm, int type, int nmaps, double *const *alm, double *const *map, sharp_geom_info *gT,
+                      sharp_geom_info *gP, sharp_alm_info *a, int flags, const XformOpts *opts, cudaStream_t st) {
+  DistComm *C = comm_or_local(comm, gT, a, "cmdr_cr");
+  if (!C) {
+    run_single(type, 0, alm, map, gT, a, flags, st, opts, 0);
+    if (nmaps == 3) run_single(type, 2, alm + 1, map + 1, gP, a, flags, st, opts, 1);
+    return;
+  }
+  int spins[2] = {0, 2};
+  sharp_geom_info *gs[2] = {gT, gP};
+  execute_dist_any(C, type, nmaps == 3 ? 2 : 1, spins, alm, map, gs, a, flags, st, opts);
 }
 
 // map *= F, the pixel-space mixing step between Y and YtW (HBM-bound: 24 bytes per pixel)

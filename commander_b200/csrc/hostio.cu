@@ -14,6 +14,7 @@
 //
 // Pinned caller buffers (cudaMallocHost / cudaHostRegister done by the application) bypass the arena.
 #include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <cstring>
 #include <map>
@@ -30,16 +31,18 @@ struct PinnedBuf { void *ptr = nullptr; size_t bytes = 0; };
 static std::map<std::string, PinnedBuf> g_pinned;
 static std::mutex g_pin_mu;
 
-void *pinned_get(const char *name, size_t bytes) {
+void *pinned_get(const char *name, size_t bytes, bool write_combined) {
   int dev = 0;
   CMDR_CUDA_CHECK(cudaGetDevice(&dev));
-  std::string key = std::string(name) + "@" + std::to_string(dev);
+  std::string key = std::string(name) + (write_combined ? "/wc@" : "@") + std::to_string(dev);
   std::lock_guard<std::mutex> lk(g_pin_mu);
   PinnedBuf &b = g_pinned[key];
   if (b.bytes < bytes) {
     if (b.ptr) { CMDR_CUDA_CHECK(cudaDeviceSynchronize()); CMDR_CUDA_CHECK(cudaFreeHost(b.ptr)); }
     size_t want = bytes + bytes / 16 + 4096;
-    CMDR_CUDA_CHECK(cudaHostAlloc(&b.ptr, want, cudaHostAllocDefault));
+    // upload staging is written by the CPU and read by the DMA engine only: write-combined pages keep it out of the
+    // CPU caches (the copy threads use streaming stores anyway) and move faster over PCIe
+    CMDR_CUDA_CHECK(cudaHostAlloc(&b.ptr, want, write_combined ? cudaHostAllocWriteCombined : cudaHostAllocDefault));
     b.bytes = want;
   }
   return b.ptr;
@@ -112,11 +115,11 @@ static CopyPool *copy_pool() {
     int n = 0;
     if (const char *e = getenv("CMDR_SHT_COPY_THREADS")) n = atoi(e);
     if (n <= 0) {
-      // the threads this process may run on (respects taskset / cgroup / mpirun binding), at most 8
+      // the threads this process may run on (respects taskset / cgroup / mpirun binding), at most 16
       cpu_set_t set;
       int avail = (sched_getaffinity(0, sizeof(set), &set) == 0) ? CPU_COUNT(&set) : (int)std::thread::hardware_concurrency();
-      n = avail / 2;
-      if (n > 8) n = 8;
+      n = avail - 1;                               // leave one for the thread that drives the streams
+      if (n > 16) n = 16;
       if (n < 1) n = 1;
     }
     return new CopyPool(n - 1);                     // leaked on purpose: detached workers, no exit-order hazards
@@ -142,14 +145,25 @@ void HostIO::init(const char *tag, double *const *cols, int ncols, long long cou
   ncols_ = ncols; count_ = count;
   pageable_ = false;
   for (int c = 0; c < ncols; ++c) { user_[c] = cols[c]; pageable_ = pageable_ || host_kind(cols[c]) == HostKind::Pageable; }
-  stage_ = pageable_ ? static_cast<double *>(pinned_get(tag, sizeof(double) * (size_t)count * ncols)) : nullptr;
+  stage_ = stage_up_ = nullptr;                    // allocated on first use: a transform uploads one array and downloads the other
+  tag_ = tag;
+}
+
+double *HostIO::stage_dn() {
+  if (!stage_) stage_ = static_cast<double *>(pinned_get(tag_, sizeof(double) * (size_t)count_ * ncols_, false));
+  return stage_;
+}
+double *HostIO::stage_up() {
+  static const bool wc = !(getenv("CMDR_SHT_STAGE_WC") && atoi(getenv("CMDR_SHT_STAGE_WC")) == 0);
+  if (!stage_up_) stage_up_ = static_cast<double *>(pinned_get(tag_, sizeof(double) * (size_t)count_ * ncols_, wc));
+  return stage_up_;
 }
 
 void HostIO::h2d(double *dev, int c, long long ofs, long long n, cudaStream_t s) {
   if (n <= 0) return;
   const double *src = user_[c] + ofs;
   if (pageable_) {
-    double *sp = stage_ + (size_t)c * count_ + ofs;
+    double *sp = stage_up() + (size_t)c * count_ + ofs;
     host_copy(sp, src, sizeof(double) * (size_t)n);
     src = sp;
   }
@@ -160,7 +174,7 @@ void HostIO::d2h(const double *dev, int c, long long ofs, long long n, cudaStrea
   if (n <= 0) return;
   double *dst = user_[c] + ofs;
   if (pageable_) {
-    double *sp = stage_ + (size_t)c * count_ + ofs;
+    double *sp = stage_dn() + (size_t)c * count_ + ofs;
     CMDR_CUDA_CHECK(cudaMemcpyAsync(sp, dev, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, s));
     drains_.push_back(Drain{nullptr, dst, sp, sizeof(double) * (size_t)n});
     return;
@@ -196,3 +210,25 @@ void HostIO::drain() {
 }
 
 }  // namespace cmdr
+
+// Throughput of the copy-thread pool, GB/s of payload (best of `reps`): pageable -> pinned arena (direction 0, the
+// upload staging: write-combined when wc != 0) or pinned arena -> pageable (direction 1).  Diagnostic for bench.py.
+extern "C" double cmdr_sht_measure_host_copy(size_t bytes, int direction, int wc, int reps) {
+  using namespace cmdr;
+  void *pin = nullptr;
+  CMDR_CUDA_CHECK(cudaHostAlloc(&pin, bytes, (wc && direction == 0) ? cudaHostAllocWriteCombined : cudaHostAllocDefault));
+  char *pg = static_cast<char *>(malloc(bytes));
+  memset(pg, 1, bytes);
+  memset(pin, 2, bytes);
+  double best = 0.0;
+  for (int r = 0; r < reps; ++r) {
+    auto t0 = std::chrono::steady_clock::now();
+    if (direction == 0) host_copy(pin, pg, bytes); else host_copy(pg, pin, bytes);
+    double s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    if (bytes / s / 1e9 > best) best = bytes / s / 1e9;
+  }
+  free(pg);
+  cudaFreeHost(pin);
+  return best;
+}
+extern "C" int cmdr_sht_host_copy_threads(void) { return cmdr::host_copy_threads(); }

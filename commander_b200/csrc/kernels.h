@@ -48,6 +48,17 @@ struct LegAlm {
   const double *Kstart = nullptr;  // start-value normalisation of this spin, indexed by m
   const long long *tofs = nullptr; // first synthesis tile row of each local m (rows padded to 8 per m)
   long long trows = 0;             // total tile rows
+  // optional factor per l for each component of this spin (device, lmax+1 entries; nullptr = 1): applied to the
+  // a_lm on load (synthesis) and on store (analysis) -- how cr_matmulA's sqrt(S), beam and F_mean passes
+  // (commander3/src/comm_cr_mod.f90:797-836, 957-1008; comm_B_bl_mod.f90:108-127) ride in the Legendre kernels
+  const double *lscale[2] = {nullptr, nullptr};
+};
+
+// Optional element-wise factors fused into a transform (cr.cu): per l on the a_lm side, per local pixel on the map
+// side of a synthesis (N^-1 of commander3/src/comm_N_rms_mod.f90:264-273 in the ring-FFT epilogue).
+struct XformOpts {
+  const double *lscale[3] = {nullptr, nullptr, nullptr};
+  const double *pixscale[3] = {nullptr, nullptr, nullptr};
 };
 
 // Phase buffer element: {north re, north im, south re, south im}.
@@ -77,7 +88,8 @@ struct PhaseLayout {
 };
 
 void ringfft_synth(sharp_geom_info *geom, int ncomp, const PhaseLayout &L, const double4 *ph,
-                   double *const *map, bool weighted, bool add, cudaStream_t st);
+                   double *const *map, bool weighted, bool add, cudaStream_t st,
+                   const double *const *pixscale = nullptr);
 void ringfft_anal(sharp_geom_info *geom, int ncomp, const PhaseLayout &L, double4 *ph,
                   const double *const *map, bool weighted, cudaStream_t st);
 
@@ -102,7 +114,7 @@ cudaEvent_t pooled_event(size_t i);
 // host staging for pageable caller arrays (hostio.cu)
 enum class HostKind { Device, Pinned, Pageable };
 HostKind host_kind(const void *p);
-void *pinned_get(const char *name, size_t bytes);
+void *pinned_get(const char *name, size_t bytes, bool write_combined = false);
 void pinned_release();
 void host_copy(void *dst, const void *src, size_t bytes);   // multi-threaded memcpy (blocking)
 int host_copy_threads();
@@ -119,8 +131,11 @@ class HostIO {
   void drain();                  // waits for the groups in order and hands the data to the caller (call before returning)
  private:
   struct Drain { cudaEvent_t ev; double *dst; const double *src; size_t bytes; bool done = false; };
+  double *stage_dn();
+  double *stage_up();
   double *user_[4] = {};
-  double *stage_ = nullptr;
+  double *stage_ = nullptr, *stage_up_ = nullptr;
+  const char *tag_ = "";
   int ncols_ = 0;
   long long count_ = 0;
   bool pageable_ = false;
@@ -137,6 +152,12 @@ Staged stage_in(const char *tag, double *const *ptrs, int n, long long count, bo
 void stage_out(Staged &s, long long count, cudaStream_t st);
 void execute_any(int type, int spin, void *alm_v, void *map_v, sharp_geom_info *g, sharp_alm_info *a,
                  int flags, double *time, unsigned long long *opcnt, cudaStream_t st);
+// device-pointer transforms with fused factors (single GPU: abi.cu; any registered comm: dist.cu)
+void run_single(int type, int spin, double *const *alm, double *const *map, sharp_geom_info *g,
+                sharp_alm_info *a, int flags, cudaStream_t st, const XformOpts *opts = nullptr, int comp_off = 0);
+int effective_comm(int comm, const sharp_geom_info *g, const sharp_alm_info *a, const char *who);
+void execute_iqu_opts(int comm, int type, int nmaps, double *const *alm, double *const *map, sharp_geom_info *gT,
+                      sharp_geom_info *gP, sharp_alm_info *a, int flags, const XformOpts *opts, cudaStream_t st);
 
 }  // namespace cmdr
 

@@ -49,6 +49,7 @@ struct KParams {
   const int *mlim;
   const int *wslot;                  // work index -> storage slot (nullptr: identity)
   double *alm0, *alm1;
+  const double *lscale0, *lscale1;   // optional factor per l on component 0 / 1 (nullptr: 1)
   double4 *ph;
   int src_rank;                      // fused exchange: block of this rank in the ring owners' buffers (-1: local buffer, block = owner)
   double4 *peer[CMDR_MAX_PEERS];     // phase buffer of each ring owner (all = ph without the fused exchange)
@@ -130,6 +131,7 @@ __global__ void __launch_bounds__(256) prep_s0_kernel(KParams p) {
     const double nrm = (p.real_packed && m > 0) ? 0.70710678118654752440 : 1.0;
     double2 c = reinterpret_cast<const double2 *>(coef)[l - m];   // {A', g}
     double gs = c.y * nrm;
+    if (p.lscale0) gs *= p.lscale0[l];
     e.A = c.x;
     if (p.real_packed) {
       if (m == 0) { e.ar = gs * a[mvs + l]; }
@@ -272,6 +274,8 @@ __global__ void __launch_bounds__(256) prep_s2_kernel(KParams p) {
       er = aE[2 * (mvs + l)]; br = aB[2 * (mvs + l)];
       if (m > 0) { ei = aE[2 * (mvs + l) + 1]; bi = aB[2 * (mvs + l) + 1]; }
     }
+    if (p.lscale0) { const double f = p.lscale0[l]; er *= f; ei *= f; }
+    if (p.lscale1) { const double f = p.lscale1[l]; br *= f; bi *= f; }
     // (+s)a = spinsign (E + iB), (-s)a = spinsign (-1)^s (E - iB) = -(E - iB); spinsign = -1 for even s
     const double sgs = p.spinsign * gs;
     e.cpr = sgs * (er - bi); e.cpi = sgs * (ei + br);
@@ -615,7 +619,8 @@ __global__ void __launch_bounds__(32, MINB) anal0_kernel(KParams p) {
     for (int e = lane; e < 2 * TL; e += 32) {
       const int li = e >> 1, part = e & 1, l = lt + li;
       if (l <= p.lmax && (m > 0 || part == 0)) {
-        const double val = T[li].g * nrm * red[e];
+        double val = T[li].g * nrm * red[e];
+        if (p.lscale0) val *= p.lscale0[l];
         const long long idx = p.real_packed ? (m == 0 ? mvs + l : mvs + 2 * (long long)l + part) : 2 * (mvs + l) + part;
         atomicAdd(&a[idx], val);
       }
@@ -839,8 +844,10 @@ __global__ void __launch_bounds__(32, MINB) anal2_kernel(KParams p) {
         const double4 v = reinterpret_cast<const double4 *>(red)[li];   // S1.re, S1.im, S2.re, S2.im
         // adjoint of the synthesis combination: E = (sp S1 - S2)/2, B = -(i/2)(sp S1 + S2), sp = spinsign
         const double gs = 0.5 * T[li].g * nrm, sp = p.spinsign;
-        const double E = part ? gs * (sp * v.y - v.w) : gs * (sp * v.x - v.z);
-        const double B = part ? -gs * (sp * v.x + v.z) : gs * (sp * v.y + v.w);
+        double E = part ? gs * (sp * v.y - v.w) : gs * (sp * v.x - v.z);
+        double B = part ? -gs * (sp * v.x + v.z) : gs * (sp * v.y + v.w);
+        if (p.lscale0) E *= p.lscale0[l];
+        if (p.lscale1) B *= p.lscale1[l];
         const long long idx = p.real_packed ? (m == 0 ? mvs + l : mvs + 2 * (long long)l + part) : 2 * (mvs + l) + part;
         atomicAdd(&aE[idx], E);
         atomicAdd(&aB[idx], B);
@@ -870,6 +877,7 @@ static KParams make_params(const LegGeom &g, const LegAlm &a, double *alm0, doub
   p.im0 = a.im_begin;
   p.trig = g.trig; p.mlim = g.mlim; p.wslot = g.wslot;
   p.alm0 = alm0; p.alm1 = alm1; p.ph = ph;
+  p.lscale0 = a.lscale[0]; p.lscale1 = a.lscale[1];
   p.src_rank = g.npeer ? g.src_rank : -1;
   for (int i = 0; i < CMDR_MAX_PEERS; ++i) p.peer[i] = g.npeer ? g.peer[i] : ph;
   return p;

@@ -40,6 +40,7 @@ struct FParams {
   PhaseLayout L;
   double4 *ph;
   double *map0, *map1, *map2;
+  const double *ps0, *ps1, *ps2;   // optional factor per local pixel on the synthesised map (nullptr: 1)
   int weighted, add;
 };
 
@@ -58,6 +59,9 @@ __device__ __forceinline__ double2 cmul(double2 a, double2 b) {
 }
 __device__ __forceinline__ double *map_ptr(const FParams &p, int c) {
   return c == 0 ? p.map0 : (c == 1 ? p.map1 : p.map2);
+}
+__device__ __forceinline__ const double *ps_ptr(const FParams &p, int c) {
+  return c == 0 ? p.ps0 : (c == 1 ? p.ps1 : p.ps2);
 }
 
 // ---- synthesis, before the FFT: fold phases into the spectrum Z = X_north + i X_south
@@ -197,14 +201,17 @@ __device__ __forceinline__ void scatter_from(const FParams &p, int pair, int c, 
   const int n = p.nph[pair], len = p.zlen[pair];
   const bool blue = p.zblue[pair];
   double *mp = map_ptr(p, c);
+  const double *ps = ps_ptr(p, c);
   const long long oN = p.ofsN[pair], oS = p.ofsS[pair];
   double w = p.weighted ? p.wgt[pair] : 1.0;
   if (blue) w /= (double)len;
   for (int j = threadIdx.x; j < n; j += blockDim.x) {
     double2 z = in[bf_pidx<PAD>(j)];
     if (blue) z = cmul(z, expipi((long long)j * j, n));
-    if (oN >= 0) { if (p.add) mp[oN + j] += w * z.x; else mp[oN + j] = w * z.x; }
-    if (oS >= 0) { if (p.add) mp[oS + j] += w * z.y; else mp[oS + j] = w * z.y; }
+    double vn = w * z.x, vs = w * z.y;
+    if (ps) { if (oN >= 0) vn *= ps[oN + j]; if (oS >= 0) vs *= ps[oS + j]; }
+    if (oN >= 0) { if (p.add) mp[oN + j] += vn; else mp[oN + j] = vn; }
+    if (oS >= 0) { if (p.add) mp[oS + j] += vs; else mp[oS + j] = vs; }
   }
 }
 __global__ void __launch_bounds__(256) scatter_kernel(FParams p, int first_pair) {
@@ -377,6 +384,7 @@ static FParams base_params(sharp_geom_info *g, int ncomp, const PhaseLayout &L, 
   p.zlen = g->d_zlen; p.zblue = g->d_zblue; p.zbase = g->d_zbase; p.ofsN = g->d_ofsN; p.ofsS = g->d_ofsS;
   p.wgt = g->d_wgt; p.buf = buf; p.vtab = reinterpret_cast<const double2 *>(g->d_vtab);
   p.L = L; p.ph = nullptr; p.map0 = p.map1 = p.map2 = nullptr; p.weighted = 0; p.add = 0;
+  p.ps0 = p.ps1 = p.ps2 = nullptr;
   return p;
 }
 
@@ -584,13 +592,14 @@ static void ensure_vtab(sharp_geom_info *g, cudaStream_t st) {
 }
 
 void ringfft_synth(sharp_geom_info *g, int ncomp, const PhaseLayout &L, const double4 *ph,
-                   double *const *map, bool weighted, bool add, cudaStream_t st) {
+                   double *const *map, bool weighted, bool add, cudaStream_t st, const double *const *pixscale) {
   if (g->npairs == 0) return;
   ensure_vtab(g, st);
   double2 *buf = static_cast<double2 *>(scratch_get("fftbuf", sizeof(double2) * (size_t)g->zlen_total * ncomp));
   FParams p = base_params(g, ncomp, L, buf);
   p.ph = const_cast<double4 *>(ph);
   p.map0 = map[0]; p.map1 = ncomp > 1 ? map[1] : nullptr; p.map2 = ncomp > 2 ? map[2] : nullptr;
+  if (pixscale) { p.ps0 = pixscale[0]; p.ps1 = ncomp > 1 ? pixscale[1] : nullptr; p.ps2 = ncomp > 2 ? pixscale[2] : nullptr; }
   p.weighted = weighted; p.add = add;
   int nfr = 0;
   const int nf = fused_prefix(g, &nfr);               // pairs [0, nf): fold + FFTs + scatter in one kernel per class

@@ -37,6 +37,9 @@ ABI_SYMBOLS = [
     "cmdr_sht_execute_iqu_dist", "cmdr_sht_mix", "cmdr_sht_invn_diag", "cmdr_sht_conviqt_cube", "cmdr_sht_allreduce_sum", "cmdr_sht_launch_count",
     "cmdr_sht_set_profiling", "cmdr_sht_last_legendre_ms", "cmdr_sht_nominal_flops",
     "cmdr_sht_release_caches", "cmdr_sht_measure_fp64_tflops", "cmdr_sht_measure_fp64_tflops_3op",
+    "cmdr_sht_measure_host_copy", "cmdr_sht_host_copy_threads",
+    "cmdr_cr_setup", "cmdr_cr_destroy", "cmdr_cr_matmulA", "cmdr_cr_invM", "cmdr_cr_set_precond_diag",
+    "cmdr_cr_get_precond_diag", "cmdr_cr_compute_rhs", "cmdr_cr_solve", "cmdr_cr_matmul_count",
 ]
 
 
@@ -87,6 +90,21 @@ def lib() -> C.CDLL:
     L.cmdr_sht_measure_fp64_tflops.restype = C.c_double
     L.cmdr_sht_measure_fp64_tflops_3op.argtypes = [ci, ci]
     L.cmdr_sht_measure_fp64_tflops_3op.restype = C.c_double
+    L.cmdr_sht_measure_host_copy.argtypes = [C.c_size_t, ci, ci, ci]
+    L.cmdr_sht_measure_host_copy.restype = C.c_double
+    L.cmdr_sht_host_copy_threads.restype = ci
+    L.cmdr_cr_setup.argtypes = [ci, ci, ci, vp, vp, vp, vp, vp, vp, ci]
+    L.cmdr_cr_setup.restype = vp
+    L.cmdr_cr_destroy.argtypes = [vp]
+    L.cmdr_cr_matmulA.argtypes = [vp, vp, vp, vp]
+    L.cmdr_cr_invM.argtypes = [vp, vp, vp, vp]
+    L.cmdr_cr_set_precond_diag.argtypes = [vp, vp]
+    L.cmdr_cr_get_precond_diag.argtypes = [vp, vp]
+    L.cmdr_cr_compute_rhs.argtypes = [vp, vp, vp, vp, vp, vp]
+    L.cmdr_cr_solve.argtypes = [vp, vp, vp, ci, ci, C.c_double, ci, ci, ci, vp, vp]
+    L.cmdr_cr_solve.restype = ci
+    L.cmdr_cr_matmul_count.argtypes = [vp]
+    L.cmdr_cr_matmul_count.restype = C.c_ulonglong
     _lib = L
     return L
 

@@ -204,6 +204,58 @@ void cmdr_sht_conviqt_cube(int comm, int nmaps, int bmax, const double *const *s
  * every rank with its partial sum). */
 void cmdr_sht_allreduce_sum(int comm, double *dev_buf, int n, void *stream);
 
+/* ---- constrained-realisation CG, device resident (commander_b200/csrc/cr.cu) ----------------------------
+ * One diffuse signal component with a diagonal prior (or none) seen through nbands bands that share the
+ * comm_mapinfo the handles come from: the CMB amplitude solve of comm_cr_mod.  The handle caches N^-1, the beams,
+ * sqrt(S) and all work vectors on the device; between cmdr_cr_setup and cmdr_cr_destroy no vector crosses PCIe
+ * except b on the way in and x on the way out of cmdr_cr_solve.
+ *
+ * Vectors are passed as sharp_execute passes a_lm: an array of nmaps column pointers, each to n_alm doubles in
+ * the local real-packed order of alm_info, host or device memory.  nmaps = 1 (T) or 3 (T, E, B).
+ * comm: the registered communicator of the comm_mapinfo (collective calls, m-distributed vectors, dot products
+ * all-reduced) or CMDR_SHT_COMM_SELF. */
+typedef struct cmdr_cr_system cmdr_cr_system;
+
+/* invN : nbands * nmaps pointers (band-major) to N^-1 per local pixel = siN^2 x mask
+ *        (commander3/src/comm_N_rms_mod.f90:264-273), host or device; copied.
+ * b_l  : nbands * nmaps pointers to lmax+1 doubles (host): the beam of commander3/src/comm_B_bl_mod.f90:108-127
+ *        times mb_eff and the mixing scalar F_mean of the band (comm_diffuse_comp_mod.f90:2077-2080).
+ * sqrtS: nmaps pointers to lmax+1 doubles (host), sqrt(C_l) of the diagonal prior
+ *        (commander3/src/comm_Cl_mod.f90:588-637), or NULL for a component without prior (P = 0, sqrt(S) = 1).
+ * precond: 0 = none (identity), 1 = diagonal (comm_diffuse_comp_mod.f90:2186-2235 for npre = 1, with
+ *        N^-1_{lm,lm} of every band from compute_invN_lm, comm_N_mod.f90:127-197, evaluated on the device). */
+cmdr_cr_system *cmdr_cr_setup(int comm, int nbands, int nmaps, const sharp_geom_info *geom_T,
+                              const sharp_geom_info *geom_P, const sharp_alm_info *alm_info,
+                              const double *const *invN, const double *const *b_l,
+                              const double *const *sqrtS, int precond);
+void cmdr_cr_destroy(cmdr_cr_system *sys);
+
+/* y = A x, cr_matmulA (commander3/src/comm_cr_mod.f90:771-1024):
+ *   A = P + sqrt(S) sum_nu B^t Y^t N^-1 Y B sqrt(S),  P = 1 with a prior, 0 without. */
+void cmdr_cr_matmulA(cmdr_cr_system *sys, const double *const *x, double *const *y, void *stream);
+
+/* z = M^-1 r, cr_invM (commander3/src/comm_cr_mod.f90:1026-1077) with the diagonal preconditioner. */
+void cmdr_cr_invM(cmdr_cr_system *sys, const double *const *r, double *const *z, void *stream);
+void cmdr_cr_set_precond_diag(cmdr_cr_system *sys, const double *const *Minv);   /* NULL: identity */
+void cmdr_cr_get_precond_diag(const cmdr_cr_system *sys, double *const *out);
+
+/* b = sqrt(S) sum_nu B^t Y^t (N^-1 d_nu + N^-1/2 eta_nu) + eta_0, cr_computeRHS (commander3/src/comm_cr_mod.f90:542-769).
+ * data, eta_pix: nbands * nmaps pointers to n_pix doubles (eta_pix may be NULL: mean-field term only);
+ * eta_alm: nmaps pointers to n_alm doubles or NULL. */
+void cmdr_cr_compute_rhs(cmdr_cr_system *sys, const double *const *data, const double *const *eta_pix,
+                         const double *const *eta_alm, double *const *b, void *stream);
+
+/* solve_cr_eqn_by_CG (commander3/src/comm_cr_mod.f90:201-348): same update order, same convergence test
+ * (stop when r^t M^-1 r < cg_tol * b^t M^-1 b, checked every cg_check_conv_freq iterations, not before
+ * cg_miniter; conv_crit 0 = 'residual', 1 = 'fixed_iter' = always maxiter iterations, the shipped setting).
+ * x: initial guess when x0_given != 0 (else zero), solution on return.  hist: optional host array of
+ * maxiter + 1 doubles, r^t M^-1 r before the loop and after every iteration.  Returns the iterations done.
+ * With 'fixed_iter' the host does not wait for the device anywhere inside the loop. */
+int cmdr_cr_solve(cmdr_cr_system *sys, const double *const *b, double *const *x, int x0_given, int maxiter,
+                  double cg_tol, int conv_crit, int cg_miniter, int cg_check_conv_freq, double *hist,
+                  void *stream);
+unsigned long long cmdr_cr_matmul_count(const cmdr_cr_system *sys);
+
 /* ---- introspection for benchmarks/tests */
 
 /* Number of CUDA kernels this library has launched since load (cuFFT execs
@@ -230,6 +282,12 @@ double cmdr_sht_measure_fp64_tflops(int iters, int reps);
  * file feeds one 64-bit operand per cycle per scheduler, so such a DFMA issues every 3 cycles
  * instead of 2 (2/3 of the peak above).  Diagnostic for the roofline discussion in DESIGN.md. */
 double cmdr_sht_measure_fp64_tflops_3op(int iters, int reps);
+
+/* Pageable caller arrays are staged through a pinned arena by a pool of copy threads (commander_b200/csrc/hostio.cu;
+ * $CMDR_SHT_COPY_THREADS, default: the CPUs the process may run on minus one, at most 16).  Payload GB/s of that
+ * pool for one copy of `bytes`: direction 0 = caller -> arena (write-combined when wc != 0), 1 = arena -> caller. */
+double cmdr_sht_measure_host_copy(size_t bytes, int direction, int wc, int reps);
+int cmdr_sht_host_copy_threads(void);
 
 /* Frees cached device buffers, cuFFT plans and coefficient tables. */
 void cmdr_sht_release_caches(void);

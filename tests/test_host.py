@@ -18,7 +18,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def test_abi_exports_every_declared_symbol(shtlib):
     hdr = open(os.path.join(ROOT, "include", "cmdr_sht.h")).read()
-    declared = set(re.findall(r"\b((?:sharp|cmdr_sht)_[a-z0-9_]+)\s*\(", hdr))
+    declared = set(re.findall(r"\b((?:sharp|cmdr_sht|cmdr_cr)_[a-zA-Z0-9_]+)\s*\(", hdr))
     declared -= {"sharp_alm_info", "sharp_geom_info"}
     assert len(declared) >= 23
     L = shtlib.lib()
