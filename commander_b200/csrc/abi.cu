@@ -330,6 +330,7 @@ void sharp_destroy_geom_info(sharp_geom_info *g) {
     cudaFree(g->d_znp); cudaFree(g->d_zlen); cudaFree(g->d_zblue);
     if (g->d_vtab) cudaFree(g->d_vtab);
     if (g->d_vtab_br) cudaFree(g->d_vtab_br);
+    for (auto &kv : g->d_vsub) cudaFree(kv.second);
     for (auto &kv : g->mlim) cudaFree(kv.second);
   }
   delete g;
@@ -616,9 +617,9 @@ static bool try_pipelined(int type, int spin, double *const *alm, double *const 
   double4 *ph = static_cast<double4 *>(scratch_get("phase", sizeof(double4) * (size_t)ncomp * a->nm * g->npairs));
   ioA.init("hstage_alm", alm, ncomp, nalm_d);
   ioM.init("hstage_map", map, ncomp, g->npix);
-  long long maxz = 0;
-  for (sharp_geom_info *sub : g->subs) { ensure_geom_device(sub); maxz = std::max(maxz, sub->zlen_total); }
-  scratch_get("fftbuf", sizeof(double2) * (size_t)maxz * ncomp);
+  size_t maxz = 0;
+  for (sharp_geom_info *sub : g->subs) { ensure_geom_device(sub); maxz = std::max(maxz, ringfft_scratch_elems(sub)); }
+  if (maxz) scratch_get("fftbuf", sizeof(double2) * maxz * ncomp);
   double *alm_dev[2], *map_dev[2];
   for (int c = 0; c < ncomp; ++c) { alm_dev[c] = alm_buf + (size_t)c * nalm_d; map_dev[c] = map_buf + (size_t)c * g->npix; }
   LegGeom G;

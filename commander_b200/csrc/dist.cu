@@ -567,9 +567,9 @@ static bool try_dist_pipelined(DistComm *C, int type, int spin, double *const *a
   const long long nalm_d = a->nalm * (a->real_packed ? 1 : 2);
   double *alm_buf = static_cast<double *>(scratch_get("stage_alm", sizeof(double) * (size_t)nalm_d * ncomp));
   double *map_buf = static_cast<double *>(scratch_get("stage_map", sizeof(double) * (size_t)g->npix * ncomp));
-  long long maxz = 0;
-  for (sharp_geom_info *sub : P->subs) if (sub) { ensure_geom_device(sub); maxz = std::max(maxz, sub->zlen_total); }
-  scratch_get("fftbuf", sizeof(double2) * (size_t)maxz * ncomp);
+  size_t maxz = 0;
+  for (sharp_geom_info *sub : P->subs) if (sub) { ensure_geom_device(sub); maxz = std::max(maxz, ringfft_scratch_elems(sub)); }
+  if (maxz) scratch_get("fftbuf", sizeof(double2) * maxz * ncomp);
   double *alm_dev[2], *map_dev[2];
   for (int c = 0; c < ncomp; ++c) { alm_dev[c] = alm_buf + (size_t)c * nalm_d; map_dev[c] = map_buf + (size_t)c * g->npix; }
   PhaseLayout L;

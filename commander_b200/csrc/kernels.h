@@ -90,6 +90,7 @@ struct PhaseLayout {
 void ringfft_synth(sharp_geom_info *geom, int ncomp, const PhaseLayout &L, const double4 *ph,
                    double *const *map, bool weighted, bool add, cudaStream_t st,
                    const double *const *pixscale = nullptr);
+size_t ringfft_scratch_elems(const sharp_geom_info *geom);   // FFT work elements per component the cuFFT regions need (0: none)
 void ringfft_anal(sharp_geom_info *geom, int ncomp, const PhaseLayout &L, double4 *ph,
                   const double *const *map, bool weighted, cudaStream_t st);
 

@@ -18,6 +18,7 @@
 
 #include "blue_fft.cuh"
 #include "kernels.h"
+#include "ring_split.cuh"
 
 namespace cmdr {
 
@@ -350,6 +351,236 @@ __global__ void __launch_bounds__(NT) blue_fused2_kernel(FParams p, int first_pa
   if (DIR == 0) scatter_from<true>(p, pair, c, u_sm); else unfold_from<true>(p, pair, c, u_sm);
 }
 
+// ---- in-place transforms of the register-blocked schedule (blue_fft.cuh, bf2_*) on a padded shared-memory array,
+// run by all NT threads of the CTA; every pass ends with a barrier
+template <int NT>
+__device__ __forceinline__ void sm_dif_strided(double2 *x, int M, const double2 *T) {
+  const int ns = bf2_num_strided(M);
+  for (int k = 0; k < ns; ++k) {
+    const int S = bf2_stages(M, k), h = bf2_half(M, k);
+    const double2 *Tk = T + bf2_tw_offset(M, k);
+    if (S == 3) { for (int q = threadIdx.x; q < (M >> 3); q += NT) dif_itemS<3, true>(x, h, Tk, q); }
+    else { for (int q = threadIdx.x; q < (M >> 4); q += NT) dif_itemS<4, true>(x, h, Tk, q); }
+    __syncthreads();
+  }
+}
+template <int NT>
+__device__ __forceinline__ void sm_dit_strided(double2 *x, int M, const double2 *T) {
+  for (int k = bf2_num_strided(M) - 1; k >= 0; --k) {
+    const int S = bf2_stages(M, k), h = bf2_half(M, k);
+    const double2 *Tk = T + bf2_tw_offset(M, k);
+    if (S == 3) { for (int q = threadIdx.x; q < (M >> 3); q += NT) dit_itemS<3, true>(x, h, Tk, q); }
+    else { for (int q = threadIdx.x; q < (M >> 4); q += NT) dit_itemS<4, true>(x, h, Tk, q); }
+    __syncthreads();
+  }
+}
+// x <- M * IDFT( DFT(x) .* V ), V in bit-reversed order (global memory)
+template <int NT>
+__device__ __forceinline__ void sm_convolve(double2 *x, int M, const double2 *T, const double2 *__restrict__ v) {
+  sm_dif_strided<NT>(x, M, T);
+  for (int q = threadIdx.x; q < (M >> 4); q += NT) conv_mid16<true>(x, v, q);
+  __syncthreads();
+  sm_dit_strided<NT>(x, M, T);
+}
+// plain transforms: DIF forward (e^-, natural in, bit-reversed out) and DIT inverse (e^+, bit-reversed in, natural out)
+template <int NT>
+__device__ __forceinline__ void sm_fft_dif(double2 *x, int M, const double2 *T) {
+  sm_dif_strided<NT>(x, M, T);
+  const double2 *Tone = T + bf2_tw_total(M) - 1;
+  for (int q = threadIdx.x; q < (M >> 4); q += NT) dif_itemS<4, true>(x, 8, Tone, q);
+  __syncthreads();
+}
+template <int NT>
+__device__ __forceinline__ void sm_fft_dit(double2 *x, int M, const double2 *T) {
+  const double2 *Tone = T + bf2_tw_total(M) - 1;
+  for (int q = threadIdx.x; q < (M >> 4); q += NT) dit_itemS<4, true>(x, 8, Tone, q);
+  __syncthreads();
+  sm_dit_strided<NT>(x, M, T);
+}
+
+// Folded spectrum bin k of a ring WITHOUT the phi0 shift factor: sum over m == +-k (mod n) of the phases with the
+// alternating sign the shift e^{i pi m / n} leaves once e^{i pi k / n} is pulled out (ring_split.cuh), so that one
+// sincospi per bin replaces one per term.
+__device__ __forceinline__ double2 fold_bin(const FParams &p, const PhaseLayout &L, int c, int pair, int n, bool shifted, int k) {
+  double2 acc = make_double2(0.0, 0.0);
+  double sg = 1.0;
+  for (int m = k; m <= L.mmax; m += n, sg = shifted ? -sg : sg) {            // m == k: p_m
+    const int src = L.m2src[m];
+    if (src < 0) continue;
+    const double4 q = p.ph[((size_t)(src * L.ncomp_tot + L.comp0 + c) * L.NML + L.m2im[m]) * L.NPL + L.pair0 + pair];
+    if (m == 0) { acc.x += q.x; acc.y += q.z; }
+    else { acc.x += sg * (q.x - q.w); acc.y += sg * (q.y + q.z); }
+  }
+  sg = shifted ? -1.0 : 1.0;
+  for (int m = n - k; m <= L.mmax; m += n, sg = shifted ? -sg : sg) {        // m == -k, m >= 1: conj p_m
+    const int src = L.m2src[m];
+    if (src < 0) continue;
+    const double4 q = p.ph[((size_t)(src * L.ncomp_tot + L.comp0 + c) * L.NML + L.m2im[m]) * L.NPL + L.pair0 + pair];
+    acc.x += sg * (q.x + q.w); acc.y += sg * (q.z - q.y);
+  }
+  return acc;
+}
+
+// phases of all m from the two DFT- bins Z_k, Z_{n-k} of z = w (x_north + i x_south)
+__device__ __forceinline__ void unfold_store(const FParams &p, const PhaseLayout &L, int c, int pair, int n, bool shifted, int e,
+                                             double2 a, double2 b) {
+  const int m = L.mlist[e];
+  // XN = (Z_k + conj Z_k2)/2 ; XS = (Z_k - conj Z_k2)/(2i)
+  double2 xn = make_double2(0.5 * (a.x + b.x), 0.5 * (a.y - b.y));
+  double2 xs = make_double2(0.5 * (a.y + b.y), -0.5 * (a.x - b.x));
+  const double cm = m == 0 ? 1.0 : 2.0;
+  double2 f = make_double2(cm, 0.0);
+  if (shifted) { double2 t = expipi(m, n); f = make_double2(cm * t.x, -cm * t.y); }
+  xn = cmul(xn, f); xs = cmul(xs, f);
+  p.ph[((size_t)(L.mlist_src[e] * L.ncomp_tot + L.comp0 + c) * L.NML + L.mlist_im[e]) * L.NPL + L.pair0 + pair] =
+      make_double4(xn.x, xn.y, xs.x, xs.y);
+}
+
+// ---- long polar-cap rings (n = 4 i, chirp-z work length of the whole ring too large for shared memory): radix-4
+// split into four length-i chirp-z transforms of work length M (ring_split.cuh).  One CTA per (ring pair, component).
+// Shared memory: zbuf (n <= nmax elements, four sub-spectra r-major) | work (M + M/16) | twiddles.
+template <int DIR, int NT>
+__global__ void __launch_bounds__(NT) ring_split_kernel(FParams p, int first_pair, int M, int nmax, const double2 *__restrict__ tw,
+                                                        const double2 *__restrict__ vsub) {
+  extern __shared__ double2 u_sm[];
+  const int pair = first_pair + blockIdx.x, c = blockIdx.y;
+  const int n = p.nph[pair], i = n >> 2;
+  const bool shifted = p.shifted[pair];
+  const PhaseLayout &L = p.L;
+  double2 *zbuf = u_sm, *work = u_sm + nmax, *T = work + M + (M >> 4);
+  const int ntw = bf2_tw_total(M);
+  for (int k = threadIdx.x; k < ntw; k += NT) T[k] = tw[k];
+  const long long oN = p.ofsN[pair], oS = p.ofsS[pair];
+  if (DIR == 0) {
+    // folded spectrum, phi0 shift and input chirp in one factor per bin
+    for (int k = threadIdx.x; k < n; k += NT)
+      zbuf[rs_slot(k, i)] = cmul(fold_bin(p, L, c, pair, n, shifted, k), rs_expipi(rs_fold_angle(k, shifted), n));
+  } else {
+    // radix-4 pass over conj(z), twiddle and input chirp
+    const double *mp = map_ptr(p, c);
+    const double w = p.weighted ? p.wgt[pair] : 1.0;
+    for (int t = threadIdx.x; t < i; t += NT) {
+      double2 y[4], o[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        y[q].x = oN >= 0 ? w * mp[oN + t + q * i] : 0.0;
+        y[q].y = oS >= 0 ? -w * mp[oS + t + q * i] : 0.0;
+      }
+      rs_butterfly4(y, o);
+#pragma unroll
+      for (int r = 0; r < 4; ++r) zbuf[r * i + t] = cmul(o[r], rs_expipi(rs_twiddle_angle(t, r), n));
+    }
+  }
+  __syncthreads();
+  const double2 *v = vsub + (size_t)(pair - first_pair) * M;
+  for (int r = 0; r < 4; ++r) {
+    for (int t = threadIdx.x; t < M; t += NT) work[bf_pidx<true>(t)] = t < i ? zbuf[r * i + t] : make_double2(0.0, 0.0);
+    __syncthreads();
+    sm_convolve<NT>(work, M, T, v);
+    for (int t = threadIdx.x; t < i; t += NT) zbuf[r * i + t] = work[bf_pidx<true>(t)];
+    __syncthreads();
+  }
+  const double invM = 1.0 / (double)M;
+  if (DIR == 0) {
+    double *mp = map_ptr(p, c);
+    const double *ps = ps_ptr(p, c);
+    const double w = (p.weighted ? p.wgt[pair] : 1.0) * invM;
+    for (int t = threadIdx.x; t < i; t += NT) {
+      double2 cr[4], o[4];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) cr[r] = cmul(zbuf[r * i + t], rs_expipi(rs_twiddle_angle(t, r), n));
+      rs_butterfly4(cr, o);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int j = t + q * i;
+        double vn = w * o[q].x, vs = w * o[q].y;
+        if (ps) { if (oN >= 0) vn *= ps[oN + j]; if (oS >= 0) vs *= ps[oS + j]; }
+        if (oN >= 0) { if (p.add) mp[oN + j] += vn; else mp[oN + j] = vn; }
+        if (oS >= 0) { if (p.add) mp[oS + j] += vs; else mp[oS + j] = vs; }
+      }
+    }
+  } else {
+    // Z_k = conj( chirp_a / M * conv_r[a] ),  k = 4 a + r
+    auto bin = [&](int k) {
+      const long long a = k >> 2;
+      const double2 g = cmul(zbuf[rs_slot(k, i)], rs_expipi(4 * a * a, n));
+      return make_double2(g.x * invM, -g.y * invM);
+    };
+    for (int e = threadIdx.x; e < L.nm_total; e += NT) {
+      const int k = L.mlist[e] % n, k2 = (n - k) % n;
+      unfold_store(p, L, c, pair, n, shifted, e, bin(k), bin(k2));
+    }
+  }
+}
+
+// filter spectra of the sub-transforms: V_i = DFT_M of v_j = e^{-i pi j^2 / i} (|j| < i, wrapped), left in the bit-reversed
+// order the DIF transform produces, which is the order conv_mid16 consumes
+template <int NT>
+__global__ void __launch_bounds__(NT) ring_split_filter_kernel(FParams p, int first_pair, int M, const double2 *__restrict__ tw,
+                                                               double2 *__restrict__ vsub) {
+  extern __shared__ double2 u_sm[];
+  const int pair = first_pair + blockIdx.x;
+  const int i = p.nph[pair] >> 2;
+  double2 *work = u_sm, *T = work + M + (M >> 4);
+  const int ntw = bf2_tw_total(M);
+  for (int k = threadIdx.x; k < ntw; k += NT) T[k] = tw[k];
+  for (int k = threadIdx.x; k < M; k += NT) {
+    const long long j = k < i ? k : (k > M - i ? M - k : -1);
+    double2 val = make_double2(0.0, 0.0);
+    if (j >= 0) { const double2 e = rs_expipi(j * j, i); val = make_double2(e.x, -e.y); }
+    work[bf_pidx<true>(k)] = val;
+  }
+  __syncthreads();
+  sm_fft_dif<NT>(work, M, T);
+  double2 *out = vsub + (size_t)(pair - first_pair) * M;
+  for (int k = threadIdx.x; k < M; k += NT) out[k] = work[bf_pidx<true>(k)];
+}
+
+// ---- rings of power-of-two length n (the belt: 4 nside): one in-place FFT of the whole ring pair
+template <int DIR, int NT>
+__global__ void __launch_bounds__(NT) ring_pow2_kernel(FParams p, int first_pair, int n, int bits, const double2 *__restrict__ tw) {
+  extern __shared__ double2 u_sm[];
+  const int pair = first_pair + blockIdx.x, c = blockIdx.y;
+  const bool shifted = p.shifted[pair];
+  const PhaseLayout &L = p.L;
+  double2 *work = u_sm, *T = work + n + (n >> 4);
+  const int ntw = bf2_tw_total(n);
+  for (int k = threadIdx.x; k < ntw; k += NT) T[k] = tw[k];
+  const long long oN = p.ofsN[pair], oS = p.ofsS[pair];
+  if (DIR == 0) {
+    for (int k = threadIdx.x; k < n; k += NT) {
+      double2 z = fold_bin(p, L, c, pair, n, shifted, k);
+      if (shifted) z = cmul(z, rs_expipi(k, n));
+      work[bf_pidx<true>((int)(__brev((unsigned)k) >> (32 - bits)))] = z;
+    }
+    __syncthreads();
+    sm_fft_dit<NT>(work, n, T);
+    double *mp = map_ptr(p, c);
+    const double *ps = ps_ptr(p, c);
+    const double w = p.weighted ? p.wgt[pair] : 1.0;
+    for (int j = threadIdx.x; j < n; j += NT) {
+      const double2 z = work[bf_pidx<true>(j)];
+      double vn = w * z.x, vs = w * z.y;
+      if (ps) { if (oN >= 0) vn *= ps[oN + j]; if (oS >= 0) vs *= ps[oS + j]; }
+      if (oN >= 0) { if (p.add) mp[oN + j] += vn; else mp[oN + j] = vn; }
+      if (oS >= 0) { if (p.add) mp[oS + j] += vs; else mp[oS + j] = vs; }
+    }
+  } else {
+    const double *mp = map_ptr(p, c);
+    const double w = p.weighted ? p.wgt[pair] : 1.0;
+    for (int j = threadIdx.x; j < n; j += NT)
+      work[bf_pidx<true>(j)] = make_double2(oN >= 0 ? w * mp[oN + j] : 0.0, oS >= 0 ? w * mp[oS + j] : 0.0);
+    __syncthreads();
+    sm_fft_dif<NT>(work, n, T);
+    for (int e = threadIdx.x; e < L.nm_total; e += NT) {
+      const int k = L.mlist[e] % n, k2 = (n - k) % n;
+      const double2 a = work[bf_pidx<true>((int)(__brev((unsigned)k) >> (32 - bits)))];
+      const double2 b = work[bf_pidx<true>((int)(__brev((unsigned)k2) >> (32 - bits)))];
+      unfold_store(p, L, c, pair, n, shifted, e, a, b);
+    }
+  }
+}
+
 // twiddles of one fused pass with leading half-size h: T[j] = exp(-i pi j / h), j < h/2 (blue_fft.cuh)
 __global__ void twiddle_kernel(double2 *T, int h, int count) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
@@ -388,19 +619,44 @@ static FParams base_params(sharp_geom_info *g, int ncomp, const PhaseLayout &L, 
   return p;
 }
 
-// Leading Bluestein regions that take the fused shared-memory kernel (work length <= 8192 complex = 128 KB):
-// returns the number of ring pairs they cover (they come first in pair order) and their count in *nregions.
-// CMDR_SHT_FUSED_BLUE=0 sends every class through cuFFT instead (cross-check / tuning).
-static int fused_prefix(const sharp_geom_info *g, int *nregions) {
-  static const bool enabled = !(getenv("CMDR_SHT_FUSED_BLUE") && atoi(getenv("CMDR_SHT_FUSED_BLUE")) == 0);
-  int nr = 0, np = 0;
-  if (enabled)
-    for (const FftRegion &R : g->regions) {
-      if (!R.bluestein || R.len > 8192 || R.first != np) break;
-      ++nr; np += R.np;
-    }
-  *nregions = nr;
-  return np;
+// How each FFT region (ring pairs of one transform length) is executed:
+//   FUSED  whole-ring chirp-z in shared memory (work length <= 8192), blue_fused[2]_kernel
+//   SPLIT  radix-4 split into four length-n/4 chirp-z transforms (ring_split_kernel): the classes whose whole-ring
+//          work length (16384) does not fit in shared memory -- 75 % of the cap pixels at nside 2048
+//   POW2   power-of-two rings (the belt, 4 nside <= 8192): one in-place FFT per ring pair (ring_pow2_kernel)
+//   CUFFT  everything else: fold / gather -> batched cuFFT (+ chirp-z through HBM) -> scatter / unfold
+// Switches for cross-checks and tuning: CMDR_SHT_FUSED_BLUE=0, CMDR_SHT_RING_SPLIT=0, CMDR_SHT_BELT_FUSED=0 send the
+// respective classes to cuFFT; CMDR_SHT_SPLIT_MIN=<len> also splits the shorter classes with whole-ring length >= len.
+enum RegionKind { RK_CUFFT = 0, RK_FUSED, RK_SPLIT, RK_POW2 };
+
+static int env_or(const char *name, int dflt) {
+  const char *e = getenv(name);
+  return (e && *e) ? atoi(e) : dflt;
+}
+static bool is_pow2(int n) { return n > 0 && (n & (n - 1)) == 0; }
+static int split_sub_len(int whole_len) { return whole_len / 4 < 1024 ? 1024 : whole_len / 4; }   // M of the length-n/4 chirp-z
+
+static RegionKind region_kind(const sharp_geom_info *g, size_t r) {
+  static const bool fused_on = env_or("CMDR_SHT_FUSED_BLUE", 1) != 0, split_on = env_or("CMDR_SHT_RING_SPLIT", 1) != 0,
+                    pow2_on = env_or("CMDR_SHT_BELT_FUSED", 1) != 0;
+  static const int split_min = env_or("CMDR_SHT_SPLIT_MIN", 16384);
+  const FftRegion &R = g->regions[r];
+  if (R.bluestein) {
+    if (split_on && R.len >= split_min && R.len <= 16384) return RK_SPLIT;     // n <= 8192, sub work length <= 4096
+    if (fused_on && R.len <= 8192) return RK_FUSED;
+    return RK_CUFFT;
+  }
+  if (pow2_on && is_pow2(R.len) && R.len >= 1024 && R.len <= 8192) return RK_POW2;
+  return RK_CUFFT;
+}
+
+// complex elements of FFT work buffer (per component) the cuFFT regions need: 0 when every region is fused
+size_t ringfft_scratch_elems(const sharp_geom_info *g) {
+  size_t need = 0;
+  for (size_t r = 0; r < g->regions.size(); ++r)
+    if (g->regions[r].np > 0 && region_kind(g, r) == RK_CUFFT)
+      need = (size_t)g->regions[r].base + (size_t)g->regions[r].np * g->regions[r].len;
+  return need;
 }
 
 static const double2 *twiddle_table(int M, cudaStream_t st) {
@@ -463,66 +719,97 @@ static cudaStream_t class_stream(int k) {
   return s;
 }
 
-// Launches the fused classes on side streams that fork from `st`; returns how many streams join_fused must
-// join back.  Threads per CTA by work length: a pass has M/4 work items.
+// One fused region on stream `cs` (DIR 0 synthesis, 1 analysis).
 template <int DIR>
-static int launch_fused(sharp_geom_info *g, int ncomp, int nregions, const FParams &p, cudaStream_t st) {
-  if (nregions == 0) return 0;
-  static bool attr_set = false;
-  const int max_smem = (int)(sizeof(double2) * (8192 + bf_tw_total(8192)));
-  if (!attr_set) {
-    attr_set = true;
-    CMDR_CUDA_CHECK(cudaFuncSetAttribute(blue_fused_kernel<DIR, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-    CMDR_CUDA_CHECK(cudaFuncSetAttribute(blue_fused_kernel<DIR, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-    CMDR_CUDA_CHECK(cudaFuncSetAttribute(blue_fused_kernel<DIR, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-  }
-  const double2 *vbr = reinterpret_cast<const double2 *>(g->d_vtab_br);
-  static const bool blocked = getenv("CMDR_SHT_FFT_BLOCKED") && atoi(getenv("CMDR_SHT_FFT_BLOCKED")) != 0;
-  if (blocked) {
-    static bool attr2_set = false;
-    if (!attr2_set) {
-      attr2_set = true;
-      const int smem2 = (int)(sizeof(double2) * (8192 + 512 + bf2_tw_total(8192)));
-      CMDR_CUDA_CHECK(cudaFuncSetAttribute(blue_fused2_kernel<DIR, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2));
-      CMDR_CUDA_CHECK(cudaFuncSetAttribute(blue_fused2_kernel<DIR, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2));
-      CMDR_CUDA_CHECK(cudaFuncSetAttribute(blue_fused2_kernel<DIR, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2));
+static void launch_region(sharp_geom_info *g, int ncomp, size_t r, RegionKind kind, const FParams &p, cudaStream_t cs) {
+  const FftRegion &R = g->regions[r];
+  const dim3 grid(R.np, ncomp);
+  if (kind == RK_SPLIT) {
+    static bool attr = false;
+    if (!attr) {
+      attr = true;
+      const int smem = (int)(sizeof(double2) * (8192 + 4096 + 256 + bf2_tw_total(4096)));
+      CMDR_CUDA_CHECK(cudaFuncSetAttribute(ring_split_kernel<DIR, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      CMDR_CUDA_CHECK(cudaFuncSetAttribute(ring_split_kernel<DIR, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      CMDR_CUDA_CHECK(cudaFuncSetAttribute(ring_split_kernel<DIR, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     }
-    for (int r = 0; r < nregions; ++r) twiddle_table2(g->regions[r].len, st);
-    cudaEvent_t e0 = pooled_event(150);
-    CMDR_CUDA_CHECK(cudaEventRecord(e0, st));
-    int ns = 0;
-    for (int r = nregions - 1; r >= 0; --r) {
-      const FftRegion &R = g->regions[r];
-      if (R.np == 0) continue;
-      cudaStream_t cs = class_stream(ns);
-      CMDR_CUDA_CHECK(cudaStreamWaitEvent(cs, e0, 0));
-      const double2 *tw = twiddle_table2(R.len, st);
+    const int M = split_sub_len(R.len), nmax = R.len / 2;          // rings of this class have n <= len / 2 points
+    const double2 *tw = twiddle_table2(M, cs);
+    const double2 *vsub = reinterpret_cast<const double2 *>(g->d_vsub[(int)r]);
+    const size_t smem = sizeof(double2) * (size_t)(nmax + M + (M >> 4) + bf2_tw_total(M));
+    static const int nt = env_or("CMDR_SHT_SPLIT_NT", 0);
+    const int NT = nt ? nt : (M >= 4096 ? 512 : (M >= 2048 ? 256 : 128));
+    if (NT <= 128) ring_split_kernel<DIR, 128><<<grid, 128, smem, cs>>>(p, R.first, M, nmax, tw, vsub);
+    else if (NT <= 256) ring_split_kernel<DIR, 256><<<grid, 256, smem, cs>>>(p, R.first, M, nmax, tw, vsub);
+    else ring_split_kernel<DIR, 512><<<grid, 512, smem, cs>>>(p, R.first, M, nmax, tw, vsub);
+  } else if (kind == RK_POW2) {
+    static bool attr = false;
+    if (!attr) {
+      attr = true;
+      const int smem = (int)(sizeof(double2) * (8192 + 512 + bf2_tw_total(8192)));
+      CMDR_CUDA_CHECK(cudaFuncSetAttribute(ring_pow2_kernel<DIR, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      CMDR_CUDA_CHECK(cudaFuncSetAttribute(ring_pow2_kernel<DIR, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      CMDR_CUDA_CHECK(cudaFuncSetAttribute(ring_pow2_kernel<DIR, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    }
+    const int n = R.len;
+    int bits = 0;
+    while ((1 << bits) < n) ++bits;
+    const double2 *tw = twiddle_table2(n, cs);
+    const size_t smem = sizeof(double2) * (size_t)(n + (n >> 4) + bf2_tw_total(n));
+    if (n <= 2048) ring_pow2_kernel<DIR, 128><<<grid, 128, smem, cs>>>(p, R.first, n, bits, tw);
+    else if (n <= 4096) ring_pow2_kernel<DIR, 256><<<grid, 256, smem, cs>>>(p, R.first, n, bits, tw);
+    else ring_pow2_kernel<DIR, 512><<<grid, 512, smem, cs>>>(p, R.first, n, bits, tw);
+  } else {   // RK_FUSED
+    const double2 *vbr = reinterpret_cast<const double2 *>(g->d_vtab_br);
+    static const bool blocked = env_or("CMDR_SHT_FFT_BLOCKED", 1) != 0;
+    if (blocked) {
+      static bool attr = false;
+      if (!attr) {
+        attr = true;
+        const int smem2 = (int)(sizeof(double2) * (8192 + 512 + bf2_tw_total(8192)));
+        CMDR_CUDA_CHECK(cudaFuncSetAttribute(blue_fused2_kernel<DIR, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2));
+        CMDR_CUDA_CHECK(cudaFuncSetAttribute(blue_fused2_kernel<DIR, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2));
+        CMDR_CUDA_CHECK(cudaFuncSetAttribute(blue_fused2_kernel<DIR, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2));
+      }
+      const double2 *tw = twiddle_table2(R.len, cs);
       const size_t smem = sizeof(double2) * (size_t)(R.len + (R.len >> 4) + bf2_tw_total(R.len));
-      if (R.len <= 2048) blue_fused2_kernel<DIR, 128><<<dim3(R.np, ncomp), 128, smem, cs>>>(p, R.first, R.len, tw, vbr);
-      else if (R.len <= 4096) blue_fused2_kernel<DIR, 256><<<dim3(R.np, ncomp), 256, smem, cs>>>(p, R.first, R.len, tw, vbr);
-      else blue_fused2_kernel<DIR, 512><<<dim3(R.np, ncomp), 512, smem, cs>>>(p, R.first, R.len, tw, vbr);
-      count_launch();
-      CMDR_CUDA_CHECK(cudaEventRecord(pooled_event(151 + ns), cs));
-      ++ns;
+      if (R.len <= 2048) blue_fused2_kernel<DIR, 128><<<grid, 128, smem, cs>>>(p, R.first, R.len, tw, vbr);
+      else if (R.len <= 4096) blue_fused2_kernel<DIR, 256><<<grid, 256, smem, cs>>>(p, R.first, R.len, tw, vbr);
+      else blue_fused2_kernel<DIR, 512><<<grid, 512, smem, cs>>>(p, R.first, R.len, tw, vbr);
+    } else {
+      static bool attr = false;
+      if (!attr) {
+        attr = true;
+        const int max_smem = (int)(sizeof(double2) * (8192 + bf_tw_total(8192)));
+        CMDR_CUDA_CHECK(cudaFuncSetAttribute(blue_fused_kernel<DIR, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+        CMDR_CUDA_CHECK(cudaFuncSetAttribute(blue_fused_kernel<DIR, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+        CMDR_CUDA_CHECK(cudaFuncSetAttribute(blue_fused_kernel<DIR, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+      }
+      const double2 *tw = twiddle_table(R.len, cs);
+      const size_t smem = sizeof(double2) * (size_t)(R.len + bf_tw_total(R.len));
+      if (R.len <= 2048) blue_fused_kernel<DIR, 256><<<grid, 256, smem, cs>>>(p, R.first, R.len, tw, vbr);
+      else if (R.len <= 4096) blue_fused_kernel<DIR, 512><<<grid, 512, smem, cs>>>(p, R.first, R.len, tw, vbr);
+      else blue_fused_kernel<DIR, 1024><<<grid, 1024, smem, cs>>>(p, R.first, R.len, tw, vbr);
     }
-    CMDR_CUDA_CHECK(cudaGetLastError());
-    return ns;
   }
-  for (int r = 0; r < nregions; ++r) twiddle_table(g->regions[r].len, st);     // built on st before the fork
+  count_launch();
+}
+
+// Launches every fused region on its own side stream forked from `st` (the classes are independent, and the short
+// ones are latency bound, so they overlap), longest class first; returns the number of streams to join.
+template <int DIR>
+static int launch_fused_regions(sharp_geom_info *g, int ncomp, const FParams &p, cudaStream_t st) {
+  std::vector<size_t> todo;
+  for (size_t r = g->regions.size(); r-- > 0;)
+    if (g->regions[r].np > 0 && region_kind(g, r) != RK_CUFFT) todo.push_back(r);
+  if (todo.empty()) return 0;
   cudaEvent_t e0 = pooled_event(150);
   CMDR_CUDA_CHECK(cudaEventRecord(e0, st));
   int ns = 0;
-  for (int r = nregions - 1; r >= 0; --r) {                                   // longest class first
-    const FftRegion &R = g->regions[r];
-    if (R.np == 0) continue;
+  for (size_t r : todo) {
     cudaStream_t cs = class_stream(ns);
     CMDR_CUDA_CHECK(cudaStreamWaitEvent(cs, e0, 0));
-    const double2 *tw = twiddle_table(R.len, st);
-    const size_t smem = sizeof(double2) * (size_t)(R.len + bf_tw_total(R.len));
-    if (R.len <= 2048) blue_fused_kernel<DIR, 256><<<dim3(R.np, ncomp), 256, smem, cs>>>(p, R.first, R.len, tw, vbr);
-    else if (R.len <= 4096) blue_fused_kernel<DIR, 512><<<dim3(R.np, ncomp), 512, smem, cs>>>(p, R.first, R.len, tw, vbr);
-    else blue_fused_kernel<DIR, 1024><<<dim3(R.np, ncomp), 1024, smem, cs>>>(p, R.first, R.len, tw, vbr);
-    count_launch();
+    launch_region<DIR>(g, ncomp, r, region_kind(g, r), p, cs);
     CMDR_CUDA_CHECK(cudaEventRecord(pooled_event(151 + ns), cs));
     ++ns;
   }
@@ -533,59 +820,74 @@ static void join_fused(int ns, cudaStream_t st) {
   for (int k = 0; k < ns; ++k) CMDR_CUDA_CHECK(cudaStreamWaitEvent(st, pooled_event(151 + k), 0));
 }
 
-static void run_ffts(sharp_geom_info *g, int ncomp, double2 *buf, int direct_dir, FParams &p, cudaStream_t st,
-                     size_t first_region = 0) {
-  for (size_t r = first_region; r < g->regions.size(); ++r) {
-    const FftRegion &R = g->regions[r];
-    if (R.np == 0) continue;
-    cufftHandle h = get_plan(g, (int)r, ncomp);
-    CMDR_CUFFT_CHECK(cufftSetStream(h, st));
-    cufftDoubleComplex *d = reinterpret_cast<cufftDoubleComplex *>(buf + (size_t)ncomp * R.base);
-    if (!R.bluestein) {
-      CMDR_CUFFT_CHECK(cufftExecZ2Z(h, d, d, direct_dir));
-      count_launch();
-    } else {
-      CMDR_CUFFT_CHECK(cufftExecZ2Z(h, d, d, CUFFT_FORWARD));
-      blue_mul_kernel<<<dim3(R.np, ncomp), 256, 0, st>>>(p, R.first);
-      CMDR_CUFFT_CHECK(cufftExecZ2Z(h, d, d, CUFFT_INVERSE));
-      count_launch(3);
-    }
+static void run_fft_region(sharp_geom_info *g, int ncomp, size_t r, double2 *buf, int direct_dir, FParams &p, cudaStream_t st) {
+  const FftRegion &R = g->regions[r];
+  cufftHandle h = get_plan(g, (int)r, ncomp);
+  CMDR_CUFFT_CHECK(cufftSetStream(h, st));
+  cufftDoubleComplex *d = reinterpret_cast<cufftDoubleComplex *>(buf + (size_t)ncomp * R.base);
+  if (!R.bluestein) {
+    CMDR_CUFFT_CHECK(cufftExecZ2Z(h, d, d, direct_dir));
+    count_launch();
+  } else {
+    CMDR_CUFFT_CHECK(cufftExecZ2Z(h, d, d, CUFFT_FORWARD));
+    blue_mul_kernel<<<dim3(R.np, ncomp), 256, 0, st>>>(p, R.first);
+    CMDR_CUFFT_CHECK(cufftExecZ2Z(h, d, d, CUFFT_INVERSE));
+    count_launch(3);
   }
-  CMDR_CUDA_CHECK(cudaGetLastError());
 }
 
+// Tables built once per geometry: chirp-z filter spectra of the cuFFT and whole-ring fused classes (natural order, and
+// bit-reversed for the fused kernels) and of the sub-transforms of the split classes; twiddle tables of every length.
 static void ensure_vtab(sharp_geom_info *g, cudaStream_t st) {
   if (g->vtab_ready) return;
   g->vtab_ready = true;
-  if (g->vlen_total == 0) return;
-  CMDR_CUDA_CHECK(cudaMalloc(&g->d_vtab, sizeof(double2) * (size_t)g->vlen_total));
   PhaseLayout L;
   FParams p = base_params(g, 1, L, nullptr);
+  size_t vneed = 0, brneed = 0;
   for (size_t r = 0; r < g->regions.size(); ++r) {
     const FftRegion &R = g->regions[r];
     if (!R.bluestein || R.np == 0) continue;
+    const RegionKind k = region_kind(g, r);
+    if (k == RK_CUFFT || k == RK_FUSED) vneed = (size_t)R.base + (size_t)R.np * R.len;
+    if (k == RK_FUSED) brneed = (size_t)R.base + (size_t)R.np * R.len;
+  }
+  if (vneed) CMDR_CUDA_CHECK(cudaMalloc(&g->d_vtab, sizeof(double2) * vneed));
+  if (brneed) CMDR_CUDA_CHECK(cudaMalloc(&g->d_vtab_br, sizeof(double2) * brneed));
+  p.vtab = reinterpret_cast<const double2 *>(g->d_vtab);
+  for (size_t r = 0; r < g->regions.size(); ++r) {
+    const FftRegion &R = g->regions[r];
+    if (R.np == 0) continue;
+    const RegionKind k = region_kind(g, r);
+    if (k == RK_POW2) { twiddle_table2(R.len, st); continue; }
+    if (!R.bluestein) continue;
+    if (k == RK_SPLIT) {
+      const int M = split_sub_len(R.len);
+      double2 *vs = nullptr;
+      CMDR_CUDA_CHECK(cudaMalloc(&vs, sizeof(double2) * (size_t)R.np * M));
+      g->d_vsub[(int)r] = reinterpret_cast<double *>(vs);
+      const double2 *tw = twiddle_table2(M, st);
+      static bool attr = false;
+      if (!attr) {
+        attr = true;
+        CMDR_CUDA_CHECK(cudaFuncSetAttribute(ring_split_filter_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)(sizeof(double2) * (4096 + 256 + bf2_tw_total(4096)))));
+      }
+      ring_split_filter_kernel<256><<<R.np, 256, sizeof(double2) * (size_t)(M + (M >> 4) + bf2_tw_total(M)), st>>>(p, R.first, M, tw, vs);
+      count_launch();
+      continue;
+    }
     blue_filter_kernel<<<R.np, 256, 0, st>>>(p, R.first, reinterpret_cast<double2 *>(g->d_vtab));
     cufftHandle h = get_plan(g, (int)r, 1);
     CMDR_CUFFT_CHECK(cufftSetStream(h, st));
     cufftDoubleComplex *d = reinterpret_cast<cufftDoubleComplex *>(g->d_vtab) + R.base;
     CMDR_CUFFT_CHECK(cufftExecZ2Z(h, d, d, CUFFT_FORWARD));
     count_launch(2);
-  }
-  // the fused classes read their filter spectra in bit-reversed order (same offsets: they are the leading regions)
-  int nfr = 0;
-  fused_prefix(g, &nfr);
-  if (nfr > 0) {
-    const FftRegion &last = g->regions[nfr - 1];
-    const size_t flen = (size_t)last.base + (size_t)last.np * last.len;
-    CMDR_CUDA_CHECK(cudaMalloc(&g->d_vtab_br, sizeof(double2) * flen));
-    p.vtab = reinterpret_cast<const double2 *>(g->d_vtab);
-    for (int r = 0; r < nfr; ++r) {
-      const FftRegion &R = g->regions[r];
-      if (R.np == 0) continue;
+    if (k == RK_FUSED) {     // the fused kernels read the spectrum in bit-reversed order
       int bits = 0;
       while ((1 << bits) < R.len) ++bits;
       bitrev_filter_kernel<<<R.np, 256, 0, st>>>(p, R.first, bits, reinterpret_cast<double2 *>(g->d_vtab_br));
       count_launch();
+      if (env_or("CMDR_SHT_FFT_BLOCKED", 1) != 0) twiddle_table2(R.len, st); else twiddle_table(R.len, st);
     }
   }
   CMDR_CUDA_CHECK(cudaGetLastError());
@@ -595,42 +897,28 @@ void ringfft_synth(sharp_geom_info *g, int ncomp, const PhaseLayout &L, const do
                    double *const *map, bool weighted, bool add, cudaStream_t st, const double *const *pixscale) {
   if (g->npairs == 0) return;
   ensure_vtab(g, st);
-  double2 *buf = static_cast<double2 *>(scratch_get("fftbuf", sizeof(double2) * (size_t)g->zlen_total * ncomp));
+  const size_t zneed = ringfft_scratch_elems(g);
+  double2 *buf = zneed ? static_cast<double2 *>(scratch_get("fftbuf", sizeof(double2) * zneed * ncomp)) : nullptr;
   FParams p = base_params(g, ncomp, L, buf);
   p.ph = const_cast<double4 *>(ph);
   p.map0 = map[0]; p.map1 = ncomp > 1 ? map[1] : nullptr; p.map2 = ncomp > 2 ? map[2] : nullptr;
   if (pixscale) { p.ps0 = pixscale[0]; p.ps1 = ncomp > 1 ? pixscale[1] : nullptr; p.ps2 = ncomp > 2 ? pixscale[2] : nullptr; }
   p.weighted = weighted; p.add = add;
-  int nfr = 0;
-  const int nf = fused_prefix(g, &nfr);               // pairs [0, nf): fold + FFTs + scatter in one kernel per class
-  const int nside_streams = launch_fused<0>(g, ncomp, nfr, p, st);
-  if (nf == g->npairs) { join_fused(nside_streams, st); return; }
-  // all remaining pairs that need the generic (aliasing) fold go in ONE launch: the blocks of short rings are
-  // latency bound (long m chains per bin) and must overlap the big ones instead of queueing
-  int gen_first = -1, gen_np = 0;
-  for (size_t r = nfr; r < g->regions.size(); ++r) {
+  const int nside_streams = launch_fused_regions<0>(g, ncomp, p, st);
+  for (size_t r = 0; r < g->regions.size(); ++r) {             // what is left goes through cuFFT on the caller's stream
     const FftRegion &R = g->regions[r];
-    if (R.np == 0) continue;
-    if (!R.bluestein && R.len >= 2 * L.mmax + 1) {      // no aliasing: coalesced transpose
+    if (R.np == 0 || region_kind(g, r) != RK_CUFFT) continue;
+    if (!R.bluestein && R.len >= 2 * L.mmax + 1) {             // no aliasing: coalesced transpose
       CMDR_CUDA_CHECK(cudaMemsetAsync(buf + (size_t)ncomp * R.base, 0, sizeof(double2) * (size_t)ncomp * R.np * R.len, st));
       dim3 grid((R.np + 31) / 32, (L.nm_total + 31) / 32, ncomp);
       fold_transpose_kernel<<<grid, 256, 0, st>>>(p, R.first, R.np, R.len);
-      count_launch();
-    } else if (gen_first < 0 || R.first == gen_first + gen_np) {
-      if (gen_first < 0) gen_first = R.first;
-      gen_np += R.np;
-    } else {                                             // non-contiguous (not produced by build_regions)
+    } else {
       fold_kernel<<<dim3(R.np, ncomp), 256, 0, st>>>(p, R.first);
-      count_launch();
     }
+    run_fft_region(g, ncomp, r, buf, CUFFT_INVERSE, p, st);
+    scatter_kernel<<<dim3(R.np, ncomp), 256, 0, st>>>(p, R.first);
+    count_launch(2);
   }
-  if (gen_np > 0) {
-    fold_kernel<<<dim3(gen_np, ncomp), 256, 0, st>>>(p, gen_first);
-    count_launch();
-  }
-  run_ffts(g, ncomp, buf, CUFFT_INVERSE, p, st, nfr);
-  scatter_kernel<<<dim3(g->npairs - nf, ncomp), 256, 0, st>>>(p, nf);
-  count_launch();
   CMDR_CUDA_CHECK(cudaGetLastError());
   join_fused(nside_streams, st);
 }
@@ -639,22 +927,23 @@ void ringfft_anal(sharp_geom_info *g, int ncomp, const PhaseLayout &L, double4 *
                   const double *const *map, bool weighted, cudaStream_t st) {
   if (g->npairs == 0) return;
   ensure_vtab(g, st);
-  double2 *buf = static_cast<double2 *>(scratch_get("fftbuf", sizeof(double2) * (size_t)g->zlen_total * ncomp));
+  const size_t zneed = ringfft_scratch_elems(g);
+  double2 *buf = zneed ? static_cast<double2 *>(scratch_get("fftbuf", sizeof(double2) * zneed * ncomp)) : nullptr;
   FParams p = base_params(g, ncomp, L, buf);
   p.ph = ph;
   p.map0 = const_cast<double *>(map[0]);
   p.map1 = ncomp > 1 ? const_cast<double *>(map[1]) : nullptr;
   p.map2 = ncomp > 2 ? const_cast<double *>(map[2]) : nullptr;
   p.weighted = weighted;
-  int nfr = 0;
-  const int nf = fused_prefix(g, &nfr);
-  const int nside_streams = launch_fused<1>(g, ncomp, nfr, p, st);
-  if (nf == g->npairs) { join_fused(nside_streams, st); return; }
-  gather_kernel<<<dim3(g->npairs - nf, ncomp), 256, 0, st>>>(p, nf);
-  count_launch();
-  run_ffts(g, ncomp, buf, CUFFT_FORWARD, p, st, nfr);
-  unfold_kernel<<<dim3(g->npairs - nf, ncomp), 256, 0, st>>>(p, nf);
-  count_launch();
+  const int nside_streams = launch_fused_regions<1>(g, ncomp, p, st);
+  for (size_t r = 0; r < g->regions.size(); ++r) {
+    const FftRegion &R = g->regions[r];
+    if (R.np == 0 || region_kind(g, r) != RK_CUFFT) continue;
+    gather_kernel<<<dim3(R.np, ncomp), 256, 0, st>>>(p, R.first);
+    run_fft_region(g, ncomp, r, buf, CUFFT_FORWARD, p, st);
+    unfold_kernel<<<dim3(R.np, ncomp), 256, 0, st>>>(p, R.first);
+    count_launch(2);
+  }
   CMDR_CUDA_CHECK(cudaGetLastError());
   join_fused(nside_streams, st);
 }

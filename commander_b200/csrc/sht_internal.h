@@ -72,6 +72,7 @@ struct sharp_geom_info {
   int *d_zidx = nullptr, *d_znp = nullptr, *d_zlen = nullptr, *d_zblue = nullptr;
   double *d_vtab = nullptr;         // Bluestein filter spectra (complex), built lazily
   double *d_vtab_br = nullptr;      // the same in bit-reversed order for the classes of the fused kernel (ringfft.cu)
+  std::map<int, double *> d_vsub;   // per split region: filter spectra of the length-n/4 sub-transforms (ringfft.cu)
   bool vtab_ready = false;
   std::map<long long, int> plans;   // key (region<<8 | ncomp) -> cufftHandle
   std::map<long long, int *> mlim;  // key (lmax<<8 | spin) -> device int[npairs]

@@ -563,13 +563,18 @@ def test_midsize_and_odd_nside_vs_oracle(shtlib, cpu_oracle, nside, lmax, spin):
     sharp.sharp_destroy_geom_info(gi)
 
 
-def test_fused_and_cufft_ring_paths_agree(shtlib):
-    """The polar-cap classes go through the fused chirp-z kernel by default and through cuFFT with
-    CMDR_SHT_FUSED_BLUE=0 (read once per process, hence the subprocess): same maps and a_lm to rounding."""
+def test_ring_fft_paths_agree(shtlib, cpu_oracle):
+    """The ring-FFT stage has several execution paths per ring class (commander_b200/csrc/ringfft.cu: region_kind): batched
+    cuFFT with chirp-z through HBM (the reference path of this test: every switch off), the whole-ring fused chirp-z
+    kernel (plain and register-blocked), the radix-4 split chirp-z kernel (default only for the classes of work length
+    16384; CMDR_SHT_SPLIT_MIN=1024 forces it for every cap ring here) and the whole-ring power-of-two kernel for the belt.
+    The switches are read once per process, hence the subprocesses.  Same maps and a_lm to rounding, and the all-cuFFT
+    result against the oracle."""
     import os
     import subprocess
     import sys
     import tempfile
+    S = cpu_oracle
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     code = r"""
 import sys, numpy as np
@@ -580,26 +585,39 @@ m = comm_map(info)
 rng = np.random.default_rng(8)
 m.alm[:] = rng.standard_normal(m.alm.shape)
 m.alm[1:3, info.lm[0] < 2] = 0
+a0 = m.alm.copy()
 m.Y(); mp = m.map.copy()
 m.map[:] = rng.standard_normal(m.map.shape)
-m.Yt()
-np.savez(sys.argv[1], map=mp, alm=m.alm)
+x0 = m.map.copy()
+m.YtW()
+np.savez(sys.argv[1], map=mp, alm=m.alm, a0=a0, x0=x0)
 """ % root
+    off = dict(CMDR_SHT_FUSED_BLUE="0", CMDR_SHT_RING_SPLIT="0", CMDR_SHT_BELT_FUSED="0")
+    variants = {
+        "cufft": off,
+        "fused": dict(off, CMDR_SHT_FUSED_BLUE="1", CMDR_SHT_FFT_BLOCKED="0"),
+        "blocked": dict(off, CMDR_SHT_FUSED_BLUE="1", CMDR_SHT_FFT_BLOCKED="1"),
+        "split": dict(off, CMDR_SHT_RING_SPLIT="1", CMDR_SHT_SPLIT_MIN="1024"),
+        "belt": dict(off, CMDR_SHT_BELT_FUSED="1"),
+        "default": {},
+    }
     res = {}
     with tempfile.TemporaryDirectory() as td:
-        for flag, blocked in (("1", "0"), ("0", "0"), ("1", "1")):
-            out = os.path.join(td, f"r{flag}{blocked}.npz")
-            env = dict(os.environ, CMDR_SHT_FUSED_BLUE=flag, CMDR_SHT_FFT_BLOCKED=blocked)
-            r = subprocess.run([sys.executable, "-c", code, out], env=env, capture_output=True, text=True, timeout=300)
-            assert r.returncode == 0, r.stderr[-2000:]
-            res[flag + blocked] = dict(np.load(out))
-    assert rel(res["10"]["map"], res["00"]["map"]) <= 1e-13
-    assert rel(res["10"]["alm"], res["00"]["alm"]) <= 1e-13
-    assert not np.array_equal(res["10"]["map"], res["00"]["map"])      # two different code paths did run
-    # the register-blocked variant of the fused kernel (opt-in, CMDR_SHT_FFT_BLOCKED=1)
-    assert rel(res["11"]["map"], res["00"]["map"]) <= 1e-12
-    assert rel(res["11"]["alm"], res["00"]["alm"]) <= 1e-12
-    assert not np.array_equal(res["11"]["map"], res["10"]["map"])
+        for name, envv in variants.items():
+            out = os.path.join(td, name + ".npz")
+            r = subprocess.run([sys.executable, "-c", code, out], env=dict(os.environ, **envv), capture_output=True, text=True,
+                               timeout=300)
+            assert r.returncode == 0, (name, r.stderr[-2000:])
+            res[name] = dict(np.load(out))
+    ref = res["cufft"]
+    for name in ("fused", "blocked", "split", "belt", "default"):
+        assert rel(res[name]["map"], ref["map"]) <= 1e-12, (name, rel(res[name]["map"], ref["map"]))
+        assert rel(res[name]["alm"], ref["alm"]) <= 1e-12, (name, rel(res[name]["alm"], ref["alm"]))
+        assert not np.array_equal(res[name]["map"], ref["map"]), name      # a different code path did run
+    oY = np.concatenate([S.execute(S.Y, 0, 512, 700, alm=ref["a0"][0:1]), S.execute(S.Y, 2, 512, 700, alm=ref["a0"][1:3])])
+    oA = np.concatenate([S.execute(S.YtW, 0, 512, 700, map=ref["x0"][0:1]), S.execute(S.YtW, 2, 512, 700, map=ref["x0"][1:3])])
+    for name in variants:
+        assert rel(res[name]["map"], oY) <= TOL and rel(res[name]["alm"], oA) <= TOL, name
 
 
 @pytest.mark.parametrize("spin", [0, 2])

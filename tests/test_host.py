@@ -314,3 +314,50 @@ def test_add_alm_set_alm_loops(shtlib):
             if j != -1:
                 want[:q, i] = m.alm[:q, j]
         assert np.array_equal(o.alm, want)
+
+
+@pytest.fixture(scope="module")
+def emul_ring():
+    """tests/host_emul/emul_ringsplit.cpp: ring_split.cuh + blue_fft.cuh sequenced as ring_split_kernel / ring_pow2_kernel do."""
+    src = os.path.join(ROOT, "tests", "host_emul", "emul_ringsplit.cpp")
+    hdrs = [os.path.join(ROOT, "commander_b200", "csrc", h) for h in ("blue_fft.cuh", "ring_split.cuh")]
+    out = os.path.join(ROOT, "tests", "host_emul", "_build")
+    os.makedirs(out, exist_ok=True)
+    so = os.path.join(out, "libemul_ringsplit.so")
+    if not os.path.exists(so) or os.path.getmtime(so) < max([os.path.getmtime(src)] + [os.path.getmtime(h) for h in hdrs]):
+        subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-o", so, src])
+    L = C.CDLL(so)
+    L.emul_ring_split.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int]
+    L.emul_ring_pow2.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+    return L
+
+
+@pytest.mark.parametrize("i,M", [(1, 1024), (3, 1024), (129, 1024), (512, 1024), (513, 2048), (1000, 2048), (1025, 4096),
+                                 (1531, 4096), (2047, 4096)])
+def test_ring_split_transform_on_host(emul_ring, i, M):
+    """A cap ring of n = 4 i points through four length-i chirp-z transforms of work length M and one radix-4 pass:
+    both directions against numpy's FFT of the whole ring (every i of the classes the kernel serves, incl. primes)."""
+    n = 4 * i
+    rng = np.random.default_rng(i)
+    Z = rng.standard_normal(n) + 1j * rng.standard_normal(n)
+    x = np.empty(n, dtype=np.complex128)
+    emul_ring.emul_ring_split(Z.ctypes.data, x.ctypes.data, n, M, 0)
+    ref = np.fft.ifft(Z) * n
+    assert np.abs(x - ref).max() <= 2e-12 * np.abs(ref).max()
+    F = np.empty(n, dtype=np.complex128)
+    emul_ring.emul_ring_split(Z.ctypes.data, F.ctypes.data, n, M, 1)
+    ref = np.fft.fft(Z)
+    assert np.abs(F - ref).max() <= 2e-12 * np.abs(ref).max()
+
+
+@pytest.mark.parametrize("n", [1024, 2048, 4096, 8192])
+def test_ring_pow2_transform_on_host(emul_ring, n):
+    rng = np.random.default_rng(n)
+    Z = rng.standard_normal(n) + 1j * rng.standard_normal(n)
+    x = np.empty(n, dtype=np.complex128)
+    emul_ring.emul_ring_pow2(Z.ctypes.data, x.ctypes.data, n, 0)
+    ref = np.fft.ifft(Z) * n
+    assert np.abs(x - ref).max() <= 1e-12 * np.abs(ref).max()
+    emul_ring.emul_ring_pow2(Z.ctypes.data, x.ctypes.data, n, 1)
+    ref = np.fft.fft(Z)
+    assert np.abs(x - ref).max() <= 1e-12 * np.abs(ref).max()
