@@ -25,6 +25,11 @@ void destroy_plans(sharp_geom_info *g);
 void forget_layout(const sharp_alm_info *a);
 void dist_forget_handle(const void *h);   // dist.cu: drops every cached distributed plan built for this handle
 
+bool phase_ring_major() {
+  static const bool ring = !(getenv("CMDR_SHT_PH_LAYOUT") && getenv("CMDR_SHT_PH_LAYOUT")[0] == 'm');
+  return ring;
+}
+
 static std::atomic<unsigned long long> g_launches{0};
 void count_launch(int n) { g_launches += (unsigned long long)n; }
 

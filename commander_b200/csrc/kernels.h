@@ -61,8 +61,18 @@ struct XformOpts {
   const double *pixscale[3] = {nullptr, nullptr, nullptr};
 };
 
-// Phase buffer element: {north re, north im, south re, south im}.
-// Index: ((owner*ncomp_tot + comp0 + c)*NML + im)*NPL + local
+// Phase buffer element: {north re, north im, south re, south im}.  One block of NML x NPL elements per (ring owner /
+// m owner, component); inside a block the element of (local m `im`, local ring pair `pair`) sits at
+//   ring-major (default):  pair * NML + im   -- the phases of ONE ring pair for consecutive m are contiguous, so the
+//                          ring-FFT kernels (one CTA per ring pair) read and write whole rows; the Legendre kernels'
+//                          one-element-per-ring accesses become 32-byte scatters, which their low bandwidth need
+//                          (1 GB over >= 20 ms) does not notice
+//   m-major (CMDR_SHT_PH_LAYOUT=m, the round-1 layout):  im * NPL + pair
+bool phase_ring_major();
+__host__ __device__ inline size_t ph_index(int block, int ncomp_tot, int comp, int NML, int NPL, int im, int pair, bool ring_major) {
+  const size_t base = (size_t)(block * ncomp_tot + comp) * NML * NPL;
+  return ring_major ? base + (size_t)pair * NML + im : base + (size_t)im * NPL + pair;
+}
 //
 // synthesis: alm (device, ncomp pointers) -> ph ; analysis: ph -> alm (atomic accumulate)
 // `prep`: (re)build the pre-scaled a_lm tile rows first; false when the same a_lm were already

@@ -36,6 +36,7 @@ struct KParams {
   int spin;          // 0, or s >= 1 for the two-component kernels
   double spinsign;   // sign of (+s)a = spinsign (E + iB): -1 for even s (HEALPix COSMO for s = 2), +1 for odd s
   int nslots, NPL, NML, ncomp_tot, comp0;
+  int ring_major;    // phase layout inside a block (kernels.h: ph_index)
   int slot_begin;   // first slot handled by this launch (nslots = one past the last)
   int im0;          // first local m handled by this launch (grid.y counts from it)
   const int *mval;
@@ -66,7 +67,7 @@ __device__ __forceinline__ const double4 *ph_in(const KParams &p, int comp, int 
   const int slot = p.wslot ? p.wslot[work] : work;
   int owner = slot / p.NPL, local = slot - owner * p.NPL;
   const int blk = p.src_rank >= 0 ? p.src_rank : owner;
-  return p.peer[owner] + ((size_t)(blk * p.ncomp_tot + p.comp0 + comp) * p.NML + im) * p.NPL + local;
+  return p.peer[owner] + ph_index(blk, p.ncomp_tot, p.comp0 + comp, p.NML, p.NPL, im, local, p.ring_major);
 }
 // synthesis output: the ring owner's buffer (its own on one GPU, peer-mapped over NVLink
 // otherwise), block of the writing rank
@@ -74,7 +75,7 @@ __device__ __forceinline__ double4 *ph_out(const KParams &p, int comp, int im, i
   const int slot = p.wslot ? p.wslot[work] : work;
   int owner = slot / p.NPL, local = slot - owner * p.NPL;
   const int blk = p.src_rank >= 0 ? p.src_rank : owner;
-  return p.peer[owner] + ((size_t)(blk * p.ncomp_tot + p.comp0 + comp) * p.NML + im) * p.NPL + local;
+  return p.peer[owner] + ph_index(blk, p.ncomp_tot, p.comp0 + comp, p.NML, p.NPL, im, local, p.ring_major);
 }
 
 // 16-byte asynchronous global -> shared copies (LDGSTS): every kernel stages its per-l
@@ -872,6 +873,7 @@ static KParams make_params(const LegGeom &g, const LegAlm &a, double *alm0, doub
   p.lmax = a.lmax; p.nm = a.nm; p.real_packed = a.real_packed;
   p.spin = a.spin; p.spinsign = (a.spin & 1) ? 1.0 : -1.0;
   p.slot_begin = g.slot_begin; p.nslots = g.slot_end >= 0 ? g.slot_end : g.nslots; p.NPL = g.NPL; p.NML = g.NML; p.ncomp_tot = g.ncomp_tot; p.comp0 = g.comp0;
+  p.ring_major = phase_ring_major() ? 1 : 0;
   p.mval = a.mval; p.mvstart = a.mvstart; p.coef = a.coef; p.cofs = a.cofs; p.Kstart = a.Kstart;
   p.tofs = nullptr; p.trows = nullptr;
   p.im0 = a.im_begin;

@@ -43,6 +43,7 @@ struct FParams {
   double *map0, *map1, *map2;
   const double *ps0, *ps1, *ps2;   // optional factor per local pixel on the synthesised map (nullptr: 1)
   int weighted, add;
+  int ring_major;                  // phase layout inside a block (kernels.h: ph_index)
 };
 
 __device__ __forceinline__ size_t zoff(const FParams &p, int pair, int c) {
@@ -57,6 +58,10 @@ __device__ __forceinline__ double2 expipi(long long num, int n) {
 }
 __device__ __forceinline__ double2 cmul(double2 a, double2 b) {
   return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+// phase element of (m owner `src`, its local m index `im`) for component c and local ring pair `pair`
+__device__ __forceinline__ double4 *ph_at(const FParams &p, const PhaseLayout &L, int src, int c, int im, int pair) {
+  return p.ph + ph_index(src, L.ncomp_tot, L.comp0 + c, L.NML, L.NPL, im, L.pair0 + pair, p.ring_major);
 }
 __device__ __forceinline__ double *map_ptr(const FParams &p, int c) {
   return c == 0 ? p.map0 : (c == 1 ? p.map1 : p.map2);
@@ -73,7 +78,7 @@ __device__ __forceinline__ double2 fold_one(const FParams &p, const PhaseLayout 
                                             bool shifted, int m, bool conj_term) {
   int src = L.m2src[m];
   if (src < 0) return make_double2(0.0, 0.0);
-  double4 q = p.ph[((size_t)(src * L.ncomp_tot + L.comp0 + c) * L.NML + L.m2im[m]) * L.NPL + L.pair0 + pair];
+  double4 q = *ph_at(p, L, src, c, L.m2im[m], pair);
   double2 e = shifted ? expipi(m, n) : make_double2(1.0, 0.0);
   double2 pn = cmul(make_double2(q.x, q.y), e), ps = cmul(make_double2(q.z, q.w), e);
   if (conj_term) return make_double2(pn.x + ps.y, -pn.y + ps.x);       // conj p_m
@@ -154,7 +159,7 @@ __global__ void __launch_bounds__(256) fold_transpose_kernel(FParams p, int firs
     int e = e0 + r, pr = p0 + tx;
     double4 q = make_double4(0, 0, 0, 0);
     if (e < L.nm_total && pr < npairs_r)
-      q = p.ph[((size_t)(L.mlist_src[e] * L.ncomp_tot + L.comp0 + c) * L.NML + L.mlist_im[e]) * L.NPL + L.pair0 + first_pair + pr];
+      q = *ph_at(p, L, L.mlist_src[e], c, L.mlist_im[e], first_pair + pr);
     tile[r][tx] = q;
   }
   __syncthreads();
@@ -266,8 +271,7 @@ __device__ __forceinline__ void unfold_from(const FParams &p, int pair, int c, c
     double2 f = make_double2(cm, 0.0);
     if (shifted) { double2 t = expipi(m, n); f = make_double2(cm * t.x, -cm * t.y); }
     xn = cmul(xn, f); xs = cmul(xs, f);
-    p.ph[((size_t)(L.mlist_src[e] * L.ncomp_tot + L.comp0 + c) * L.NML + L.mlist_im[e]) * L.NPL + L.pair0 + pair] =
-        make_double4(xn.x, xn.y, xs.x, xs.y);
+    *ph_at(p, L, L.mlist_src[e], c, L.mlist_im[e], pair) = make_double4(xn.x, xn.y, xs.x, xs.y);
   }
 }
 __global__ void __launch_bounds__(256) unfold_kernel(FParams p, int first_pair) {
@@ -407,7 +411,7 @@ __device__ __forceinline__ double2 fold_bin(const FParams &p, const PhaseLayout 
   for (int m = k; m <= L.mmax; m += n, sg = shifted ? -sg : sg) {            // m == k: p_m
     const int src = L.m2src[m];
     if (src < 0) continue;
-    const double4 q = p.ph[((size_t)(src * L.ncomp_tot + L.comp0 + c) * L.NML + L.m2im[m]) * L.NPL + L.pair0 + pair];
+    const double4 q = *ph_at(p, L, src, c, L.m2im[m], pair);
     if (m == 0) { acc.x += q.x; acc.y += q.z; }
     else { acc.x += sg * (q.x - q.w); acc.y += sg * (q.y + q.z); }
   }
@@ -415,10 +419,54 @@ __device__ __forceinline__ double2 fold_bin(const FParams &p, const PhaseLayout 
   for (int m = n - k; m <= L.mmax; m += n, sg = shifted ? -sg : sg) {        // m == -k, m >= 1: conj p_m
     const int src = L.m2src[m];
     if (src < 0) continue;
-    const double4 q = p.ph[((size_t)(src * L.ncomp_tot + L.comp0 + c) * L.NML + L.m2im[m]) * L.NPL + L.pair0 + pair];
+    const double4 q = *ph_at(p, L, src, c, L.m2im[m], pair);
     acc.x += sg * (q.x + q.w); acc.y += sg * (q.z - q.y);
   }
   return acc;
+}
+
+// The same folded spectrum for a ring with n > mmax (no aliasing: bin k receives at most the direct term of m = k and
+// the conjugate term of m = n - k), m-major: every thread takes NB phases per round, all NB loads in flight before the
+// first is used (the bin-major form above chains table look-up -> phase load -> next bin, which left the 16-warp CTAs
+// of the whole-ring kernels waiting on DRAM latency).  The two contributions of a bin come from different threads and
+// are added with shared-memory atomics; two addends commute, so the result stays bitwise reproducible.
+// slot(k): position of bin k in z;  fac(k): factor of bin k (phi0 shift, chirp).  z must hold n zeroed slots on return
+// of the first barrier; ends with a barrier.
+template <int NT, int NB, class Slot, class Fac>
+__device__ __forceinline__ void fold_noalias(const FParams &p, const PhaseLayout &L, int c, int pair, int n, bool shifted, double2 *z,
+                                             Slot slot, Fac fac) {
+  for (int k = threadIdx.x; k < n; k += NT) z[slot(k)] = make_double2(0.0, 0.0);
+  __syncthreads();
+  const double sgc = shifted ? -1.0 : 1.0;        // e^{i pi m / n} of m = -k + n leaves (-1) next to e^{i pi k / n}
+  for (int m0 = threadIdx.x; m0 <= L.mmax; m0 += NT * NB) {
+    double4 q[NB];
+    bool ok[NB];
+#pragma unroll
+    for (int j = 0; j < NB; ++j) {
+      const int m = m0 + j * NT;
+      const int src = m <= L.mmax ? L.m2src[m] : -1;
+      ok[j] = src >= 0;
+      if (ok[j]) q[j] = *ph_at(p, L, src, c, L.m2im[m], pair);
+    }
+#pragma unroll
+    for (int j = 0; j < NB; ++j) {
+      if (!ok[j]) continue;
+      const int m = m0 + j * NT;
+      if (m == 0) {
+        const double2 v = cmul(make_double2(q[j].x, q[j].z), fac(0));
+        double2 *d = z + slot(0);
+        atomicAdd(&d->x, v.x); atomicAdd(&d->y, v.y);
+      } else {
+        const double2 v = cmul(make_double2(q[j].x - q[j].w, q[j].y + q[j].z), fac(m));
+        double2 *d = z + slot(m);
+        atomicAdd(&d->x, v.x); atomicAdd(&d->y, v.y);
+        const double2 u = cmul(make_double2(sgc * (q[j].x + q[j].w), sgc * (q[j].z - q[j].y)), fac(n - m));
+        double2 *e = z + slot(n - m);
+        atomicAdd(&e->x, u.x); atomicAdd(&e->y, u.y);
+      }
+    }
+  }
+  __syncthreads();
 }
 
 // phases of all m from the two DFT- bins Z_k, Z_{n-k} of z = w (x_north + i x_south)
@@ -432,8 +480,7 @@ __device__ __forceinline__ void unfold_store(const FParams &p, const PhaseLayout
   double2 f = make_double2(cm, 0.0);
   if (shifted) { double2 t = expipi(m, n); f = make_double2(cm * t.x, -cm * t.y); }
   xn = cmul(xn, f); xs = cmul(xs, f);
-  p.ph[((size_t)(L.mlist_src[e] * L.ncomp_tot + L.comp0 + c) * L.NML + L.mlist_im[e]) * L.NPL + L.pair0 + pair] =
-      make_double4(xn.x, xn.y, xs.x, xs.y);
+  *ph_at(p, L, L.mlist_src[e], c, L.mlist_im[e], pair) = make_double4(xn.x, xn.y, xs.x, xs.y);
 }
 
 // ---- long polar-cap rings (n = 4 i, chirp-z work length of the whole ring too large for shared memory): radix-4
@@ -453,8 +500,13 @@ __global__ void __launch_bounds__(NT) ring_split_kernel(FParams p, int first_pai
   const long long oN = p.ofsN[pair], oS = p.ofsS[pair];
   if (DIR == 0) {
     // folded spectrum, phi0 shift and input chirp in one factor per bin
-    for (int k = threadIdx.x; k < n; k += NT)
-      zbuf[rs_slot(k, i)] = cmul(fold_bin(p, L, c, pair, n, shifted, k), rs_expipi(rs_fold_angle(k, shifted), n));
+    if (n > L.mmax) {
+      fold_noalias<NT, 4>(p, L, c, pair, n, shifted, zbuf, [i](int k) { return rs_slot(k, i); },
+                          [n, shifted](int k) { return rs_expipi(rs_fold_angle(k, shifted), n); });
+    } else {
+      for (int k = threadIdx.x; k < n; k += NT)
+        zbuf[rs_slot(k, i)] = cmul(fold_bin(p, L, c, pair, n, shifted, k), rs_expipi(rs_fold_angle(k, shifted), n));
+    }
   } else {
     // radix-4 pass over conj(z), twiddle and input chirp
     const double *mp = map_ptr(p, c);
@@ -548,12 +600,18 @@ __global__ void __launch_bounds__(NT) ring_pow2_kernel(FParams p, int first_pair
   for (int k = threadIdx.x; k < ntw; k += NT) T[k] = tw[k];
   const long long oN = p.ofsN[pair], oS = p.ofsS[pair];
   if (DIR == 0) {
-    for (int k = threadIdx.x; k < n; k += NT) {
-      double2 z = fold_bin(p, L, c, pair, n, shifted, k);
-      if (shifted) z = cmul(z, rs_expipi(k, n));
-      work[bf_pidx<true>((int)(__brev((unsigned)k) >> (32 - bits)))] = z;
+    auto slot = [bits](int k) { return bf_pidx<true>((int)(__brev((unsigned)k) >> (32 - bits))); };
+    if (n > L.mmax) {
+      fold_noalias<NT, 4>(p, L, c, pair, n, shifted, work, slot,
+                          [n, shifted](int k) { return shifted ? rs_expipi(k, n) : make_double2(1.0, 0.0); });
+    } else {
+      for (int k = threadIdx.x; k < n; k += NT) {
+        double2 z = fold_bin(p, L, c, pair, n, shifted, k);
+        if (shifted) z = cmul(z, rs_expipi(k, n));
+        work[slot(k)] = z;
+      }
+      __syncthreads();
     }
-    __syncthreads();
     sm_fft_dit<NT>(work, n, T);
     double *mp = map_ptr(p, c);
     const double *ps = ps_ptr(p, c);
@@ -616,6 +674,7 @@ static FParams base_params(sharp_geom_info *g, int ncomp, const PhaseLayout &L, 
   p.wgt = g->d_wgt; p.buf = buf; p.vtab = reinterpret_cast<const double2 *>(g->d_vtab);
   p.L = L; p.ph = nullptr; p.map0 = p.map1 = p.map2 = nullptr; p.weighted = 0; p.add = 0;
   p.ps0 = p.ps1 = p.ps2 = nullptr;
+  p.ring_major = phase_ring_major() ? 1 : 0;
   return p;
 }
 
