@@ -258,9 +258,12 @@ class cr_system:
     with a prior, 0 on the others; sqrt(S) = 1 on the latter).  x is the flat vector of cr_extract_comp /
     cr_insert_comp (:408-540): component after component, each (nmaps, nalm) in memory order."""
 
-    def __init__(self, comps, bands, device):
+    def __init__(self, comps, bands, device, precond: str = "diagonal"):
         import torch
         from .comm_diffuse_comp import diffuse_band
+        if precond not in ("diagonal", "pseudoinv"):
+            raise ValueError("Preconditioner type not supported: " + precond)
+        self.precond = precond
         self.torch, self.dev = torch, device
         self.comps, self.bands = list(comps), list(bands)
         self.off = [0]
@@ -440,9 +443,107 @@ class cr_system:
             k = pre.lm2i_vec(c.x_info.lm[0], c.x_info.lm[1])
             self.pre_idx.append(torch.as_tensor(k, device=self.dev))
 
-    def invM(self, r):
-        """applyDiffPrecond_diagonal, :2186-2235."""
+    # -- pseudo-inverse preconditioner
+    def compute_alpha_nu(self, q):
+        """N%alpha_nu of band q for the pseudo-inverse preconditioner (commander3/src/comm_N_rms_mod.f90:218-247):
+        tau = Y Yt (siN^2), alpha = sqrt(sum tau^2 / sum tau), T alone and Q,U together."""
         torch = self.torch
+        b = self.bands[q]
+        m = comm_map(b.info, device=self.dev)
+        m.map.copy_(b.invN)
+        m.Yt()
+        m.Y()
+        nm = b.info.nmaps
+        groups = [slice(0, 1)] + ([slice(1, 3)] if nm == 3 else [])
+        alpha = torch.zeros(nm, dtype=torch.float64, device=self.dev)
+        for g in groups:
+            t = torch.stack([m.map[g].sum(), (m.map[g] ** 2).sum()])
+            self._allreduce(t)
+            alpha[g] = torch.sqrt(t[1] / t[0]) if float(t[0]) > 0.0 else 0.0
+        return alpha.cpu().numpy()
+
+    def initDiffPrecond_pseudoinv(self):
+        """initDiffPrecond_pseudoinv + updateDiffPrecond_pseudoinv, commander3/src/comm_diffuse_comp_mod.f90:1255-1294,
+        1560-1658: per (l, pol) the (numband + npre) x npre matrix V = [alpha_nu b_l F sqrt(S); P] and its pseudo-inverse."""
+        torch = self.torch
+        npre, nb = len(self.comps), len(self.bands)
+        nmaps_pre = max(c.nmaps for c in self.comps)
+        b0 = self.bands[0].info
+        pre = comm_mapinfo(b0.comm, b0.nside, self.lmax, nmaps_pre, nmaps_pre == 3)
+        self.info_pre = pre
+        self.alpha_nu = [self.compute_alpha_nu(q) for q in range(nb)]
+        V = np.zeros((nmaps_pre, self.lmax + 1, nb + npre, npre))
+        for j in range(nmaps_pre):
+            for q, b in enumerate(self.bands):
+                if j >= b.info.nmaps:
+                    continue
+                lb = min(b.info.lmax, self.lmax)
+                for k, c in enumerate(self.comps):
+                    if j >= c.nmaps:
+                        continue
+                    lk = min(lb, c.lmax_amp)
+                    v = self.alpha_nu[q][j] * b.b_l[:lk + 1, j] * c.F_mean[q, j]
+                    if c.Cl is not None:
+                        v = v * np.sqrt(np.maximum(c.Cl[:lk + 1, j], 0.0))
+                        if j > 0:
+                            v[:2] = 0.0          # sqrt(S) carries no l < 2 polarisation modes (matmulA zeroes them too)
+                    V[j, :lk + 1, q, k] = v
+            for k, c in enumerate(self.comps):
+                if c.Cl is not None and j < c.nmaps:
+                    V[j, :c.lmax_amp + 1, nb + k, k] = 1.0
+        self.pinvV = torch.linalg.pinv(torch.as_tensor(V, device=self.dev))     # (nmaps_pre, lmax+1, npre, nb + npre)
+        self.pre_idx = []
+        for c in self.comps:
+            self.pre_idx.append(torch.as_tensor(pre.lm2i_vec(c.x_info.lm[0], c.x_info.lm[1]), device=self.dev))
+        self.l_pre = torch.as_tensor(pre.lm[0].astype(np.int64), device=self.dev)
+        # band layout <-> info_pre layout (:2277-2279: `if (l > info_pre%lmax) cycle; call info_pre%lm2i(l,m,j)`)
+        self.band_pre = []
+        for b in self.bands:
+            j = pre.lm2i_vec(b.info.lm[0], b.info.lm[1])
+            ok = (j >= 0) & (b.info.lm[0] <= pre.lmax)
+            self.band_pre.append((torch.as_tensor(np.nonzero(ok)[0], device=self.dev), torch.as_tensor(j[ok], device=self.dev),
+                                  torch.as_tensor(b.info.lm[0][ok].astype(np.int64), device=self.dev)))
+        self.Nmap = [torch.where(b.invN > 0, 1.0 / b.invN.clamp_min(1e-300), torch.zeros_like(b.invN)) for b in self.bands]
+
+    def invM_pseudoinv(self, r):
+        """applyDiffPrecond_pseudoinv, commander3/src/comm_diffuse_comp_mod.f90:2237-2380."""
+        torch = self.torch
+        if getattr(self, "pinvV", None) is None:
+            self.initDiffPrecond_pseudoinv()
+        npre, nb = len(self.comps), len(self.bands)
+        nmaps_pre, nalm_pre = self.info_pre.nmaps, self.info_pre.nalm
+        y = torch.zeros((npre, nmaps_pre, nalm_pre), dtype=torch.float64, device=self.dev)           # :2255-2268
+        for i, c in enumerate(self.comps):
+            y[i, :c.nmaps, self.pre_idx[i]] = self.extract_comp(i, r)
+        z = torch.zeros_like(y)
+        for q, b in enumerate(self.bands):                                                           # :2271-2318
+            m = comm_map(b.info, device=self.dev)
+            bi, pj, lb = self.band_pre[q]
+            nm = b.info.nmaps
+            for p_ in range(min(nm, nmaps_pre)):
+                Mq = self.pinvV[p_, lb, :, q]                       # (n, npre): M(qq, k) at this slot's l
+                m.alm[p_, bi] = (Mq * y[:, p_, pj].T).sum(dim=1)    # sum over (U^plus)^t
+            m.WY()                                                  # :2288
+            m.map.mul_(self.Nmap[q])                                # N%N
+            m.YtW()                                                 # :2292
+            for p_ in range(nm):
+                m.alm[p_].mul_(float(self.alpha_nu[q][p_]) ** 2)    # :2293-2295
+            for p_ in range(min(nm, nmaps_pre)):
+                Mq = self.pinvV[p_, lb, :, q]
+                z[:, p_, pj] += (Mq * m.alm[p_, bi][:, None]).T     # sum over U^plus
+        Mp = self.pinvV[:, self.l_pre][..., nb:]                     # (nmaps_pre, nalm_pre, npre, npre): prior columns, :2322-2346
+        w2 = torch.einsum("jakb,kja->bja", Mp, y)                    # w2(j) = sum_k M(k, numband + j) w(k)
+        z += torch.einsum("jakb,bja->kja", Mp, w2)                   # w(j)  = sum_k M(j, numband + k) w2(k)
+        out = torch.empty_like(r)
+        for i, c in enumerate(self.comps):                           # :2350-2363
+            self.extract_comp(i, out).copy_(z[i, :c.nmaps, self.pre_idx[i]])
+        return out
+
+    def invM(self, r):
+        """cr_invM: applyDiffPrecond_diagonal (:2186-2235) or, with precond = 'pseudoinv', applyDiffPrecond_pseudoinv."""
+        torch = self.torch
+        if getattr(self, "precond", "diagonal") == "pseudoinv":
+            return self.invM_pseudoinv(r)
         if self.Minv is None:
             self.initDiffPrecond_diagonal()
         npre = len(self.comps)

@@ -209,3 +209,84 @@ def test_multi_component_cg(shtlib, cpu_oracle):
     Ax = np.concatenate([v.ravel() for v in _oracle_A(S, bands, comps, xs)])
     bb = b.cpu().numpy()
     assert np.linalg.norm(Ax - bb) <= 1e-4 * np.linalg.norm(bb)
+
+
+def _oracle_pseudoinv(S, bands, comps, r_parts):
+    """applyDiffPrecond_pseudoinv (commander3/src/comm_diffuse_comp_mod.f90:2237-2380) with alpha_nu
+    (comm_N_rms_mod.f90:218-247) and the per-(l, pol) pseudo-inverse (:1560-1658), composed from oracle transforms."""
+    lmax_pre = max(max(c["lmax"] for c in comps), 2)
+    nb, npre = len(bands), len(comps)
+    lp, mp_, pos_pre = _lm(lmax_pre)
+    alpha = []
+    for b in bands:
+        tau = _Y(S, b["nside"], b["lmax"], _Yt(S, b["nside"], b["lmax"], b["invN"]))
+        a = np.zeros(3)
+        a[0] = np.sqrt((tau[0] ** 2).sum() / tau[0].sum())
+        a[1:] = np.sqrt((tau[1:] ** 2).sum() / tau[1:].sum())
+        alpha.append(a)
+    M = np.zeros((3, lmax_pre + 1, npre, nb + npre))
+    for j in range(3):
+        for l in range(lmax_pre + 1):
+            V = np.zeros((nb + npre, npre))
+            for q, b in enumerate(bands):
+                if l > b["lmax"]:
+                    continue
+                for k, c in enumerate(comps):
+                    if l > c["lmax"] or j >= c["nmaps"]:
+                        continue
+                    V[q, k] = alpha[q][j] * b["b_l"][l, j] * c["F_mean"][q, j]
+                    if c["Cl"] is not None:
+                        V[q, k] *= 0.0 if (j > 0 and l < 2) else np.sqrt(c["Cl"][l, j])
+            for k, c in enumerate(comps):
+                if c["Cl"] is not None and l <= c["lmax"] and j < c["nmaps"]:
+                    V[nb + k, k] = 1.0
+            M[j, l] = np.linalg.pinv(V)
+    y = np.zeros((npre, 3, lp.size))
+    for i, (c, r) in enumerate(zip(comps, r_parts)):
+        y[i] = _repack(r, c["lmax"], lmax_pre, nmaps_to=3)
+    z = np.zeros_like(y)
+    for q, b in enumerate(bands):
+        lb, mb, _ = _lm(b["lmax"])
+        sel = lb <= lmax_pre
+        jpre = np.array([pos_pre[(int(a), int(c_))] for a, c_ in zip(lb[sel], mb[sel])])
+        alm = np.zeros((3, lb.size))
+        for p_ in range(3):
+            alm[p_, sel] = np.einsum("nk,kn->n", M[p_, lb[sel], :, q], y[:, p_, jpre])
+        wpix = 4 * np.pi / (12 * b["nside"] ** 2)
+        mp = _Y(S, b["nside"], b["lmax"], alm) * wpix                     # WY with unit ring weights
+        mp = np.where(b["invN"] > 0, mp / np.where(b["invN"] > 0, b["invN"], 1.0), 0.0)
+        back = _Yt(S, b["nside"], b["lmax"], mp, job=S.YtW) * (alpha[q] ** 2)[:, None]
+        for p_ in range(3):
+            z[:, p_, jpre] += (M[p_, lb[sel], :, q] * back[p_, sel][:, None]).T
+    Mp = M[:, lp][..., nb:]
+    w2 = np.einsum("jakb,kja->bja", Mp, y)
+    z += np.einsum("jakb,bja->kja", Mp, w2)
+    return [_repack(z[i], lmax_pre, c["lmax"], nmaps_to=c["nmaps"]) for i, c in enumerate(comps)]
+
+
+def test_pseudoinv_preconditioner_vs_oracle(shtlib, cpu_oracle):
+    """precond_type 'pseudoinv' for the general system: one application against the same operator composed from oracle
+    transforms (1e-9: two pinv implementations), symmetry, and PCG with it reaching the solution of the diagonal run."""
+    import torch
+    from commander_b200.comm_cr import solve_cr_eqn_by_CG
+    S = cpu_oracle
+    dev = torch.device("cuda", 0)
+    bands, comps, rng = _problem(6, False)
+    sysd = _build(bands, comps, dev)
+    sysp = _build(bands, comps, dev)
+    sysp.precond = "pseudoinv"
+    rs = [rng.standard_normal((c["nmaps"], _lm(c["lmax"])[0].size)) for c in comps]
+    r = torch.as_tensor(np.concatenate([v.ravel() for v in rs]), device=dev)
+    got = sysp.invM(r).cpu().numpy()
+    ref = np.concatenate([v.ravel() for v in _oracle_pseudoinv(S, bands, comps, rs)])
+    assert rel(got, ref) <= 1e-9, rel(got, ref)
+    r2 = torch.as_tensor(rng.standard_normal(sysp.ncr), device=dev)
+    a, b = float(torch.dot(r2, sysp.invM(r))), float(torch.dot(r, sysp.invM(r2)))
+    assert abs(a - b) <= 1e-10 * max(abs(a), abs(b))
+    data = [torch.as_tensor(rng.standard_normal((3, 12 * b_["nside"] ** 2)) / np.sqrt(b_["invN"]), device=dev) for b_ in bands]
+    rhs = sysd.computeRHS(data)
+    xd, itd, _ = solve_cr_eqn_by_CG(sysd, rhs, maxiter=800, cg_tol=1e-12, cg_conv_crit="residual")
+    xp, itp, _ = solve_cr_eqn_by_CG(sysp, rhs, maxiter=800, cg_tol=1e-12, cg_conv_crit="residual")
+    assert float((xd - xp).norm() / xd.norm()) <= 1e-4, (itd, itp)
+    assert itp < 800 and itd < 800
+    print("CG iterations: diagonal", itd, "pseudoinv", itp)

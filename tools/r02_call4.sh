@@ -2,7 +2,7 @@
 # round-2 GPU call 4: ring-major phase layout + m-major fold: parity + timing; DMMA microbenchmark; pageable pipeline trace
 cd "$GRAFT_REPO_ROOT" 2>/dev/null || cd /root/repo
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_mix.py tests/test_gpu_conviqt.py -m gpu -x -q > gpurun_out/r02_tests4.log 2>&1; echo "pytest rc=$?" >> gpurun_out/r02_tests4.log
+timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_mix.py tests/test_gpu_conviqt.py tests/test_gpu_cr_multi.py -m gpu -x -q > gpurun_out/r02_tests4.log 2>&1; echo "pytest rc=$?" >> gpurun_out/r02_tests4.log
 tail -4 gpurun_out/r02_tests4.log
 CMDR_SHT_PH_LAYOUT=m timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "all_jobs or ring_fft_paths or midsize or full_size_vs_oracle" > gpurun_out/r02_tests4m.log 2>&1; echo "pytest(m-major) rc=$?"; tail -2 gpurun_out/r02_tests4m.log
 B="python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-cg --no-batch --no-conviqt --no-parity --e2e-steps 2"
