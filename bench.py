@@ -16,7 +16,8 @@ One "step" = one pair = comm_map%Y() followed by comm_map%YtW() on an IQU object
 
 N > 1 (torchrun): ONE transform pair distributed over N GPUs exactly as libsharp's MPI mode
 shards it (m's and ring pairs round-robin, commander3/src/comm_map_mod.f90:197-261) with an
-NCCL all-to-all of the phases -> strong scaling.
+the m <-> ring exchange of the phases fused into the Legendre kernels over NVLink (NCCL all-to-all as fallback)
+-> strong scaling.
 
 --impl reference times the CPU path (all host threads) on the same config/metric.
 """
@@ -69,10 +70,11 @@ def workload(args):
             "l2_policy": "inputs larger than L2 (alm 0.38 GB, map 1.2 GB, phases 1.6 GB per direction)",
             "parallelism": "m-distributed alm / ring-distributed map; m<->ring exchange fused into the Legendre kernels over NVLink "
                            "(NCCL all-to-all as fallback)",
-            "ring_fft": ("cuFFT for every ring class" if os.environ.get("CMDR_SHT_FUSED_BLUE", "1") == "0" else
-                         "fused chirp-z kernel for the polar-cap classes with work length <= 8192"
-                         + (" (register-blocked variant)" if os.environ.get("CMDR_SHT_FFT_BLOCKED", "0") not in ("", "0") else "")
-                         + ", cuFFT for the belt and the 16384 classes")}
+            "ring_fft": "one shared-memory kernel per ring class, no cuFFT at this size: whole-ring chirp-z (work length <= 8192), "
+                        "radix-4 split chirp-z (4 x work length 4096) for the cap rings longer than 4096, whole-ring FFT for the belt"
+                        + "".join(f"; {k}={os.environ[k]}" for k in ("CMDR_SHT_FUSED_BLUE", "CMDR_SHT_RING_SPLIT", "CMDR_SHT_BELT_FUSED",
+                                                                    "CMDR_SHT_FFT_BLOCKED", "CMDR_SHT_SPLIT_MIN", "CMDR_SHT_PH_LAYOUT")
+                                  if k in os.environ)}
 
 
 # ------------------------------------------------------------------ CPU baseline / reference arm

@@ -648,13 +648,15 @@ static bool try_pipelined(int type, int spin, double *const *alm, double *const 
       cudaEvent_t e0 = pooled_event(ns + 1);               // earlier work on `st` may still read the staging buffer
       CMDR_CUDA_CHECK(cudaEventRecord(e0, st));
       CMDR_CUDA_CHECK(cudaStreamWaitEvent(cs, e0, 0));
-      for (int j = 0; j < nmch; ++j) {
-        const long long b = mstart[mcut[j]], e = mstart[mcut[j + 1]];
-        for (int c = 0; c < ncomp; ++c) ioA.h2d(alm_dev[c] + b, c, b, e - b, cs);
-        CMDR_CUDA_CHECK(cudaEventRecord(pooled_event(ns + 2 + j), cs));
-        mark("up", j, cs);
-      }
     }
+    // m-chunk j: upload on the copy stream (for pageable caller arrays the copy threads stage it first, which blocks
+    // this thread -- hence the kernels of chunk j are queued right behind its upload, not after all uploads)
+    auto upload_mchunk = [&](int j) {
+      const long long b = mstart[mcut[j]], e = mstart[mcut[j + 1]];
+      for (int c = 0; c < ncomp; ++c) ioA.h2d(alm_dev[c] + b, c, b, e - b, cs);
+      CMDR_CUDA_CHECK(cudaEventRecord(pooled_event(ns + 2 + j), cs));
+      mark("up", j, cs);
+    };
     // The first `nj` ring-pair chunks share the m-chunked start: per m-chunk the Legendre kernels of all of
     // them run before the next m-chunk is needed, so the a_lm upload (4.7 ms for spin 2 at lmax 4000) hides
     // behind nj chunks of compute instead of one.
@@ -682,6 +684,7 @@ static bool try_pipelined(int type, int spin, double *const *alm, double *const 
       if (as != st) CMDR_CUDA_CHECK(cudaStreamWaitEvent(as, pooled_event(ns + 1), 0));   // e0: earlier work on st
       for (int j = 0; j < nmch; ++j) {
         cudaStream_t sj = (j & 1) ? as : st;
+        upload_mchunk(j);
         CMDR_CUDA_CHECK(cudaStreamWaitEvent(sj, pooled_event(ns + 2 + j), 0));
         LegAlm Aj = A;
         Aj.im_begin = mcut[j]; Aj.im_end = mcut[j + 1];

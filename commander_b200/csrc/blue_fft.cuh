@@ -106,8 +106,12 @@ BF_HD int bf_tw_total(int M) { return bf_tw_offset(M, bf_num_passes(M)); }
 // Schedule (bf2_*): passes of 3 or 4 stages with st >= 16 down to half-size 16, then ONE pass of 4 stages on 16
 // consecutive elements per item (st = 1).  With the padding a thread's 16 consecutive elements are 17 slots from its
 // neighbour's, and every strided pass reads 8 consecutive slots per quarter warp: no bank conflicts in any pass.
+// A second, coarser pad (one slot per 256 elements) makes the bit-reversed accesses of the whole-ring transforms
+// conflict free as well: consecutive bins sit M/32 elements apart after bit reversal, a multiple of 256, which
+// the 17/16 pad alone maps to one bank group (ring_pow2_kernel's fold and unfold ran 32-way conflicted).
 template <bool PAD>
-BF_HD int bf_pidx(int i) { return PAD ? i + (i >> 4) : i; }
+BF_HD int bf_pidx(int i) { return PAD ? i + (i >> 4) + (i >> 8) : i; }
+BF_HD int bf_padded(int M) { return M + (M >> 4) + (M >> 8) + 1; }    // slots of a padded array of M elements
 
 BF_HD double2 bf_root(int k, int d) {          // exp(-i pi k / d), d in {1, 2, 4, 8}, 0 <= k < d (constants after unrolling)
   const double c8[8] = {1.0, 0.92387953251128675613, 0.70710678118654752440, 0.38268343236508977173,

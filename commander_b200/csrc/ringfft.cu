@@ -326,10 +326,10 @@ __global__ void __launch_bounds__(NT) blue_fused_kernel(FParams p, int first_pai
 template <int DIR, int NT>
 __global__ void __launch_bounds__(NT) blue_fused2_kernel(FParams p, int first_pair, int M, const double2 *__restrict__ tw,
                                                          const double2 *__restrict__ vbr) {
-  extern __shared__ double2 u_sm[];                 // M + M/16 work slots, then the twiddle table
+  extern __shared__ double2 u_sm[];                 // bf_padded(M) work slots, then the twiddle table
   __shared__ double2 part_sum[DIR == 0 ? NT : 1];
   const int pair = first_pair + blockIdx.x, c = blockIdx.y;
-  double2 *T = u_sm + M + (M >> 4);
+  double2 *T = u_sm + bf_padded(M);
   const int ntw = bf2_tw_total(M);
   for (int k = threadIdx.x; k < ntw; k += NT) T[k] = tw[k];
   if (DIR == 0) fold_into<NT, true>(p, pair, c, u_sm, M, part_sum); else gather_into<true>(p, pair, c, u_sm);
@@ -425,48 +425,58 @@ __device__ __forceinline__ double2 fold_bin(const FParams &p, const PhaseLayout 
   return acc;
 }
 
-// The same folded spectrum for a ring with n > mmax (no aliasing: bin k receives at most the direct term of m = k and
-// the conjugate term of m = n - k), m-major: every thread takes NB phases per round, all NB loads in flight before the
-// first is used (the bin-major form above chains table look-up -> phase load -> next bin, which left the 16-warp CTAs
-// of the whole-ring kernels waiting on DRAM latency).  The two contributions of a bin come from different threads and
-// are added with shared-memory atomics; two addends commute, so the result stays bitwise reproducible.
-// slot(k): position of bin k in z;  fac(k): factor of bin k (phi0 shift, chirp).  z must hold n zeroed slots on return
-// of the first barrier; ends with a barrier.
-template <int NT, int NB, class Slot, class Fac>
-__device__ __forceinline__ void fold_noalias(const FParams &p, const PhaseLayout &L, int c, int pair, int n, bool shifted, double2 *z,
-                                             Slot slot, Fac fac) {
-  for (int k = threadIdx.x; k < n; k += NT) z[slot(k)] = make_double2(0.0, 0.0);
-  __syncthreads();
-  const double sgc = shifted ? -1.0 : 1.0;        // e^{i pi m / n} of m = -k + n leaves (-1) next to e^{i pi k / n}
-  for (int m0 = threadIdx.x; m0 <= L.mmax; m0 += NT * NB) {
-    double4 q[NB];
-    bool ok[NB];
-#pragma unroll
-    for (int j = 0; j < NB; ++j) {
-      const int m = m0 + j * NT;
-      const int src = m <= L.mmax ? L.m2src[m] : -1;
-      ok[j] = src >= 0;
-      if (ok[j]) q[j] = *ph_at(p, L, src, c, L.m2im[m], pair);
+// The folded spectrum of a whole ring into shared memory, position-major: thread t fills position t of z, which holds
+// bin k = binof(t) (the identity, or the bit reversal the DIT transform wants -- a phase element is exactly one 32-byte
+// sector, so reading the phases in permuted order costs no extra DRAM traffic, while writing shared memory in
+// permuted order would serialise on bank conflicts).  Rings with n > mmax (no aliasing: bin k receives at most the
+// direct term of m = k and the conjugate term of m = n - k) take NB positions per thread and round with all 2 NB
+// loads in flight before the first is used; the chained table look-up -> phase load -> next bin of fold_bin left the
+// 16-warp CTAs of the whole-ring kernels waiting on DRAM latency.  fac(k): factor of bin k (phi0 shift, chirp).
+template <int NT, int NB, class BinOf, class Slot, class Fac>
+__device__ __forceinline__ void fold_positions(const FParams &p, const PhaseLayout &L, int c, int pair, int n, bool shifted, double2 *z,
+                                               BinOf binof, Slot slot, Fac fac) {
+  if (n <= L.mmax) {                                // aliasing: several m per bin
+    for (int t = threadIdx.x; t < n; t += NT) {
+      const int k = binof(t);
+      z[slot(t)] = cmul(fold_bin(p, L, c, pair, n, shifted, k), fac(k));
     }
+    return;
+  }
+  const double sgc = shifted ? -1.0 : 1.0;          // e^{i pi m / n} of m = n - k leaves (-1) next to e^{i pi k / n}
+  for (int t0 = threadIdx.x; t0 < n; t0 += NT * NB) {
+    double4 qd[NB], qc[NB];
+    bool hd[NB], hc[NB];
+    int kk[NB];
 #pragma unroll
     for (int j = 0; j < NB; ++j) {
-      if (!ok[j]) continue;
-      const int m = m0 + j * NT;
-      if (m == 0) {
-        const double2 v = cmul(make_double2(q[j].x, q[j].z), fac(0));
-        double2 *d = z + slot(0);
-        atomicAdd(&d->x, v.x); atomicAdd(&d->y, v.y);
-      } else {
-        const double2 v = cmul(make_double2(q[j].x - q[j].w, q[j].y + q[j].z), fac(m));
-        double2 *d = z + slot(m);
-        atomicAdd(&d->x, v.x); atomicAdd(&d->y, v.y);
-        const double2 u = cmul(make_double2(sgc * (q[j].x + q[j].w), sgc * (q[j].z - q[j].y)), fac(n - m));
-        double2 *e = z + slot(n - m);
-        atomicAdd(&e->x, u.x); atomicAdd(&e->y, u.y);
+      const int t = t0 + j * NT;
+      hd[j] = hc[j] = false;
+      kk[j] = 0;
+      if (t >= n) continue;
+      const int k = binof(t), m2 = n - k;
+      kk[j] = k;
+      if (k <= L.mmax) {
+        const int src = L.m2src[k];
+        if (src >= 0) { hd[j] = true; qd[j] = *ph_at(p, L, src, c, L.m2im[k], pair); }
+      }
+      if (m2 <= L.mmax) {                           // m2 >= 1 always (k < n)
+        const int src = L.m2src[m2];
+        if (src >= 0) { hc[j] = true; qc[j] = *ph_at(p, L, src, c, L.m2im[m2], pair); }
       }
     }
+#pragma unroll
+    for (int j = 0; j < NB; ++j) {
+      const int t = t0 + j * NT;
+      if (t >= n) continue;
+      double2 acc = make_double2(0.0, 0.0);
+      if (hd[j]) {
+        if (kk[j] == 0) acc = make_double2(qd[j].x, qd[j].z);
+        else acc = make_double2(qd[j].x - qd[j].w, qd[j].y + qd[j].z);
+      }
+      if (hc[j]) { acc.x += sgc * (qc[j].x + qc[j].w); acc.y += sgc * (qc[j].z - qc[j].y); }
+      z[slot(t)] = (hd[j] || hc[j]) ? cmul(acc, fac(kk[j])) : acc;
+    }
   }
-  __syncthreads();
 }
 
 // phases of all m from the two DFT- bins Z_k, Z_{n-k} of z = w (x_north + i x_south)
@@ -485,7 +495,7 @@ __device__ __forceinline__ void unfold_store(const FParams &p, const PhaseLayout
 
 // ---- long polar-cap rings (n = 4 i, chirp-z work length of the whole ring too large for shared memory): radix-4
 // split into four length-i chirp-z transforms of work length M (ring_split.cuh).  One CTA per (ring pair, component).
-// Shared memory: zbuf (n <= nmax elements, four sub-spectra r-major) | work (M + M/16) | twiddles.
+// Shared memory: zbuf (n <= nmax elements, four sub-spectra r-major) | work (bf_padded(M)) | twiddles.
 template <int DIR, int NT>
 __global__ void __launch_bounds__(NT) ring_split_kernel(FParams p, int first_pair, int M, int nmax, const double2 *__restrict__ tw,
                                                         const double2 *__restrict__ vsub) {
@@ -494,19 +504,14 @@ __global__ void __launch_bounds__(NT) ring_split_kernel(FParams p, int first_pai
   const int n = p.nph[pair], i = n >> 2;
   const bool shifted = p.shifted[pair];
   const PhaseLayout &L = p.L;
-  double2 *zbuf = u_sm, *work = u_sm + nmax, *T = work + M + (M >> 4);
+  double2 *zbuf = u_sm, *work = u_sm + nmax, *T = work + bf_padded(M);
   const int ntw = bf2_tw_total(M);
   for (int k = threadIdx.x; k < ntw; k += NT) T[k] = tw[k];
   const long long oN = p.ofsN[pair], oS = p.ofsS[pair];
   if (DIR == 0) {
     // folded spectrum, phi0 shift and input chirp in one factor per bin
-    if (n > L.mmax) {
-      fold_noalias<NT, 4>(p, L, c, pair, n, shifted, zbuf, [i](int k) { return rs_slot(k, i); },
+    fold_positions<NT, 4>(p, L, c, pair, n, shifted, zbuf, [](int t) { return t; }, [i](int t) { return rs_slot(t, i); },
                           [n, shifted](int k) { return rs_expipi(rs_fold_angle(k, shifted), n); });
-    } else {
-      for (int k = threadIdx.x; k < n; k += NT)
-        zbuf[rs_slot(k, i)] = cmul(fold_bin(p, L, c, pair, n, shifted, k), rs_expipi(rs_fold_angle(k, shifted), n));
-    }
   } else {
     // radix-4 pass over conj(z), twiddle and input chirp
     const double *mp = map_ptr(p, c);
@@ -573,7 +578,7 @@ __global__ void __launch_bounds__(NT) ring_split_filter_kernel(FParams p, int fi
   extern __shared__ double2 u_sm[];
   const int pair = first_pair + blockIdx.x;
   const int i = p.nph[pair] >> 2;
-  double2 *work = u_sm, *T = work + M + (M >> 4);
+  double2 *work = u_sm, *T = work + bf_padded(M);
   const int ntw = bf2_tw_total(M);
   for (int k = threadIdx.x; k < ntw; k += NT) T[k] = tw[k];
   for (int k = threadIdx.x; k < M; k += NT) {
@@ -595,23 +600,15 @@ __global__ void __launch_bounds__(NT) ring_pow2_kernel(FParams p, int first_pair
   const int pair = first_pair + blockIdx.x, c = blockIdx.y;
   const bool shifted = p.shifted[pair];
   const PhaseLayout &L = p.L;
-  double2 *work = u_sm, *T = work + n + (n >> 4);
+  double2 *work = u_sm, *T = work + bf_padded(n);
   const int ntw = bf2_tw_total(n);
   for (int k = threadIdx.x; k < ntw; k += NT) T[k] = tw[k];
   const long long oN = p.ofsN[pair], oS = p.ofsS[pair];
   if (DIR == 0) {
-    auto slot = [bits](int k) { return bf_pidx<true>((int)(__brev((unsigned)k) >> (32 - bits))); };
-    if (n > L.mmax) {
-      fold_noalias<NT, 4>(p, L, c, pair, n, shifted, work, slot,
+    fold_positions<NT, 4>(p, L, c, pair, n, shifted, work, [bits](int t) { return (int)(__brev((unsigned)t) >> (32 - bits)); },
+                          [](int t) { return bf_pidx<true>(t); },
                           [n, shifted](int k) { return shifted ? rs_expipi(k, n) : make_double2(1.0, 0.0); });
-    } else {
-      for (int k = threadIdx.x; k < n; k += NT) {
-        double2 z = fold_bin(p, L, c, pair, n, shifted, k);
-        if (shifted) z = cmul(z, rs_expipi(k, n));
-        work[slot(k)] = z;
-      }
-      __syncthreads();
-    }
+    __syncthreads();
     sm_fft_dit<NT>(work, n, T);
     double *mp = map_ptr(p, c);
     const double *ps = ps_ptr(p, c);
@@ -787,7 +784,7 @@ static void launch_region(sharp_geom_info *g, int ncomp, size_t r, RegionKind ki
     static bool attr = false;
     if (!attr) {
       attr = true;
-      const int smem = (int)(sizeof(double2) * (8192 + 4096 + 256 + bf2_tw_total(4096)));
+      const int smem = (int)(sizeof(double2) * (8192 + bf_padded(4096) + bf2_tw_total(4096)));
       CMDR_CUDA_CHECK(cudaFuncSetAttribute(ring_split_kernel<DIR, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
       CMDR_CUDA_CHECK(cudaFuncSetAttribute(ring_split_kernel<DIR, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
       CMDR_CUDA_CHECK(cudaFuncSetAttribute(ring_split_kernel<DIR, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -795,7 +792,7 @@ static void launch_region(sharp_geom_info *g, int ncomp, size_t r, RegionKind ki
     const int M = split_sub_len(R.len), nmax = R.len / 2;          // rings of this class have n <= len / 2 points
     const double2 *tw = twiddle_table2(M, cs);
     const double2 *vsub = reinterpret_cast<const double2 *>(g->d_vsub[(int)r]);
-    const size_t smem = sizeof(double2) * (size_t)(nmax + M + (M >> 4) + bf2_tw_total(M));
+    const size_t smem = sizeof(double2) * (size_t)(nmax + bf_padded(M) + bf2_tw_total(M));
     static const int nt = env_or("CMDR_SHT_SPLIT_NT", 0);
     const int NT = nt ? nt : (M >= 4096 ? 512 : (M >= 2048 ? 256 : 128));
     if (NT <= 128) ring_split_kernel<DIR, 128><<<grid, 128, smem, cs>>>(p, R.first, M, nmax, tw, vsub);
@@ -805,7 +802,7 @@ static void launch_region(sharp_geom_info *g, int ncomp, size_t r, RegionKind ki
     static bool attr = false;
     if (!attr) {
       attr = true;
-      const int smem = (int)(sizeof(double2) * (8192 + 512 + bf2_tw_total(8192)));
+      const int smem = (int)(sizeof(double2) * (bf_padded(8192) + bf2_tw_total(8192)));
       CMDR_CUDA_CHECK(cudaFuncSetAttribute(ring_pow2_kernel<DIR, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
       CMDR_CUDA_CHECK(cudaFuncSetAttribute(ring_pow2_kernel<DIR, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
       CMDR_CUDA_CHECK(cudaFuncSetAttribute(ring_pow2_kernel<DIR, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -814,7 +811,7 @@ static void launch_region(sharp_geom_info *g, int ncomp, size_t r, RegionKind ki
     int bits = 0;
     while ((1 << bits) < n) ++bits;
     const double2 *tw = twiddle_table2(n, cs);
-    const size_t smem = sizeof(double2) * (size_t)(n + (n >> 4) + bf2_tw_total(n));
+    const size_t smem = sizeof(double2) * (size_t)(bf_padded(n) + bf2_tw_total(n));
     if (n <= 2048) ring_pow2_kernel<DIR, 128><<<grid, 128, smem, cs>>>(p, R.first, n, bits, tw);
     else if (n <= 4096) ring_pow2_kernel<DIR, 256><<<grid, 256, smem, cs>>>(p, R.first, n, bits, tw);
     else ring_pow2_kernel<DIR, 512><<<grid, 512, smem, cs>>>(p, R.first, n, bits, tw);
@@ -825,13 +822,13 @@ static void launch_region(sharp_geom_info *g, int ncomp, size_t r, RegionKind ki
       static bool attr = false;
       if (!attr) {
         attr = true;
-        const int smem2 = (int)(sizeof(double2) * (8192 + 512 + bf2_tw_total(8192)));
+        const int smem2 = (int)(sizeof(double2) * (bf_padded(8192) + bf2_tw_total(8192)));
         CMDR_CUDA_CHECK(cudaFuncSetAttribute(blue_fused2_kernel<DIR, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2));
         CMDR_CUDA_CHECK(cudaFuncSetAttribute(blue_fused2_kernel<DIR, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2));
         CMDR_CUDA_CHECK(cudaFuncSetAttribute(blue_fused2_kernel<DIR, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2));
       }
       const double2 *tw = twiddle_table2(R.len, cs);
-      const size_t smem = sizeof(double2) * (size_t)(R.len + (R.len >> 4) + bf2_tw_total(R.len));
+      const size_t smem = sizeof(double2) * (size_t)(bf_padded(R.len) + bf2_tw_total(R.len));
       if (R.len <= 2048) blue_fused2_kernel<DIR, 128><<<grid, 128, smem, cs>>>(p, R.first, R.len, tw, vbr);
       else if (R.len <= 4096) blue_fused2_kernel<DIR, 256><<<grid, 256, smem, cs>>>(p, R.first, R.len, tw, vbr);
       else blue_fused2_kernel<DIR, 512><<<grid, 512, smem, cs>>>(p, R.first, R.len, tw, vbr);
@@ -929,9 +926,9 @@ static void ensure_vtab(sharp_geom_info *g, cudaStream_t st) {
       if (!attr) {
         attr = true;
         CMDR_CUDA_CHECK(cudaFuncSetAttribute(ring_split_filter_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)(sizeof(double2) * (4096 + 256 + bf2_tw_total(4096)))));
+                                             (int)(sizeof(double2) * (bf_padded(4096) + bf2_tw_total(4096)))));
       }
-      ring_split_filter_kernel<256><<<R.np, 256, sizeof(double2) * (size_t)(M + (M >> 4) + bf2_tw_total(M)), st>>>(p, R.first, M, tw, vs);
+      ring_split_filter_kernel<256><<<R.np, 256, sizeof(double2) * (size_t)(bf_padded(M) + bf2_tw_total(M)), st>>>(p, R.first, M, tw, vs);
       count_launch();
       continue;
     }

@@ -40,7 +40,7 @@ extern "C" void emul_fft(double *xv, int M, int dir, int nthreads) {
   }
 }
 
-// the register-blocked, padded variant (bf2_* schedule): x has M + M/16 slots
+// the register-blocked, padded variant (bf2_* schedule): x has bf_padded(M) slots
 static std::vector<double2> twiddles2(int M) {
   std::vector<double2> tw(bf2_tw_total(M));
   for (int k = 0; k < bf2_num_strided(M); ++k) {

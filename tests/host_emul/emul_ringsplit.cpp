@@ -46,7 +46,7 @@ static void convolve(double2 *x, int M, const double2 *T, const double2 *v) {
   strided<1>(x, M, T);
 }
 static std::vector<double2> sub_filter(int i, int M, const double2 *T) {     // ring_split_filter_kernel
-  std::vector<double2> w(M + (M >> 4));
+  std::vector<double2> w(bf_padded(M));
   for (int k = 0; k < M; ++k) {
     const long long j = k < i ? k : (k > M - i ? M - k : -1);
     double2 val; val.x = val.y = 0.0;
@@ -66,7 +66,7 @@ extern "C" void emul_ring_split(const double *inv, double *outv, int n, int M, i
   double2 *out = reinterpret_cast<double2 *>(outv);
   const int i = n >> 2;
   std::vector<double2> tw = twiddles2(M), v = sub_filter(i, M, tw.data());
-  std::vector<double2> zbuf(n), work(M + (M >> 4));
+  std::vector<double2> zbuf(n), work(bf_padded(M));
   if (dir == 0) {
     for (int k = 0; k < n; ++k) zbuf[rs_slot(k, i)] = cmul(in[k], rs_expipi(rs_fold_angle(k, 0), n));
   } else {
@@ -106,7 +106,7 @@ extern "C" void emul_ring_pow2(const double *inv, double *outv, int n, int dir) 
   double2 *out = reinterpret_cast<double2 *>(outv);
   int bits = 0;
   while ((1 << bits) < n) ++bits;
-  std::vector<double2> tw = twiddles2(n), work(n + (n >> 4));
+  std::vector<double2> tw = twiddles2(n), work(bf_padded(n));
   if (dir == 0) {
     for (int k = 0; k < n; ++k) work[bf_pidx<true>((int)bf_bitrev((unsigned)k, bits))] = in[k];
     fft_dit(work.data(), n, tw.data());

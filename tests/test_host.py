@@ -249,28 +249,29 @@ def test_empty_and_single_ring_handles(shtlib):
 @pytest.mark.parametrize("M", [1024, 2048, 4096, 8192])
 def test_blue_fft_register_blocked_variant_on_host(emul_fft, M):
     """The register-blocked, padded FFT pair (3-4 stages per pass, bf2_* schedule) computes the same bit-reversed
-    spectrum and the same inverse as numpy; slots i + (i >> 4) hold element i, the pad slots are never touched."""
+    spectrum and the same inverse as numpy; slots i + (i >> 4) + (i >> 8) hold element i, the pad slots are never touched."""
     rng = np.random.default_rng(M + 1)
     bits = M.bit_length() - 1
     br = np.array([emul_fft.emul_bitrev(i, bits) for i in range(M)])
-    idx = np.arange(M) + (np.arange(M) >> 4)
+    idx = np.arange(M) + (np.arange(M) >> 4) + (np.arange(M) >> 8)
+    nslots = M + M // 16 + M // 256 + 1                       # bf_padded(M)
     x = rng.standard_normal(M) + 1j * rng.standard_normal(M)
     for nthreads in (1, 5, 512):
-        buf = np.full(M + M // 16, 7.0 + 3.0j)
+        buf = np.full(nslots, 7.0 + 3.0j)
         buf[idx] = x
         emul_fft.emul_fft2(buf.ctypes.data, M, 0, nthreads)
         ref = np.fft.fft(x)
         assert np.abs(buf[idx] - ref[br]).max() <= 1e-12 * np.abs(ref).max()
         emul_fft.emul_fft2(buf.ctypes.data, M, 1, nthreads)
         assert np.abs(buf[idx] - M * x).max() <= 1e-12 * M * np.abs(x).max()
-        pad = np.setdiff1d(np.arange(M + M // 16), idx)
+        pad = np.setdiff1d(np.arange(nslots), idx)
         assert np.all(buf[pad] == 7.0 + 3.0j)
     # the whole convolution as the kernel sequences it (strided DIF passes, in-register middle with the bit-reversed
     # filter spectrum, strided DIT passes)
     v = rng.standard_normal(M) + 1j * rng.standard_normal(M)
     V = np.fft.fft(v)
     vbr = np.ascontiguousarray(V[br])
-    buf = np.full(M + M // 16, 7.0 + 3.0j)
+    buf = np.full(nslots, 7.0 + 3.0j)
     buf[idx] = x
     emul_fft.emul_conv2(buf.ctypes.data, vbr.ctypes.data, M, 33)
     conv = np.fft.ifft(np.fft.fft(x) * V) * M
