@@ -21,6 +21,7 @@
 #include <mutex>
 #include <string>
 #include <thread>
+#include <vector>
 
 #include "kernels.h"
 
@@ -62,52 +63,61 @@ class CopyPool {
     for (int i = 0; i < nw_; ++i) std::thread([this, i] { run(i); }).detach();   // live until the process exits
   }
   void copy(void *dst, const void *src, size_t n) {
-    if (n < (size_t)(1 << 20) || nw_ == 0) { memcpy(dst, src, n); return; }
+    if (n < (size_t)(256 << 10) || nw_ == 0) { memcpy(dst, src, n); return; }
+    std::lock_guard<std::mutex> job(job_mu_);                      // one job at a time (callers: the API thread)
     const int parts = nw_ + 1;
     const size_t slice = ((n / parts) + 4095) & ~(size_t)4095;
+    dst_ = static_cast<char *>(dst); src_ = static_cast<const char *>(src); n_ = n; slice_ = slice;
+    pending_.store(nw_, std::memory_order_relaxed);
     {
       std::lock_guard<std::mutex> lk(mu_);
-      dst_ = static_cast<char *>(dst); src_ = static_cast<const char *>(src); n_ = n; slice_ = slice;
-      pending_ = nw_;
-      ++gen_;
+      gen_.fetch_add(1, std::memory_order_release);
     }
     cv_.notify_all();
     do_slice(nw_);                                  // the caller takes the last slice
-    std::unique_lock<std::mutex> lk(mu_);
-    done_.wait(lk, [this] { return pending_ == 0; });
+    while (pending_.load(std::memory_order_acquire) != 0) cpu_relax();
   }
   int workers() const { return nw_; }
 
  private:
+  static void cpu_relax() {
+#if defined(__x86_64__)
+    __builtin_ia32_pause();
+#endif
+  }
   void do_slice(int i) {
     const size_t b = slice_ * (size_t)i;
     if (b >= n_) return;
     const size_t e = b + slice_ < n_ ? b + slice_ : n_;
     memcpy(dst_ + b, src_ + b, e - b);
   }
+  // Workers spin for a short while after a job before they go to sleep: the staged uploads / downloads of one
+  // transform arrive as a burst of jobs a few hundred microseconds apart, and a condition-variable wake-up per job
+  // would cost as much as a small job itself.
   void run(int i) {
     unsigned long long seen = 0;
     for (;;) {
-      {
+      bool got = false;
+      for (int spin = 0; spin < 20000 && !got; ++spin) {           // ~100-200 us
+        if (gen_.load(std::memory_order_acquire) != seen) got = true; else cpu_relax();
+      }
+      if (!got) {
         std::unique_lock<std::mutex> lk(mu_);
-        cv_.wait(lk, [&] { return gen_ != seen; });
-        seen = gen_;
+        cv_.wait(lk, [&] { return gen_.load(std::memory_order_acquire) != seen; });
       }
+      seen = gen_.load(std::memory_order_acquire);
       do_slice(i);
-      {
-        std::lock_guard<std::mutex> lk(mu_);
-        if (--pending_ == 0) done_.notify_one();
-      }
+      pending_.fetch_sub(1, std::memory_order_release);
     }
   }
   int nw_;
-  std::mutex mu_;
-  std::condition_variable cv_, done_;
+  std::mutex mu_, job_mu_;
+  std::condition_variable cv_;
   char *dst_ = nullptr;
   const char *src_ = nullptr;
   size_t n_ = 0, slice_ = 0;
-  int pending_ = 0;
-  unsigned long long gen_ = 0;
+  std::atomic<int> pending_{0};
+  std::atomic<unsigned long long> gen_{0};
 };
 
 static CopyPool *copy_pool() {
@@ -129,6 +139,40 @@ static CopyPool *copy_pool() {
 
 void host_copy(void *dst, const void *src, size_t bytes) { copy_pool()->copy(dst, src, bytes); }
 int host_copy_threads() { return copy_pool()->workers() + 1; }
+
+// ---------------------------------------------------------------- cache-resident upload ring
+// Uploads of pageable arrays do not need an arena as large as the array: the copy threads fill a small ring of pinned
+// slots with ordinary (cached) stores, the DMA engine reads each slot while it is still in the CPU's caches, and the
+// slot is reused as soon as its copy has left.  Per payload byte DRAM then sees one read (the caller's page) instead of
+// read + write + read -- the staging copy had made the host memory system, not PCIe, the limit of the end-to-end path.
+// $CMDR_SHT_UP_PIECE_MB (default 4) x $CMDR_SHT_UP_SLOTS (default 6); CMDR_SHT_UP_PIECE_MB=0 stages whole ranges through
+// the big arena as before.
+struct UpRing {
+  char *base = nullptr;
+  size_t piece = 0;
+  int nslot = 0, next = 0;
+  std::vector<cudaEvent_t> ev;
+  std::vector<char> busy;
+};
+static UpRing *up_ring() {
+  static std::map<int, UpRing *> rings;
+  int dev = 0;
+  CMDR_CUDA_CHECK(cudaGetDevice(&dev));
+  auto it = rings.find(dev);
+  if (it != rings.end()) return it->second;
+  UpRing *R = new UpRing;
+  int mb = 4, ns = 6;
+  if (const char *e = getenv("CMDR_SHT_UP_PIECE_MB")) mb = atoi(e);
+  if (const char *e = getenv("CMDR_SHT_UP_SLOTS")) ns = atoi(e);
+  if (mb > 0 && ns >= 2) {
+    R->piece = (size_t)mb << 20; R->nslot = ns;
+    CMDR_CUDA_CHECK(cudaHostAlloc(reinterpret_cast<void **>(&R->base), R->piece * ns, cudaHostAllocDefault));
+    R->ev.resize(ns); R->busy.assign(ns, 0);
+    for (int k = 0; k < ns; ++k) CMDR_CUDA_CHECK(cudaEventCreateWithFlags(&R->ev[k], cudaEventDisableTiming));
+  }
+  rings[dev] = R;
+  return R;
+}
 
 // ---------------------------------------------------------------- pointer classes
 HostKind host_kind(const void *p) {
@@ -163,6 +207,24 @@ void HostIO::h2d(double *dev, int c, long long ofs, long long n, cudaStream_t s)
   if (n <= 0) return;
   const double *src = user_[c] + ofs;
   if (pageable_) {
+    UpRing *R = up_ring();
+    if (R->nslot) {                                  // piece by piece through the cache-resident ring
+      const char *from = reinterpret_cast<const char *>(src);
+      char *to = reinterpret_cast<char *>(dev);
+      const size_t bytes = sizeof(double) * (size_t)n;
+      for (size_t off = 0; off < bytes; off += R->piece) {
+        const size_t len = bytes - off < R->piece ? bytes - off : R->piece;
+        const int k = R->next;
+        R->next = (k + 1) % R->nslot;
+        if (R->busy[k]) CMDR_CUDA_CHECK(cudaEventSynchronize(R->ev[k]));
+        char *slot = R->base + (size_t)k * R->piece;
+        host_copy(slot, from + off, len);
+        CMDR_CUDA_CHECK(cudaMemcpyAsync(to + off, slot, len, cudaMemcpyHostToDevice, s));
+        CMDR_CUDA_CHECK(cudaEventRecord(R->ev[k], s));
+        R->busy[k] = 1;
+      }
+      return;
+    }
     double *sp = stage_up() + (size_t)c * count_ + ofs;
     host_copy(sp, src, sizeof(double) * (size_t)n);
     src = sp;

@@ -605,8 +605,10 @@ __global__ void __launch_bounds__(NT) ring_pow2_kernel(FParams p, int first_pair
   for (int k = threadIdx.x; k < ntw; k += NT) T[k] = tw[k];
   const long long oN = p.ofsN[pair], oS = p.ofsS[pair];
   if (DIR == 0) {
-    fold_positions<NT, 4>(p, L, c, pair, n, shifted, work, [bits](int t) { return (int)(__brev((unsigned)t) >> (32 - bits)); },
-                          [](int t) { return bf_pidx<true>(t); },
+    // bins in natural order (coalesced phase reads), stored at their bit-reversed positions: the two-level padding of
+    // bf_pidx keeps those stores free of bank conflicts
+    fold_positions<NT, 4>(p, L, c, pair, n, shifted, work, [](int t) { return t; },
+                          [bits](int t) { return bf_pidx<true>((int)(__brev((unsigned)t) >> (32 - bits))); },
                           [n, shifted](int k) { return shifted ? rs_expipi(k, n) : make_double2(1.0, 0.0); });
     __syncthreads();
     sm_fft_dit<NT>(work, n, T);

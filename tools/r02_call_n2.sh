@@ -8,7 +8,8 @@ TR="python -m torch.distributed.run --nnodes=1 --master-addr 127.0.0.1"
 {
 for p2p in 1 0; do
   echo "== dist_check world=$N CMDR_SHT_P2P=$p2p"
-  CMDR_SHT_P2P=$p2p timeout 900 $TR --nproc-per-node $N --master-port $((29500 + p2p)) tests/dist_check.py 2>&1 | grep -v -E "^\s*$|OMP_NUM_THREADS|^\*+$|Setting OMP" | tail -8
+  CMDR_SHT_P2P=$p2p timeout 900 $TR --nproc-per-node $N --master-port $((29500 + p2p)) tests/dist_check.py > gpurun_out/r02_dist_full_p2p$p2p.log 2>&1
+  grep -E "DIST_CHECK|Error|error|assert|Traceback|File \"" gpurun_out/r02_dist_full_p2p$p2p.log | head -30
 done
 echo "== dist_check world=$N, NCCL barriers (CMDR_SHT_FLAG_BARRIER=0)"
 CMDR_SHT_FLAG_BARRIER=0 timeout 900 $TR --nproc-per-node $N --master-port 29503 tests/dist_check.py 2>&1 | grep -E "DIST_CHECK|Error|error|assert" | tail -5
