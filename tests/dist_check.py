@@ -167,15 +167,14 @@ def main():
             f = sS * np.stack([bls[q][lg, j] for j in range(3)])
             out += f * Ytg(invN_g[q] * Yg(f * v))
         return out
-    sysn = cr_native_system(info, [torch.as_tensor(v[:, info.pix], device=dev) for v in invN_g], bls, Cl)
-    y = sysn.matmulA(torch.as_tensor(x_g[:, gidx], device=dev)).cpu().numpy()
+    sysn = cr_native_system(info, [torch.as_tensor(np.ascontiguousarray(v[:, info.pix]), device=dev) for v in invN_g], bls, Cl)
+    y = sysn.matmulA(torch.as_tensor(np.ascontiguousarray(x_g[:, gidx]), device=dev)).cpu().numpy()
     want = Ag(x_g)[:, gidx]
     e6 = np.linalg.norm(y - want) / np.linalg.norm(want)
     worst = max(worst, e6)
     assert e6 <= 1e-10, ("cmdr_cr_matmulA", e6)
     b_g = Ag(rng.standard_normal(x_g.shape))
     xs, it, hist = sysn.solve(np.ascontiguousarray(b_g[:, gidx]), maxiter=300, cg_tol=1e-10, cg_conv_crit="residual")
-    res = Ag_res = None
     # the solution satisfies the global system: gather nothing, check the residual of the local rows through the operator
     r_loc = sysn.matmulA(xs) - b_g[:, gidx]
     t = torch.tensor([float(np.sum(r_loc ** 2)), float(np.sum(b_g[:, gidx] ** 2))], dtype=torch.float64, device=dev)
