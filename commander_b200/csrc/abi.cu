@@ -620,8 +620,8 @@ static bool try_pipelined(int type, int spin, double *const *alm, double *const 
   double *alm_buf = static_cast<double *>(scratch_get("stage_alm", sizeof(double) * (size_t)nalm_d * ncomp));
   double *map_buf = static_cast<double *>(scratch_get("stage_map", sizeof(double) * (size_t)g->npix * ncomp));
   double4 *ph = static_cast<double4 *>(scratch_get("phase", sizeof(double4) * (size_t)ncomp * a->nm * g->npairs));
-  ioA.init("hstage_alm", alm, ncomp, nalm_d);
-  ioM.init("hstage_map", map, ncomp, g->npix);
+  ioA.init("hstage_alm", alm, ncomp, nalm_d, true);
+  ioM.init("hstage_map", map, ncomp, g->npix, true);
   size_t maxz = 0;
   for (sharp_geom_info *sub : g->subs) { ensure_geom_device(sub); maxz = std::max(maxz, ringfft_scratch_elems(sub)); }
   if (maxz) scratch_get("fftbuf", sizeof(double2) * maxz * ncomp);

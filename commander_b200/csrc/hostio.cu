@@ -146,7 +146,9 @@ int host_copy_threads() { return copy_pool()->workers() + 1; }
 // slot is reused as soon as its copy has left.  Per payload byte DRAM then sees one read (the caller's page) instead of
 // read + write + read -- the staging copy had made the host memory system, not PCIe, the limit of the end-to-end path.
 // $CMDR_SHT_UP_PIECE_MB (default 4) x $CMDR_SHT_UP_SLOTS (default 6); CMDR_SHT_UP_PIECE_MB=0 stages whole ranges through
-// the big arena as before.
+// the big arena as before.  Measured at nside 2048 / lmax 4000 on one B200 (16 host cores): pageable pair 100.8 -> 96.3 ms
+// (pinned: 83.1).  The distributed pipeline keeps the arena: there a rank that blocks on a ring slot delays its next
+// exchange barrier and with it every other rank (2 GPUs: 96.8 ms with the arena, 112.6 ms with the ring).
 struct UpRing {
   char *base = nullptr;
   size_t piece = 0;
@@ -185,8 +187,9 @@ HostKind host_kind(const void *p) {
 }
 
 // ---------------------------------------------------------------- HostIO
-void HostIO::init(const char *tag, double *const *cols, int ncols, long long count) {
+void HostIO::init(const char *tag, double *const *cols, int ncols, long long count, bool upload_ring) {
   ncols_ = ncols; count_ = count;
+  ring_ = upload_ring;
   pageable_ = false;
   for (int c = 0; c < ncols; ++c) { user_[c] = cols[c]; pageable_ = pageable_ || host_kind(cols[c]) == HostKind::Pageable; }
   stage_ = stage_up_ = nullptr;                    // allocated on first use: a transform uploads one array and downloads the other
@@ -207,8 +210,8 @@ void HostIO::h2d(double *dev, int c, long long ofs, long long n, cudaStream_t s)
   if (n <= 0) return;
   const double *src = user_[c] + ofs;
   if (pageable_) {
-    UpRing *R = up_ring();
-    if (R->nslot) {                                  // piece by piece through the cache-resident ring
+    UpRing *R = ring_ ? up_ring() : nullptr;
+    if (R && R->nslot) {                             // piece by piece through the cache-resident ring
       const char *from = reinterpret_cast<const char *>(src);
       char *to = reinterpret_cast<char *>(dev);
       const size_t bytes = sizeof(double) * (size_t)n;

@@ -134,7 +134,7 @@ int host_copy_threads();
 // threads before the H2D is queued, downloads landing in the arena and moved to the caller by drain().
 class HostIO {
  public:
-  void init(const char *tag, double *const *cols, int ncols, long long count);
+  void init(const char *tag, double *const *cols, int ncols, long long count, bool upload_ring = false);
   bool pageable() const { return pageable_; }
   void h2d(double *dev, int c, long long ofs, long long n, cudaStream_t s);
   void d2h(const double *dev, int c, long long ofs, long long n, cudaStream_t s);
@@ -149,7 +149,7 @@ class HostIO {
   const char *tag_ = "";
   int ncols_ = 0;
   long long count_ = 0;
-  bool pageable_ = false;
+  bool pageable_ = false, ring_ = false;
   std::vector<Drain> drains_;
   std::vector<cudaEvent_t> events_;
 };
