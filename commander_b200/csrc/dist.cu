@@ -765,6 +765,7 @@ int cmdr_sht_comm_register(int comm, int rank, int nranks, const void *id128) {
     CMDR_NCCL_CHECK(nccl_api()->CommInitRank(&C->nccl, nranks, id, rank));
   }
   g_comms[comm] = C;
+  host_copy_set_ranks(nranks);           // one process per GPU on one node: the copy threads of all ranks share its CPUs
   return 0;
 }
 

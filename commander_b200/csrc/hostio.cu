@@ -120,20 +120,35 @@ class CopyPool {
   std::atomic<unsigned long long> gen_{0};
 };
 
+// Ranks that share this host's cores (set by cmdr_sht_comm_register: one process per GPU, all on one node): the copy
+// threads of all of them must fit into the CPUs the node has, or they only take each other's time slices -- 8 ranks x 16
+// spinning workers on a 32-core host made the pageable path slower than one GPU.
+static std::atomic<int> g_ranks_per_node{1};
+void host_copy_set_ranks(int n) { if (n >= 1) g_ranks_per_node.store(n); }
+
+static int copy_threads_wanted() {
+  if (const char *e = getenv("CMDR_SHT_COPY_THREADS")) { const int n = atoi(e); if (n > 0) return n; }
+  // the threads this process may run on (respects taskset / cgroup / mpirun binding), shared with the other ranks of the
+  // node; one is left for the thread that drives the streams; at most 16
+  cpu_set_t set;
+  int avail = (sched_getaffinity(0, sizeof(set), &set) == 0) ? CPU_COUNT(&set) : (int)std::thread::hardware_concurrency();
+  int n = avail / g_ranks_per_node.load() - 1;
+  if (n > 16) n = 16;
+  if (n < 1) n = 1;
+  return n;
+}
+
 static CopyPool *copy_pool() {
-  static CopyPool *pool = [] {
-    int n = 0;
-    if (const char *e = getenv("CMDR_SHT_COPY_THREADS")) n = atoi(e);
-    if (n <= 0) {
-      // the threads this process may run on (respects taskset / cgroup / mpirun binding), at most 16
-      cpu_set_t set;
-      int avail = (sched_getaffinity(0, sizeof(set), &set) == 0) ? CPU_COUNT(&set) : (int)std::thread::hardware_concurrency();
-      n = avail - 1;                               // leave one for the thread that drives the streams
-      if (n > 16) n = 16;
-      if (n < 1) n = 1;
-    }
-    return new CopyPool(n - 1);                     // leaked on purpose: detached workers, no exit-order hazards
-  }();
+  static std::mutex mu;
+  static CopyPool *pool = nullptr;
+  static int pool_threads = 0;
+  std::lock_guard<std::mutex> lk(mu);
+  const int want = copy_threads_wanted();
+  if (!pool || want != pool_threads) {
+    // pools are never destroyed (detached workers, no exit-order hazards); a superseded pool's workers just stay asleep
+    pool = new CopyPool(want - 1);
+    pool_threads = want;
+  }
   return pool;
 }
 

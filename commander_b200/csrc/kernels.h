@@ -129,6 +129,7 @@ void *pinned_get(const char *name, size_t bytes, bool write_combined = false);
 void pinned_release();
 void host_copy(void *dst, const void *src, size_t bytes);   // multi-threaded memcpy (blocking)
 int host_copy_threads();
+void host_copy_set_ranks(int ranks_on_this_node);   // sizes the copy-thread pool so that all ranks fit the node's CPUs
 // The columns of one caller array (alm or map) as the pipelined paths move them: pinned columns are copied in
 // place; pageable columns go through the library's pinned arena (same offsets), uploads staged by the copy
 // threads before the H2D is queued, downloads landing in the arena and moved to the caller by drain().
