@@ -620,6 +620,51 @@ np.savez(sys.argv[1], map=mp, alm=m.alm, a0=a0, x0=x0)
         assert rel(res[name]["map"], oY) <= TOL and rel(res[name]["alm"], oA) <= TOL, name
 
 
+def test_ring_kernels_with_aliasing(shtlib, cpu_oracle):
+    """lmax > ring length: several m fold into one bin of the belt (n = 4 nside = 1024 <= mmax = 1100) and of the cap rings.
+    The whole-ring power-of-two kernel and the radix-4 split kernel (forced for every cap class) then take their
+    bin-major fold; compared with the oracle and with the all-cuFFT path."""
+    import os
+    import subprocess
+    import sys
+    import tempfile
+    S = cpu_oracle
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    nside, lmax = 256, 1100
+    code = r"""
+import sys, numpy as np
+sys.path.insert(0, %r)
+from commander_b200 import comm_map, comm_mapinfo
+info = comm_mapinfo(None, %d, %d, 3, True)
+m = comm_map(info)
+rng = np.random.default_rng(18)
+m.alm[:] = rng.standard_normal(m.alm.shape)
+m.alm[1:3, info.lm[0] < 2] = 0
+a0 = m.alm.copy()
+m.Y(); mp = m.map.copy()
+m.map[:] = rng.standard_normal(m.map.shape)
+x0 = m.map.copy()
+m.Yt()
+np.savez(sys.argv[1], map=mp, alm=m.alm, a0=a0, x0=x0)
+""" % (root, nside, lmax)
+    res = {}
+    with tempfile.TemporaryDirectory() as td:
+        for name, envv in (("kernels", dict(CMDR_SHT_SPLIT_MIN="1024")),
+                           ("cufft", dict(CMDR_SHT_FUSED_BLUE="0", CMDR_SHT_RING_SPLIT="0", CMDR_SHT_BELT_FUSED="0"))):
+            out = os.path.join(td, name + ".npz")
+            r = subprocess.run([sys.executable, "-c", code, out], env=dict(os.environ, **envv), capture_output=True, text=True,
+                               timeout=300)
+            assert r.returncode == 0, (name, r.stderr[-2000:])
+            res[name] = dict(np.load(out))
+    a0, x0 = res["cufft"]["a0"], res["cufft"]["x0"]
+    oY = np.concatenate([S.execute(S.Y, 0, nside, lmax, alm=a0[0:1]), S.execute(S.Y, 2, nside, lmax, alm=a0[1:3])])
+    oA = np.concatenate([S.execute(S.Yt, 0, nside, lmax, map=x0[0:1]), S.execute(S.Yt, 2, nside, lmax, map=x0[1:3])])
+    for name in res:
+        assert rel(res[name]["map"], oY) <= TOL, (name, rel(res[name]["map"], oY))
+        assert rel(res[name]["alm"], oA) <= TOL, (name, rel(res[name]["alm"], oA))
+    assert not np.array_equal(res["kernels"]["map"], res["cufft"]["map"])
+
+
 @pytest.mark.parametrize("spin", [0, 2])
 def test_empty_and_ragged_inputs(shtlib, cpu_oracle, spin):
     """What a rank with nothing to do passes (commander3/src/sharp.f90:219-224: null pointers when n_local == 0): no m's ->
