@@ -497,14 +497,14 @@ def run_ours(args):
         kern[f"spin{k[0]}_{'analysis' if k[1] else 'synthesis'}_tflops_executed"] = round(fe / (v * 1e-3) / 1e12, 3)
     traffic = None
     try:   # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from the committed ncu --set full capture
-        prof = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_summary.json")))
-        key = "anal2_kernel" if dom[0][1] else "synth2_kernel"
+        prof = json.load(open(os.path.join(ROOT, "profiles", "r02_ncu_summary.json")))
+        key = next(k for k in prof if k.startswith("anal2_kernel" if dom[0][1] else "synth2_kernel"))
         if world == 1 and nside == 2048 and lmax == 4000:
             traffic = prof[key]["dram_bytes_per_launch"]
-    except (OSError, KeyError, ValueError):
+    except (OSError, KeyError, ValueError, StopIteration):
         pass
     traffic_source = ("dram__bytes_read.sum + dram__bytes_write.sum of this kernel from the committed ncu --set full capture "
-                      "profiles/r01_ncu_summary.json (not measured by this run)") if traffic is not None else None
+                      "profiles/r02_ncu_summary.json (not measured by this run)") if traffic is not None else None
     roofline = {"bound": "fp64", "traffic_source": traffic_source, "kernel": f"spin-2 Legendre {'analysis (anal2_kernel)' if dom[0][1] else 'synthesis (synth2_kernel)'}",
                 "achieved": round(achieved, 3), "peak": round(fp64_peak, 3), "unit": "TFLOP/s",
                 "frac": round(achieved / fp64_peak, 4), "traffic": traffic,
