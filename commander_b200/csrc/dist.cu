@@ -238,7 +238,9 @@ static DistPlan *get_plan(DistComm *C, sharp_geom_info *g, sharp_alm_info *a, cu
   }
   P->nvalid = w;
   {
-    const int K = 4;                                    // chunks per transform
+    // chunks per transform of the host-buffer pipeline (one exchange barrier each; the first chunk's upload and the last
+    // chunk's download are not hidden behind kernels, so smaller chunks shorten both ends): CMDR_SHT_DIST_CHUNKS, default 8
+    static const int K = (getenv("CMDR_SHT_DIST_CHUNKS") && atoi(getenv("CMDR_SHT_DIST_CHUNKS")) > 0) ? std::min(24, atoi(getenv("CMDR_SHT_DIST_CHUNKS"))) : 8;
     int per = ((P->nvalid + K - 1) / K + 127) / 128 * 128;
     if (per < 128) per = 128;
     for (int b = 0; b < P->nvalid; b += per) P->wcut.push_back(b);
