@@ -552,7 +552,7 @@ void sub_ranges(const sharp_geom_info *s, long long &nb, long long &ne, long lon
 // Columns of consecutive local m's are contiguous in the packed a_lm array for the layouts Commander
 // builds (sharp_make_mmajor_real_packed_alm_info): returns their start offsets (doubles) and cuts the
 // m range into `nch` pieces of about equal size.  False for layouts that are not dense.
-static bool alm_m_chunks(const sharp_alm_info *a, long long nalm_d, int nch, std::vector<long long> &mstart,
+bool alm_m_chunks(const sharp_alm_info *a, long long nalm_d, int nch, std::vector<long long> &mstart,
                          std::vector<int> &mcut) {
   mstart.assign(a->nm + 1, 0);
   const long long f2 = a->real_packed ? 1 : 2;

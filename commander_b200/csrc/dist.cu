@@ -632,12 +632,38 @@ static bool try_dist_pipelined(DistComm *C, int type, int spin, double *const *a
   HostIO ioA, ioM;                                        // pageable caller arrays go through the pinned arena (hostio.cu)
   ioA.init("hstage_alm", alm, ncomp, nalm_d);
   ioM.init("hstage_map", map, ncomp, g->npix);
+  // The a_lm move in NMCH chunks of local m's beside the kernels of ONE work-slot chunk (rank-local: no barrier inside):
+  // synthesis runs the first chunk's Legendre kernel m-chunk by m-chunk as the upload lands, analysis the last chunk's,
+  // sending finished columns back while the next m-chunk is accumulated.
+  constexpr int NMCH = 4;
+  std::vector<long long> mstart;
+  std::vector<int> mcut;
+  const int nmch = alm_m_chunks(a, nalm_d, NMCH, mstart, mcut) ? NMCH : 1;
+  const size_t evm = 200;                                 // events of the m-chunks
   if (synth) {
-    for (int c = 0; c < ncomp; ++c) ioA.h2d(alm_dev[c], c, 0, nalm_d, st);
+    if (nmch == 1) for (int c = 0; c < ncomp; ++c) ioA.h2d(alm_dev[c], c, 0, nalm_d, st);
+    else {
+      cudaEvent_t e0 = pooled_event(evm + 2 * NMCH);       // the staging a_lm may still be read by earlier work on `st`
+      CMDR_CUDA_CHECK(cudaEventRecord(e0, st));
+      CMDR_CUDA_CHECK(cudaStreamWaitEvent(cs, e0, 0));
+    }
     stream_barrier(C, st);                                 // every rank has finished reading its buffer
     for (int c = K - 1; c >= 0; --c) {                     // belt first, polar caps last
       G.slot_begin = P->wcut[c]; G.slot_end = P->wcut[c + 1];
-      launch_legendre_synth(spin, G, A, alm_dev, reinterpret_cast<double4 *>(B.mine), st, c == K - 1);
+      if (c == K - 1 && nmch > 1) {
+        for (int j = 0; j < nmch; ++j) {
+          const long long b = mstart[mcut[j]], e = mstart[mcut[j + 1]];
+          for (int k = 0; k < ncomp; ++k) ioA.h2d(alm_dev[k] + b, k, b, e - b, cs);
+          cudaEvent_t ej = pooled_event(evm + j);
+          CMDR_CUDA_CHECK(cudaEventRecord(ej, cs));
+          CMDR_CUDA_CHECK(cudaStreamWaitEvent(st, ej, 0));
+          LegAlm Aj = A;
+          Aj.im_begin = mcut[j]; Aj.im_end = mcut[j + 1];
+          launch_legendre_synth(spin, G, Aj, alm_dev, reinterpret_cast<double4 *>(B.mine), st, true);
+        }
+      } else {
+        launch_legendre_synth(spin, G, A, alm_dev, reinterpret_cast<double4 *>(B.mine), st, c == K - 1);
+      }
       stream_barrier(C, st);                               // chunk c has landed everywhere
       sharp_geom_info *sub = P->subs[c];
       if (!sub) continue;
@@ -680,11 +706,28 @@ static bool try_dist_pipelined(DistComm *C, int type, int spin, double *const *a
       }
       stream_barrier(C, st);                               // chunk c is complete on every rank
       G.slot_begin = P->wcut[c]; G.slot_end = P->wcut[c + 1];
-      launch_legendre_anal(spin, G, A, alm_dev, reinterpret_cast<const double4 *>(B.mine), st);
+      if (c == K - 1 && nmch > 1) {
+        for (int j = 0; j < nmch; ++j) {
+          LegAlm Aj = A;
+          Aj.im_begin = mcut[j]; Aj.im_end = mcut[j + 1];
+          launch_legendre_anal(spin, G, Aj, alm_dev, reinterpret_cast<const double4 *>(B.mine), st);
+          cudaEvent_t ej = pooled_event(evm + NMCH + j);
+          CMDR_CUDA_CHECK(cudaEventRecord(ej, st));
+          CMDR_CUDA_CHECK(cudaStreamWaitEvent(cs, ej, 0));
+          const long long b = mstart[mcut[j]], e = mstart[mcut[j + 1]];
+          for (int k = 0; k < ncomp; ++k) ioA.d2h(alm_dev[k] + b, k, b, e - b, cs);
+          ioA.commit(cs);
+        }
+      } else {
+        launch_legendre_anal(spin, G, A, alm_dev, reinterpret_cast<const double4 *>(B.mine), st);
+      }
     }
-    for (int c = 0; c < ncomp; ++c) ioA.d2h(alm_dev[c], c, 0, nalm_d, st);
-    ioA.commit(st);
+    if (nmch == 1) {
+      for (int c = 0; c < ncomp; ++c) ioA.d2h(alm_dev[c], c, 0, nalm_d, st);
+      ioA.commit(st);
+    }
     ioA.drain();
+    CMDR_CUDA_CHECK(cudaStreamSynchronize(cs));
     CMDR_CUDA_CHECK(cudaStreamSynchronize(st));
   }
   return true;

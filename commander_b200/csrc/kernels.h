@@ -120,6 +120,9 @@ sharp_geom_info *make_subgeom(const sharp_geom_info *g, int a, int b);
 bool pairs_contiguous(const sharp_geom_info *g);
 void sub_ranges(const sharp_geom_info *s, long long &nb, long long &ne, long long &sb, long long &se);
 bool is_pinned_host(const void *p);
+// start offsets of the local m columns in a dense packed a_lm array and a cut of the m range into nch pieces of about equal
+// size (false for layouts that are not dense or have fewer than 64 m's)
+bool alm_m_chunks(const sharp_alm_info *a, long long nalm_d, int nch, std::vector<long long> &mstart, std::vector<int> &mcut);
 cudaStream_t copy_stream();
 cudaEvent_t pooled_event(size_t i);
 // host staging for pageable caller arrays (hostio.cu)
