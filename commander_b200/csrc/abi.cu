@@ -225,7 +225,7 @@ void ensure_subgeoms(sharp_geom_info *g, int nchunks) {
   if (np < 1024 || !pairs_contiguous(g)) return;
   // chunk = a multiple of 512 ring pairs: the Legendre CTAs cover 256 or 512 pair slots, so
   // any other boundary would leave lanes idle in every CTA row of the chunk
-  const int unit = 512;
+  const int unit = nchunks > 8 ? 256 : 512;
   int per = ((np + nchunks - 1) / nchunks + unit - 1) / unit * unit;
   if (per >= np) return;
   for (int a = 0; a < np; a += per) g->subs.push_back(make_subgeom(g, a, std::min(np, a + per)));

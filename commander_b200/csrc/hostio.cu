@@ -169,24 +169,38 @@ struct UpRing {
   std::vector<cudaEvent_t> ev;
   std::vector<char> busy;
 };
-static UpRing *up_ring() {
+static UpRing *make_ring(int which) {         // 0: upload ring, 1: download ring
   static std::map<int, UpRing *> rings;
   int dev = 0;
   CMDR_CUDA_CHECK(cudaGetDevice(&dev));
-  auto it = rings.find(dev);
+  const int key = dev * 2 + which;
+  auto it = rings.find(key);
   if (it != rings.end()) return it->second;
   UpRing *R = new UpRing;
-  int mb = 4, ns = 6;
-  if (const char *e = getenv("CMDR_SHT_UP_PIECE_MB")) mb = atoi(e);
-  if (const char *e = getenv("CMDR_SHT_UP_SLOTS")) ns = atoi(e);
+  int mb = which == 0 ? 4 : 0, ns = 6;          // the download ring is opt-in (CMDR_SHT_DN_PIECE_MB)
+  if (const char *e = getenv(which == 0 ? "CMDR_SHT_UP_PIECE_MB" : "CMDR_SHT_DN_PIECE_MB")) mb = atoi(e);
+  if (const char *e = getenv(which == 0 ? "CMDR_SHT_UP_SLOTS" : "CMDR_SHT_DN_SLOTS")) ns = atoi(e);
   if (mb > 0 && ns >= 2) {
     R->piece = (size_t)mb << 20; R->nslot = ns;
     CMDR_CUDA_CHECK(cudaHostAlloc(reinterpret_cast<void **>(&R->base), R->piece * ns, cudaHostAllocDefault));
     R->ev.resize(ns); R->busy.assign(ns, 0);
     for (int k = 0; k < ns; ++k) CMDR_CUDA_CHECK(cudaEventCreateWithFlags(&R->ev[k], cudaEventDisableTiming));
   }
-  rings[dev] = R;
+  rings[key] = R;
   return R;
+}
+static UpRing *up_ring() { return make_ring(0); }
+static UpRing *dn_ring() { return make_ring(1); }
+static cudaStream_t dn_stream() {
+  static std::map<int, cudaStream_t> ss;
+  int dev = 0;
+  CMDR_CUDA_CHECK(cudaGetDevice(&dev));
+  auto it = ss.find(dev);
+  if (it != ss.end()) return it->second;
+  cudaStream_t s;
+  CMDR_CUDA_CHECK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+  ss[dev] = s;
+  return s;
 }
 
 // ---------------------------------------------------------------- pointer classes
@@ -253,6 +267,10 @@ void HostIO::h2d(double *dev, int c, long long ofs, long long n, cudaStream_t s)
 void HostIO::d2h(const double *dev, int c, long long ofs, long long n, cudaStream_t s) {
   if (n <= 0) return;
   double *dst = user_[c] + ofs;
+  if (pageable_ && ring_ && dn_ring()->nslot) {      // fetched piece by piece at drain time through the download ring
+    drains_.push_back(Drain{nullptr, dst, dev, sizeof(double) * (size_t)n, false, true});
+    return;
+  }
   if (pageable_) {
     double *sp = stage_dn() + (size_t)c * count_ + ofs;
     CMDR_CUDA_CHECK(cudaMemcpyAsync(sp, dev, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, s));
@@ -277,6 +295,39 @@ void HostIO::commit(cudaStream_t s) {
 }
 
 void HostIO::drain() {
+  // requests deferred to the download ring: D2H of piece p + 1 ... p + nslot - 1 runs while the copy threads move piece p
+  // out of its slot (still cache resident) into the caller's pages
+  {
+    UpRing *R = dn_ring();
+    cudaStream_t ds = dn_stream();
+    struct Fly { int k; double *dst; size_t len; };
+    std::vector<Fly> fly;
+    size_t head = 0;
+    auto retire = [&]() {
+      const Fly &f = fly[head++];
+      CMDR_CUDA_CHECK(cudaEventSynchronize(R->ev[f.k]));
+      host_copy(f.dst, R->base + (size_t)f.k * R->piece, f.len);
+    };
+    cudaEvent_t last = nullptr;
+    for (Drain &d : drains_) {
+      if (!d.deferred || d.done) continue;
+      if (d.ev && d.ev != last) { CMDR_CUDA_CHECK(cudaStreamWaitEvent(ds, d.ev, 0)); last = d.ev; }
+      else if (!d.ev) CMDR_CUDA_CHECK(cudaDeviceSynchronize());
+      const char *from = reinterpret_cast<const char *>(d.src);
+      char *to = reinterpret_cast<char *>(d.dst);
+      for (size_t off = 0; off < d.bytes; off += R->piece) {
+        const size_t len = d.bytes - off < R->piece ? d.bytes - off : R->piece;
+        if ((int)(fly.size() - head) == R->nslot) retire();
+        const int k = R->next;
+        R->next = (k + 1) % R->nslot;
+        CMDR_CUDA_CHECK(cudaMemcpyAsync(R->base + (size_t)k * R->piece, from + off, len, cudaMemcpyDeviceToHost, ds));
+        CMDR_CUDA_CHECK(cudaEventRecord(R->ev[k], ds));
+        fly.push_back(Fly{k, reinterpret_cast<double *>(to + off), len});
+      }
+      d.done = true;
+    }
+    while (head < fly.size()) retire();
+  }
   for (Drain &d : drains_) {
     if (d.done) continue;
     if (d.ev) CMDR_CUDA_CHECK(cudaEventSynchronize(d.ev));

@@ -145,7 +145,7 @@ class HostIO {
   void commit(cudaStream_t s);   // marks the downloads queued so far on `s` as one completion group
   void drain();                  // waits for the groups in order and hands the data to the caller (call before returning)
  private:
-  struct Drain { cudaEvent_t ev; double *dst; const double *src; size_t bytes; bool done = false; };
+  struct Drain { cudaEvent_t ev; double *dst; const double *src; size_t bytes; bool done = false; bool deferred = false; };
   double *stage_dn();
   double *stage_up();
   double *user_[4] = {};
