@@ -638,7 +638,7 @@ static bool try_pipelined(int type, int spin, double *const *alm, double *const 
     // a_lm upload in NMCH chunks of local m's (the packed columns of consecutive m's are contiguous): the
     // first ring-pair chunk runs its Legendre kernel m-chunk by m-chunk as the data lands, so only the
     // first quarter of the upload is exposed.  Falls back to one copy for layouts that are not dense.
-    static const int NMCH = getenv("CMDR_SHT_MCHUNKS") ? std::max(1, std::min(16, atoi(getenv("CMDR_SHT_MCHUNKS")))) : 8;
+    static const int NMCH = getenv("CMDR_SHT_MCHUNKS") ? std::max(1, std::min(16, atoi(getenv("CMDR_SHT_MCHUNKS")))) : 16;
     std::vector<long long> mstart;
     std::vector<int> mcut;
     const int nmch = alm_m_chunks(a, nalm_d, NMCH, mstart, mcut) ? NMCH : 1;
@@ -710,7 +710,7 @@ static bool try_pipelined(int type, int spin, double *const *alm, double *const 
     CMDR_CUDA_CHECK(cudaStreamSynchronize(cs));
     CMDR_CUDA_CHECK(cudaStreamSynchronize(st));
   } else {
-    static const int NMCH = getenv("CMDR_SHT_MCHUNKS") ? std::max(1, std::min(16, atoi(getenv("CMDR_SHT_MCHUNKS")))) : 8;
+    static const int NMCH = getenv("CMDR_SHT_MCHUNKS") ? std::max(1, std::min(16, atoi(getenv("CMDR_SHT_MCHUNKS")))) : 16;
     std::vector<long long> mstart;
     std::vector<int> mcut;
     const int nmch = alm_m_chunks(a, nalm_d, NMCH, mstart, mcut) ? NMCH : 1;

@@ -159,8 +159,10 @@ int host_copy_threads() { return copy_pool()->workers() + 1; }
 // slot is reused as soon as its copy has left.  Per payload byte DRAM then sees one read (the caller's page) instead of
 // read + write + read -- the staging copy had made the host memory system, not PCIe, the limit of the end-to-end path.
 // $CMDR_SHT_UP_PIECE_MB (default 4) x $CMDR_SHT_UP_SLOTS (default 6); CMDR_SHT_UP_PIECE_MB=0 stages whole ranges through
-// the big arena as before.  Measured at nside 2048 / lmax 4000 on one B200 (16 host cores): pageable pair 100.8 -> 96.3 ms
-// (pinned: 83.1).  The distributed pipeline keeps the arena: there a rank that blocks on a ring slot delays its next
+// the big arena as before.  Downloads take the mirror image ($CMDR_SHT_DN_PIECE_MB x $CMDR_SHT_DN_SLOTS, same defaults): the
+// D2H copies of a finished chunk are issued at drain time, piece by piece into a second ring, and the copy threads move
+// piece p to the caller while pieces p + 1 ... are in flight.  Measured at nside 2048 / lmax 4000 on one B200 (16 host
+// cores): pageable pair 100.8 (arena both ways) -> 96.3 (upload ring) -> 90.4 ms (both rings); pinned: 83.1.  The distributed pipeline keeps the arena: there a rank that blocks on a ring slot delays its next
 // exchange barrier and with it every other rank (2 GPUs: 96.8 ms with the arena, 112.6 ms with the ring).
 struct UpRing {
   char *base = nullptr;
@@ -177,7 +179,7 @@ static UpRing *make_ring(int which) {         // 0: upload ring, 1: download rin
   auto it = rings.find(key);
   if (it != rings.end()) return it->second;
   UpRing *R = new UpRing;
-  int mb = which == 0 ? 4 : 0, ns = 6;          // the download ring is opt-in (CMDR_SHT_DN_PIECE_MB)
+  int mb = 4, ns = 6;
   if (const char *e = getenv(which == 0 ? "CMDR_SHT_UP_PIECE_MB" : "CMDR_SHT_DN_PIECE_MB")) mb = atoi(e);
   if (const char *e = getenv(which == 0 ? "CMDR_SHT_UP_SLOTS" : "CMDR_SHT_DN_SLOTS")) ns = atoi(e);
   if (mb > 0 && ns >= 2) {
