@@ -98,15 +98,25 @@ void ensure_coef(sharp_alm_info *a, int spin) {
   CoefDev &c = a->coef[spin];
   if (c.ready) return;
   std::vector<double> tab; std::vector<long long> ofs;
-  build_coef_table(a->lmax, spin, a->mval, tab, ofs);
+  std::vector<long long> tofs(a->nm + 1, 0);
+  if (spin == COEF_KEY_S0X2) {   // spin 0 in steps of two l: one tile row per step
+    std::vector<double> mix;
+    build_coef_table_x2(a->lmax, a->mval, tab, mix, ofs);
+    c.tab2 = upload(mix);
+    for (int i = 0; i < a->nm; ++i) {
+      long long n = a->lmax >= a->mval[i] ? (a->lmax - a->mval[i]) / 2 + 1 : 0;
+      tofs[i + 1] = tofs[i] + ((n + 7) & ~7LL);
+    }
+  } else {
+    build_coef_table(a->lmax, spin, a->mval, tab, ofs);
+    for (int i = 0; i < a->nm; ++i) {
+      int l0 = a->mval[i] > spin ? a->mval[i] : spin;
+      long long n = a->lmax >= l0 ? a->lmax - l0 + 1 : 0;
+      tofs[i + 1] = tofs[i] + ((n + 7) & ~7LL);
+    }
+  }
   c.tab = upload(tab);
   c.ofs = upload(ofs);
-  std::vector<long long> tofs(a->nm + 1, 0);
-  for (int i = 0; i < a->nm; ++i) {
-    int l0 = a->mval[i] > spin ? a->mval[i] : spin;
-    long long n = a->lmax >= l0 ? a->lmax - l0 + 1 : 0;
-    tofs[i + 1] = tofs[i] + ((n + 7) & ~7LL);
-  }
   c.tofs = upload(tofs);
   c.trows = tofs[a->nm];
   c.ready = true;
@@ -282,7 +292,7 @@ void sharp_destroy_alm_info(sharp_alm_info *a) {
     forget_layout(a);
     cudaFree(a->d_mval); cudaFree(a->d_mvstart); cudaFree(a->d_m2im);
     for (auto &kv : a->d_K) cudaFree(kv.second);
-    for (auto &kv : a->coef) if (kv.second.ready) { cudaFree(kv.second.tab); cudaFree(kv.second.ofs); cudaFree(kv.second.tofs); }
+    for (auto &kv : a->coef) if (kv.second.ready) { cudaFree(kv.second.tab); cudaFree(kv.second.tab2); cudaFree(kv.second.ofs); cudaFree(kv.second.tofs); }
   }
   delete a;
 }
@@ -409,16 +419,18 @@ void forget_layout(const sharp_alm_info *a) {
   g_idlayout.erase(it);
 }
 
-LegAlm make_legalm(sharp_alm_info *a, int spin) {
+// `classic`: spin 0 with the one-step table {A', g} (invn.cu); the transforms use the two-l-per-step tables
+LegAlm make_legalm(sharp_alm_info *a, int spin, bool classic) {
   ensure_alm_device(a);
-  ensure_coef(a, spin);
+  const int key = (spin == 0 && !classic) ? COEF_KEY_S0X2 : spin;
+  ensure_coef(a, key);
   LegAlm A;
   A.lmax = a->lmax; A.nm = a->nm; A.real_packed = a->real_packed ? 1 : 0;
   A.mval = a->d_mval; A.mvstart = a->d_mvstart;
   A.spin = spin;
-  A.coef = a->coef[spin].tab; A.cofs = a->coef[spin].ofs;
+  A.coef = a->coef[key].tab; A.coef2 = a->coef[key].tab2; A.cofs = a->coef[key].ofs;
   A.Kstart = ensure_start_norms(a, spin);
-  A.tofs = a->coef[spin].tofs; A.trows = a->coef[spin].trows;
+  A.tofs = a->coef[key].tofs; A.trows = a->coef[key].trows;
   return A;
 }
 

@@ -37,6 +37,61 @@ static void fill_spin0(int lmax, int m, double *out /* {A', g} per l = m..lmax *
   }
 }
 
+// spin 0, two l per step (the scheme libsharp2 itself uses for scalar transforms): with l_j = m + 2j and
+// q_j = lam_{l_j+1} / x, the three-term recurrence above applied twice gives a recurrence in x^2,
+//     al_j q_{j+1} = (x^2 - be_j) q_j - al_{j-1} q_{j-1},  al_j = b_{l_j+2} b_{l_j+3},  be_j = b_{l_j+1}^2 + b_{l_j+2}^2,
+// and both parities of lam come from the q_j alone:
+//     lam_{l_j} = b_{l_j+1} q_j + b_{l_j} q_{j-1},      lam_{l_j+1} = x q_j.
+// Normalised as q_j = h_j nu_j with nu_{j+1} = (a_j x^2 + b'_j) nu_j - nu_{j-1}  (2 DFMA-pipe ops per TWO l):
+//     h_0 = h_1 = sqrt(2m+3) (so that nu_0 = lam_mm, the start value of the one-step form),
+//     h_{j+1} = al_{j-1} h_{j-1} / al_j,   a_j = h_j / (al_j h_{j+1}),   b'_j = -be_j a_j.
+// rec row j = {a_j, b'_j};  mix row j = {u_j, v_j, h_j, v_{j-1}} with u_j = h_j b_{l_j+1}, v_j = h_j b_{l_j+2}:
+//     sum_l a_l lam_l = sum_j nu_j (u_j a_{l_j} + v_j a_{l_j+2}) + x sum_j nu_j h_j a_{l_j+1}.
+static void fill_spin0_x2(int lmax, int m, double *rec, double *mix) {
+  auto beta = [m](int l) -> long double {
+    return sqrtl(((long double)l * l - (long double)m * m) / (4.0L * l * l - 1.0L));
+  };
+  const int J = (lmax - m) / 2 + 1;
+  long double h_prev = sqrtl(2.0L * m + 3.0L), h_cur = h_prev;   // h_{j-1}, h_j
+  long double al_prev = 0.0L, v_prev = 0.0L;                      // al_{j-1}, v_{j-1}
+  for (int j = 0; j < J; ++j) {
+    const int l = m + 2 * j;
+    const long double b1 = beta(l + 1), b2 = beta(l + 2), b3 = beta(l + 3);
+    const long double al = b2 * b3, be = b1 * b1 + b2 * b2;
+    const long double h_next = j == 0 ? h_cur : al_prev * h_prev / al;
+    const long double a = h_cur / (al * h_next);
+    rec[2 * j] = (double)a; rec[2 * j + 1] = (double)(-be * a);
+    mix[4 * j] = (double)(h_cur * b1); mix[4 * j + 1] = (double)(h_cur * b2); mix[4 * j + 2] = (double)h_cur; mix[4 * j + 3] = (double)v_prev;
+    v_prev = h_cur * b2;
+    h_prev = h_cur; h_cur = h_next; al_prev = al;
+  }
+}
+
+void build_coef_table_x2(int lmax, const std::vector<int> &mval, std::vector<double> &rec, std::vector<double> &mix,
+                         std::vector<long long> &ofs) {
+  const int nm = (int)mval.size();
+  ofs.assign(nm + 1, 0);
+  for (int i = 0; i < nm; ++i) {
+    long long n = lmax >= mval[i] ? (lmax - mval[i]) / 2 + 1 : 0;
+    ofs[i + 1] = ofs[i] + n * 2;
+  }
+  // zero padding: whole tiles of up to 256 rows are staged with cp.async past the last row of the last m
+  rec.assign((size_t)ofs[nm] + 2 * 256 + 4, 0.0);
+  mix.assign((size_t)2 * ofs[nm] + 4 * 256 + 4, 0.0);
+  unsigned nt = std::thread::hardware_concurrency();
+  if (nt == 0) nt = 4;
+  if (nt > 32) nt = 32;
+  if ((int)nt > nm) nt = nm > 0 ? nm : 1;
+  std::vector<std::thread> th;
+  for (unsigned t = 0; t < nt; ++t) {
+    th.emplace_back([&, t]() {
+      for (int i = (int)t; i < nm; i += (int)nt)
+        if (lmax >= mval[i]) fill_spin0_x2(lmax, mval[i], rec.data() + ofs[i], mix.data() + 2 * ofs[i]);
+    });
+  }
+  for (auto &t : th) t.join();
+}
+
 static void fill_spins(int lmax, int m, int s, double *out /* {A', C', g, pad} per l = l0..lmax */) {
   int l0 = m > s ? m : s;
   auto D = [m, s](int l) -> long double {

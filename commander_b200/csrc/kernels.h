@@ -43,7 +43,8 @@ struct LegAlm {
   int im_begin = 0, im_end = -1;   // sub-range of local m's to process (-1: all)
   const int *mval = nullptr;
   const long long *mvstart = nullptr;
-  const double *coef = nullptr;
+  const double *coef = nullptr;    // spin 0: rec rows {a_j, b'_j} of the two-l-per-step scheme; spin s: {A', C', g, 0}
+  const double *coef2 = nullptr;   // spin 0: mix rows {u_j, v_j, h_j, v_{j-1}}
   const long long *cofs = nullptr;
   const double *Kstart = nullptr;  // start-value normalisation of this spin, indexed by m
   const long long *tofs = nullptr; // first synthesis tile row of each local m (rows padded to 8 per m)
@@ -108,7 +109,7 @@ void ringfft_anal(sharp_geom_info *geom, int ncomp, const PhaseLayout &L, double
 void *scratch_get(const char *name, size_t bytes);
 void ensure_alm_device(sharp_alm_info *a);
 void ensure_geom_device(sharp_geom_info *g);
-LegAlm make_legalm(sharp_alm_info *a, int spin);
+LegAlm make_legalm(sharp_alm_info *a, int spin, bool classic = false);
 void ring_trig_ld(int nside, int north, long double &cth, long double &sth, long double &sh, long double &ch);
 bool is_device_ptr(const void *p);
 extern thread_local int g_profiling;

@@ -14,7 +14,7 @@
 // reads per-l data (recurrence coefficients and, for synthesis, the pre-scaled a_lm) as
 // warp-uniform broadcasts from a shared-memory tile of TL consecutive l that the warp stages
 // itself with cp.async.  FP64-pipe cost per (l, m, ring pair):
-//   spin 0: 2 (recurrence) + 2 (accumulate) ; spin s: 4 + 8.
+//   spin 0: 1 (recurrence) + 2 (accumulate) -- two l per step, recurrence in x^2 (coef.cpp) ; spin s: 4 + 8.
 // Analysis reduces over the rings of the warp with a select-free, software-pipelined register
 // butterfly and adds the sums to the a_lm with coalesced atomics.
 #include <cstdio>
@@ -42,6 +42,7 @@ struct KParams {
   const int *mval;
   const long long *mvstart;
   const double *coef;
+  const double *coef2;               // spin 0: mix rows {u_j, v_j, h_j, v_{j-1}} of the two-l-per-step scheme (coef.cpp)
   const long long *cofs;
   const double *Kstart;
   const long long *tofs;             // synthesis: first tile row of each local m (rows padded to 8 per m)
@@ -56,9 +57,9 @@ struct KParams {
   double4 *peer[CMDR_MAX_PEERS];     // phase buffer of each ring owner (all = ph without the fused exchange)
 };
 
-struct __align__(16) TileS0 { double A, ar, ai, pad; };
+struct __align__(16) TileS0 { double A, B, c1r, c1i, c2r, c2i; };   // one row = two l (l_j = m + 2j, l_j + 1)
 struct __align__(16) TileS2 { double A, C, cpr, cpi, cmr, cmi; };
-struct __align__(16) TileA0 { double A, g; };
+struct __align__(16) TileA0 { double A, B; };
 struct __align__(16) TileA2 { double A, C, g, pad; };
 
 // analysis input: blocks indexed by the rank that owns the rings in the local buffer; with the
@@ -89,23 +90,27 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
 // ------------------------------------------------------------------------------------
-// spin-0 synthesis
+// spin-0 synthesis, two l per recurrence step (coef.cpp, fill_spin0_x2):
+//   nu_{j+1} = (A_j x^2 + B_j) nu_j - nu_{j-1};  sum_l a_l lam_l = sum_j nu_j c1_j + x sum_j nu_j c2_j
+//   c1_j = u_j a_{l_j} + v_j a_{l_j+2} (even l - m),  c2_j = h_j a_{l_j+1} (odd l - m);  south ring: x -> -x.
+// One group = 4 rows = 8 l.
 // ------------------------------------------------------------------------------------
 template <int MODE, int R>
-__device__ __forceinline__ void synth0_group(const TileS0 *t, const double (&x)[R], double (&cur)[R],
+__device__ __forceinline__ void synth0_group(const TileS0 *t, const double (&x2)[R], double (&cur)[R],
                                              double (&prev)[R], double (&per)[R], double (&pei)[R],
                                              double (&por)[R], double (&poi)[R], int (&k)[R]) {
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const double A = t[j].A, ar = t[j].ar, ai = t[j].ai;
+  for (int j = 0; j < 4; ++j) {
+    const double A = t[j].A, B = t[j].B;
+    const double c1r = t[j].c1r, c1i = t[j].c1i, c2r = t[j].c2r, c2i = t[j].c2i;
 #pragma unroll
     for (int r = 0; r < R; ++r) {
       if (MODE >= 1) {
         double v = (MODE == 2 || k[r] == 0) ? cur[r] : 0.0;
-        if (j & 1) { por[r] = fma(v, ar, por[r]); poi[r] = fma(v, ai, poi[r]); }
-        else       { per[r] = fma(v, ar, per[r]); pei[r] = fma(v, ai, pei[r]); }
+        per[r] = fma(v, c1r, per[r]); pei[r] = fma(v, c1i, pei[r]);
+        por[r] = fma(v, c2r, por[r]); poi[r] = fma(v, c2i, poi[r]);
       }
-      double nxt = step0(A, x[r], cur[r], prev[r]);
+      double nxt = step0x2(A, B, x2[r], cur[r], prev[r]);
       prev[r] = cur[r]; cur[r] = nxt;
     }
   }
@@ -116,31 +121,39 @@ __device__ __forceinline__ void synth0_group(const TileS0 *t, const double (&x)[
   }
 }
 
-// Tile rows for synthesis: {A', g a_lm} per (m, l), written once per transform by a prep kernel so
+// Tile rows for synthesis: {A_j, B_j, c1_j, c2_j} per (m, j), written once per transform by a prep kernel so
 // that every warp of the Legendre kernel can stage them with plain asynchronous copies.  Rows of one
-// m are padded with zero rows to a multiple of 8 (the kernels walk l in groups of 8).
+// m are padded with zero rows to a multiple of 8 (the kernels walk the rows in groups of 4).
 __global__ void __launch_bounds__(256) prep_s0_kernel(KParams p) {
   const int im = p.im0 + blockIdx.y, m = p.mval[im];
-  const int j = blockIdx.x * blockDim.x + threadIdx.x, l = m + j;
-  const int npad = (p.lmax - m + 1 + 7) & ~7;
+  const int j = blockIdx.x * blockDim.x + threadIdx.x, l = m + 2 * j;
+  const int J = p.lmax >= m ? (p.lmax - m) / 2 + 1 : 0;
+  const int npad = (J + 7) & ~7;
   if (j >= npad) return;
-  TileS0 e{0.0, 0.0, 0.0, 0.0};
-  if (l <= p.lmax) {
-    const double *coef = p.coef + p.cofs[im];
+  TileS0 e{0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+  if (j < J) {
+    const double2 rc = reinterpret_cast<const double2 *>(p.coef + p.cofs[im])[j];        // {A_j, B_j}
+    const double4 mx = reinterpret_cast<const double4 *>(p.coef2 + 2 * p.cofs[im])[j];   // {u_j, v_j, h_j, v_{j-1}}
     const double *a = p.alm0;
     const long long mvs = p.mvstart[im];
     const double nrm = (p.real_packed && m > 0) ? 0.70710678118654752440 : 1.0;
-    double2 c = reinterpret_cast<const double2 *>(coef)[l - m];   // {A', g}
-    double gs = c.y * nrm;
-    if (p.lscale0) gs *= p.lscale0[l];
-    e.A = c.x;
-    if (p.real_packed) {
-      if (m == 0) { e.ar = gs * a[mvs + l]; }
-      else { e.ar = gs * a[mvs + 2 * (long long)l]; e.ai = gs * a[mvs + 2 * (long long)l + 1]; }
-    } else {
-      e.ar = gs * a[2 * (mvs + l)];
-      e.ai = m == 0 ? 0.0 : gs * a[2 * (mvs + l) + 1];
-    }
+    auto load = [&](int ll, double &re, double &imv) {
+      re = 0.0; imv = 0.0;
+      if (ll > p.lmax) return;
+      const double f = p.lscale0 ? nrm * p.lscale0[ll] : nrm;
+      if (p.real_packed) {
+        if (m == 0) re = f * a[mvs + ll];
+        else { re = f * a[mvs + 2 * (long long)ll]; imv = f * a[mvs + 2 * (long long)ll + 1]; }
+      } else {
+        re = f * a[2 * (mvs + ll)];
+        if (m > 0) imv = f * a[2 * (mvs + ll) + 1];
+      }
+    };
+    double r0, i0, r1, i1, r2, i2;
+    load(l, r0, i0); load(l + 1, r1, i1); load(l + 2, r2, i2);
+    e.A = rc.x; e.B = rc.y;
+    e.c1r = fma(mx.x, r0, mx.y * r2); e.c1i = fma(mx.x, i0, mx.y * i2);
+    e.c2r = mx.z * r1; e.c2i = mx.z * i1;
   }
   reinterpret_cast<TileS0 *>(p.trows)[p.tofs[im] + j] = e;
 }
@@ -153,7 +166,8 @@ __global__ void __launch_bounds__(32, MINB) synth0_kernel(KParams p) {
   const int im = p.im0 + blockIdx.y, m = p.mval[im];
   const int lane = threadIdx.x;
   const int chunk0 = p.slot_begin + blockIdx.x * (32 * R);
-  double x[R], cur[R], prev[R], per[R], pei[R], por[R], poi[R];
+  const int J = p.lmax >= m ? (p.lmax - m) / 2 + 1 : 0;   // rows (steps of two l) of this m
+  double x[R], x2[R], cur[R], prev[R], per[R], pei[R], por[R], poi[R];
   int k[R], slot[R];
   bool any = false;
   const double K = p.Kstart[m];
@@ -162,39 +176,39 @@ __global__ void __launch_bounds__(32, MINB) synth0_kernel(KParams p) {
     slot[r] = chunk0 + lane * R + r;
     bool valid = slot[r] < p.nslots && m <= p.mlim[min(slot[r], p.nslots - 1)];
     per[r] = pei[r] = por[r] = poi[r] = 0.0;
-    prev[r] = 0.0; cur[r] = 0.0; k[r] = 0; x[r] = 0.0;
+    prev[r] = 0.0; cur[r] = 0.0; k[r] = 0; x[r] = 0.0; x2[r] = 0.0;
     if (valid) {
       const double4 tg = reinterpret_cast<const double4 *>(p.trig)[slot[r]];
       RingTrig g{tg.x, tg.y, tg.z, tg.w};
-      x[r] = g.cth;
+      x[r] = g.cth; x2[r] = g.cth * g.cth;
       start_spin0(m, K, g, cur[r], k[r]);
       any = true;
     }
   }
   if (__any_sync(FULL, any)) {
     const TileS0 *rows = reinterpret_cast<const TileS0 *>(p.trows) + p.tofs[im];
-    auto issue_tile = [&](int b, int lt) {     // rows past this m's padded range are never used
-      const char *src = reinterpret_cast<const char *>(rows + (lt - m));
+    auto issue_tile = [&](int b, int jt) {     // rows past this m's padded range are never used
+      const char *src = reinterpret_cast<const char *>(rows + jt);
       char *dst = reinterpret_cast<char *>(tile[b]);
 #pragma unroll
       for (int q = 0; q < (int)(TL * sizeof(TileS0)) / 512; ++q) cp_async16(dst + (q * 32 + lane) * 16, src + (q * 32 + lane) * 16);
       cp_async_commit();
     };
-    issue_tile(0, m);
+    issue_tile(0, 0);
     cp_async_wait_all();
     __syncwarp();
     int buf = 0;
-    for (int lt = m; lt <= p.lmax; lt += TL, buf ^= 1) {
-      if (lt + TL <= p.lmax) issue_tile(buf ^ 1, lt + TL);
-      const int ngroups = min(TL, p.lmax - lt + 8) / 8;
+    for (int jt = 0; jt < J; jt += TL, buf ^= 1) {
+      if (jt + TL < J) issue_tile(buf ^ 1, jt + TL);
+      const int ngroups = min(TL, J - jt + 3) / 4;
 #pragma unroll 1
       for (int g = 0; g < ngroups; ++g) {
         bool all_on = true, none_on = true;
 #pragma unroll
         for (int r = 0; r < R; ++r) { all_on &= (k[r] == 0); none_on &= (k[r] < 0); }
-        if (__all_sync(FULL, all_on)) synth0_group<2, R>(tile[buf] + 8 * g, x, cur, prev, per, pei, por, poi, k);
-        else if (__all_sync(FULL, none_on)) synth0_group<0, R>(tile[buf] + 8 * g, x, cur, prev, per, pei, por, poi, k);
-        else synth0_group<1, R>(tile[buf] + 8 * g, x, cur, prev, per, pei, por, poi, k);
+        if (__all_sync(FULL, all_on)) synth0_group<2, R>(tile[buf] + 4 * g, x2, cur, prev, per, pei, por, poi, k);
+        else if (__all_sync(FULL, none_on)) synth0_group<0, R>(tile[buf] + 4 * g, x2, cur, prev, per, pei, por, poi, k);
+        else synth0_group<1, R>(tile[buf] + 4 * g, x2, cur, prev, per, pei, por, poi, k);
       }
       cp_async_wait_all();
       __syncwarp();
@@ -204,7 +218,7 @@ __global__ void __launch_bounds__(32, MINB) synth0_kernel(KParams p) {
   for (int r = 0; r < R; ++r)
     if (slot[r] < p.nslots)
       *ph_out(p, 0, im, slot[r]) =
-          make_double4(per[r] + por[r], pei[r] + poi[r], per[r] - por[r], pei[r] - poi[r]);
+          make_double4(fma(x[r], por[r], per[r]), fma(x[r], poi[r], pei[r]), fma(-x[r], por[r], per[r]), fma(-x[r], poi[r], pei[r]));
 }
 
 // ------------------------------------------------------------------------------------
@@ -453,29 +467,33 @@ __device__ __forceinline__ void pipe_tail(const ReducePipe &in, ReducePipe &out,
 }
 
 // ------------------------------------------------------------------------------------
-// spin-0 analysis:  a_l = sum_rings mu_l * (l-m even ? qN+qS : qN-qS)
-// One group = 8 l; acc[2 j + {0,1}] = {re, im} (as named) of l = group start + j.
+// spin-0 analysis, two l per recurrence step (transpose of the synthesis above):
+//   T1_j = sum_rings nu_j (qN + qS),  T2_j = sum_rings nu_j x (qN - qS)
+//   a_{l_j} = u_j T1_j + v_{j-1} T1_{j-1},  a_{l_j+1} = h_j T2_j        (done in the per-tile flush)
+// One group = 4 rows (8 l); acc[4 j + 2 s + c] = {T1.re, T1.im, T2.re, T2.im} (as named) of row j, i.e. the layout of
+// the spin-2 kernel, whose reduction is reused: lanes with bit 3 set run with the T1 / T2 inputs swapped, lanes with
+// bit 4 set with re / im swapped.  w[r] = {s.re, s.im, d.re, d.im} (before the per-lane permutation),
+// s = qN + qS, d = x (qN - qS).
 // ------------------------------------------------------------------------------------
 template <int MODE, int R>
-__device__ __forceinline__ void anal0_fma(const TileA0 *tA, const double (&x)[R], double (&cur)[R],
-                                          double (&prev)[R], const double (&sr)[R], const double (&si)[R],
-                                          const double (&dr)[R], const double (&di)[R], int (&k)[R],
+__device__ __forceinline__ void anal0_fma(const TileA0 *tA, const double (&x2)[R], double (&cur)[R],
+                                          double (&prev)[R], const double (&w)[R][4], int (&k)[R],
                                           double (&acc)[16]) {
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const double A = tA[j].A;
-    double ar = 0.0, ai = 0.0;
+  for (int j = 0; j < 4; ++j) {
+    const double A = tA[j].A, B = tA[j].B;
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
 #pragma unroll
     for (int r = 0; r < R; ++r) {
       if (MODE >= 1) {
         double v = (MODE == 2 || k[r] == 0) ? cur[r] : 0.0;
-        if (j & 1) { ar = fma(v, dr[r], ar); ai = fma(v, di[r], ai); }
-        else       { ar = fma(v, sr[r], ar); ai = fma(v, si[r], ai); }
+        s0 = fma(v, w[r][0], s0); s1 = fma(v, w[r][1], s1);
+        s2 = fma(v, w[r][2], s2); s3 = fma(v, w[r][3], s3);
       }
-      double nxt = step0(A, x[r], cur[r], prev[r]);
+      double nxt = step0x2(A, B, x2[r], cur[r], prev[r]);
       prev[r] = cur[r]; cur[r] = nxt;
     }
-    if (MODE >= 1) { acc[2 * j] = ar; acc[2 * j + 1] = ai; }
+    if (MODE >= 1) { acc[4 * j] = s0; acc[4 * j + 1] = s1; acc[4 * j + 2] = s2; acc[4 * j + 3] = s3; }
   }
   if (MODE < 2) {
 #pragma unroll
@@ -484,26 +502,26 @@ __device__ __forceinline__ void anal0_fma(const TileA0 *tA, const double (&x)[R]
   }
 }
 
-// steady-phase step: FMAs of one group with stage 1 applied per l, stages 2-5 on the older groups
+// steady-phase step: FMAs of one group with stage 1 applied per row, stages 2-5 on the older groups
 template <int R, bool FMA>
-__device__ __forceinline__ void anal0_step(const TileA0 *tA, const double (&x)[R], double (&cur)[R],
-                                           double (&prev)[R], const double (&sr)[R], const double (&si)[R],
-                                           const double (&dr)[R], const double (&di)[R],
+__device__ __forceinline__ void anal0_step(const TileA0 *tA, const double (&x2)[R], double (&cur)[R],
+                                           double (&prev)[R], const double (&w)[R][4],
                                            const ReducePipe &in, ReducePipe &out, double *dst, bool store, int lane) {
-  pipe_tail<false>(in, out, dst, store, lane);
+  pipe_tail<true>(in, out, dst, store, lane);
   if (FMA) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const double A = tA[j].A;
-      double ar = 0.0, ai = 0.0;
+    for (int j = 0; j < 4; ++j) {
+      const double A = tA[j].A, B = tA[j].B;
+      double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
 #pragma unroll
       for (int r = 0; r < R; ++r) {
-        if (j & 1) { ar = fma(cur[r], dr[r], ar); ai = fma(cur[r], di[r], ai); }
-        else       { ar = fma(cur[r], sr[r], ar); ai = fma(cur[r], si[r], ai); }
-        double nxt = step0(A, x[r], cur[r], prev[r]);
+        s0 = fma(cur[r], w[r][0], s0); s1 = fma(cur[r], w[r][1], s1);
+        s2 = fma(cur[r], w[r][2], s2); s3 = fma(cur[r], w[r][3], s3);
+        double nxt = step0x2(A, B, x2[r], cur[r], prev[r]);
         prev[r] = cur[r]; cur[r] = nxt;
       }
-      out.v1[j] = ar + shfl_xor_d(ai, 16);
+      out.v1[2 * j] = s0 + shfl_xor_d(s1, 16);
+      out.v1[2 * j + 1] = s2 + shfl_xor_d(s3, 16);
     }
   }
 }
@@ -511,68 +529,75 @@ __device__ __forceinline__ void anal0_step(const TileA0 *tA, const double (&x)[R
 // Analysis kernels, common structure: ONE WARP PER CTA, no block-level synchronisation at all.
 // A thread owns R ADJACENT ring pairs, the warp 32 R adjacent ones (similar colatitude, so they
 // cross the accumulation threshold at similar l, and whole warps fall beyond the m cut-off near
-// the poles).  The warp stages its own coefficient tiles (TL l, double buffered, cp.async
+// the poles).  The warp stages its own coefficient tiles (TL rows, double buffered, cp.async
 // straight from the table) and walks the groups of a tile in two phases: a transient one while
 // some of its rings are still below the threshold (warp-uniform choice between "recurrence only"
 // and "predicated", reduction done at once) and a steady one (all rings on -- they stay on) in
 // which the butterfly of group g-1 sits in the same basic block as the FMAs of group g, so the
-// shuffle latency hides behind FP64 work.  After each tile the reduced sums are read back l-major
+// shuffle latency hides behind FP64 work.  After each tile the reduced sums are read back row-major
 // from shared memory and added to the a_lm with fully coalesced atomics (other warps hold the
 // other rings of the same m).
 template <int R, int MINB>
 __global__ void __launch_bounds__(32, MINB) anal0_kernel(KParams p) {
   __shared__ __align__(16) TileA0 tile[2][TL];
-  __shared__ __align__(16) double red[TL * 2];
+  __shared__ __align__(16) double red[(TL + 1) * 4];   // row 0: T1 of the last row of the previous tile
   const int im = p.im0 + blockIdx.y, m = p.mval[im];
   const int lane = threadIdx.x;
   const int chunk0 = p.slot_begin + blockIdx.x * (32 * R);
-  double x[R], cur[R], prev[R], sr[R], si[R], dr[R], di[R];
+  const int J = p.lmax >= m ? (p.lmax - m) / 2 + 1 : 0;   // rows (steps of two l) of this m
+  double x2[R], cur[R], prev[R], w[R][4];
   int k[R];
   bool any = false;
   const double K = p.Kstart[m];
-  const bool swapRI = lane & 16;
+  const bool swapRI = lane & 16, swapT = lane & 8;
 #pragma unroll
   for (int r = 0; r < R; ++r) {
     int slot = chunk0 + lane * R + r;
     bool valid = slot < p.nslots && m <= p.mlim[min(slot, p.nslots - 1)];
-    prev[r] = cur[r] = x[r] = 0.0; k[r] = 0;
-    sr[r] = si[r] = dr[r] = di[r] = 0.0;
+    prev[r] = cur[r] = x2[r] = 0.0; k[r] = 0;
+    w[r][0] = w[r][1] = w[r][2] = w[r][3] = 0.0;
     if (valid) {
       const double4 tg = reinterpret_cast<const double4 *>(p.trig)[slot];
       RingTrig g{tg.x, tg.y, tg.z, tg.w};
-      x[r] = g.cth;
+      x2[r] = g.cth * g.cth;
       start_spin0(m, K, g, cur[r], k[r]);
       double4 q = *ph_in(p, 0, im, slot);
-      const double re_s = q.x + q.z, im_s = q.y + q.w, re_d = q.x - q.z, im_d = q.y - q.w;
-      sr[r] = swapRI ? im_s : re_s; si[r] = swapRI ? re_s : im_s;
-      dr[r] = swapRI ? im_d : re_d; di[r] = swapRI ? re_d : im_d;
+      double z[4] = {q.x + q.z, q.y + q.w, g.cth * (q.x - q.z), g.cth * (q.y - q.w)};
+      // w[i] = z[i ^ (swapT ? 2 : 0) ^ (swapRI ? 1 : 0)]
+#pragma unroll
+      for (int i = 0; i < 4; i += 2) {
+        double a0 = swapT ? z[i ^ 2] : z[i], a1 = swapT ? z[(i ^ 2) + 1] : z[i + 1];
+        w[r][i] = swapRI ? a1 : a0; w[r][i + 1] = swapRI ? a0 : a1;
+      }
       any = true;
     }
   }
   if (!__any_sync(FULL, any)) return;
   const double *coef = p.coef + p.cofs[im];
+  const double4 *mix = reinterpret_cast<const double4 *>(p.coef2 + 2 * p.cofs[im]);   // {u_j, v_j, h_j, v_{j-1}}
   const long long mvs = p.mvstart[im];
   // real-packed: orthonormal real basis (sqrt2 both ways).  complex a_lm: the phases carry the
   // factor 2 of the m>0 terms, so the adjoint needs 1/2 to return sum conj(Y) x as libsharp2 does
   const double nrm = m > 0 ? (p.real_packed ? 0.70710678118654752440 : 0.5) : 1.0;
-  // rows past lmax belong to the next m (or the table's zero padding): finite, never used
-  auto issue_tile = [&](int b, int lt) {
-    const char *src = reinterpret_cast<const char *>(coef + 2 * (size_t)(lt - m));
+  // rows past the last one belong to the next m (or the table's zero padding): finite, never used
+  auto issue_tile = [&](int b, int jt) {
+    const char *src = reinterpret_cast<const char *>(coef + 2 * (size_t)jt);
     char *dst = reinterpret_cast<char *>(tile[b]);
 #pragma unroll
     for (int q = 0; q < (int)(TL * sizeof(TileA0)) / 512; ++q) cp_async16(dst + (q * 32 + lane) * 16, src + (q * 32 + lane) * 16);
     cp_async_commit();
   };
-  issue_tile(0, m);
+  issue_tile(0, 0);
+  if (lane < 4) red[lane] = 0.0;
   cp_async_wait_all();
   __syncwarp();
   int buf = 0;
   bool steady = false;
-  for (int lt = m; lt <= p.lmax; lt += TL, buf ^= 1) {
-    if (lt + TL <= p.lmax) issue_tile(buf ^ 1, lt + TL);
-    const int ngroups = min(TL, p.lmax - lt + 8) / 8;
+  for (int jt = 0; jt < J; jt += TL, buf ^= 1) {
+    if (jt + TL < J) issue_tile(buf ^ 1, jt + TL);
+    const int ngroups = min(TL, J - jt + 3) / 4;
     const TileA0 *T = tile[buf];
-    double *dst = red;
+    double *dst = red + 4;
     int g = 0;
     if (!steady) {
 #pragma unroll 1
@@ -583,11 +608,11 @@ __global__ void __launch_bounds__(32, MINB) anal0_kernel(KParams p) {
         if (__all_sync(FULL, all_on)) { steady = true; break; }
         double acc[16];
         if (__all_sync(FULL, none_on)) {
-          anal0_fma<0, R>(T + 8 * g, x, cur, prev, sr, si, dr, di, k, acc);
+          anal0_fma<0, R>(T + 4 * g, x2, cur, prev, w, k, acc);
           if (!(lane & 1)) dst[16 * g + (lane >> 1)] = 0.0;
         } else {
-          anal0_fma<1, R>(T + 8 * g, x, cur, prev, sr, si, dr, di, k, acc);
-          reduce_store_s0(acc, dst + 16 * g, lane);
+          anal0_fma<1, R>(T + 4 * g, x2, cur, prev, w, k, acc);
+          reduce_store_s2(acc, dst + 16 * g, lane);
         }
       }
     }
@@ -602,30 +627,35 @@ __global__ void __launch_bounds__(32, MINB) anal0_kernel(KParams p) {
 #pragma unroll 2
       for (; g < ngroups; ++g) {
         ReducePipe nx;
-        anal0_step<R, true>(T + 8 * g, x, cur, prev, sr, si, dr, di, st, nx, dst + 16 * (g - 4), g - 4 >= gs, lane);
+        anal0_step<R, true>(T + 4 * g, x2, cur, prev, w, st, nx, dst + 16 * (g - 4), g - 4 >= gs, lane);
         st = nx;
       }
 #pragma unroll
       for (int d = 0; d < 4; ++d, ++g) {   // drain
         ReducePipe nx;
-        anal0_step<R, false>(T, x, cur, prev, sr, si, dr, di, st, nx, dst + 16 * (g - 4), g - 4 >= gs, lane);
+        anal0_step<R, false>(T, x2, cur, prev, w, st, nx, dst + 16 * (g - 4), g - 4 >= gs, lane);
         st = nx;
       }
     }
     cp_async_wait_all();
     __syncwarp();
-    // flush the tile: lane pair (2i, 2i+1) = (re, im) of one l -> contiguous atomics
+    // flush the tile: four consecutive lanes = (re, im) of l_j and of l_j + 1 -> contiguous atomics
     double *a = p.alm0;
 #pragma unroll 1
-    for (int e = lane; e < 2 * TL; e += 32) {
-      const int li = e >> 1, part = e & 1, l = lt + li;
+    for (int e = lane; e < 4 * TL; e += 32) {
+      const int li = e >> 2, odd = (e >> 1) & 1, part = e & 1, j = jt + li, l = m + 2 * j + odd;
       if (l <= p.lmax && (m > 0 || part == 0)) {
-        double val = T[li].g * nrm * red[e];
+        const double4 mx = mix[j];
+        double val = odd ? mx.z * red[4 * (li + 1) + 2 + part]
+                         : fma(mx.x, red[4 * (li + 1) + part], mx.w * red[4 * li + part]);
+        val *= nrm;
         if (p.lscale0) val *= p.lscale0[l];
         const long long idx = p.real_packed ? (m == 0 ? mvs + l : mvs + 2 * (long long)l + part) : 2 * (mvs + l) + part;
         atomicAdd(&a[idx], val);
       }
     }
+    __syncwarp();
+    if (lane < 2) red[lane] = red[4 * TL + lane];   // T1 of the tile's last row, for the first row of the next tile
     __syncwarp();
   }
 }
@@ -874,7 +904,7 @@ static KParams make_params(const LegGeom &g, const LegAlm &a, double *alm0, doub
   p.spin = a.spin; p.spinsign = (a.spin & 1) ? 1.0 : -1.0;
   p.slot_begin = g.slot_begin; p.nslots = g.slot_end >= 0 ? g.slot_end : g.nslots; p.NPL = g.NPL; p.NML = g.NML; p.ncomp_tot = g.ncomp_tot; p.comp0 = g.comp0;
   p.ring_major = phase_ring_major() ? 1 : 0;
-  p.mval = a.mval; p.mvstart = a.mvstart; p.coef = a.coef; p.cofs = a.cofs; p.Kstart = a.Kstart;
+  p.mval = a.mval; p.mvstart = a.mvstart; p.coef = a.coef; p.coef2 = a.coef2; p.cofs = a.cofs; p.Kstart = a.Kstart;
   p.tofs = nullptr; p.trows = nullptr;
   p.im0 = a.im_begin;
   p.trig = g.trig; p.mlim = g.mlim; p.wslot = g.wslot;

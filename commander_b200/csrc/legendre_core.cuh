@@ -84,6 +84,11 @@ CMDR_HD double step0(double A, double x, double cur, double prev) {
   return fma(A * x, cur, -prev);
 }
 
+// one step of the two-l-per-step form (coef.cpp, fill_spin0_x2): returns nu_{j+1}; x2 = x^2
+CMDR_HD double step0x2(double A, double B, double x2, double cur, double prev) {
+  return fma(fma(A, x2, B), cur, -prev);
+}
+
 // ---- spin 2 --------------------------------------------------------------
 // P = (+2)lambda_{l0,m}, M = (-2)lambda_{l0,m} at l0 = max(m,2).
 //   m>=2: P = K2[m] sth^(m-2) sh^4 , M = K2[m] sth^(m-2) ch^4

@@ -12,12 +12,17 @@ namespace cmdr {
 // ---- host-side table builders (coef.cpp)
 void build_coef_table(int lmax, int spin, const std::vector<int> &mval, std::vector<double> &tab,
                       std::vector<long long> &ofs);
+// spin 0 in steps of two l (x^2 recurrence, coef.cpp): rec rows {a_j, b'_j} (ofs in doubles, 2 per row), mix rows {u_j, v_j, h_j, v_{j-1}}
+void build_coef_table_x2(int lmax, const std::vector<int> &mval, std::vector<double> &rec, std::vector<double> &mix,
+                         std::vector<long long> &ofs);
+constexpr int COEF_KEY_S0X2 = -1;   // key of that table in sharp_alm_info::coef (key 0 stays the one-step table of invn.cu)
 void build_start_norms(int mmax, std::vector<double> &K0, std::vector<double> &K2);
 void build_start_norms_spin(int mmax, int spin, std::vector<double> &Ks);
 
 struct CoefDev {            // device copy of one (alm_info, spin) coefficient table
   bool ready = false;
-  double *tab = nullptr;    // spin 0: {A', g} per l ; spin 2: {A', C', g, 0} per l
+  double *tab = nullptr;    // spin 0: {A', g} per l ; spin 2: {A', C', g, 0} per l ; COEF_KEY_S0X2: {a_j, b'_j} per two l
+  double *tab2 = nullptr;   // COEF_KEY_S0X2 only: mix rows {u_j, v_j, h_j, v_{j-1}}, row index = ofs / 2 + j
   long long *ofs = nullptr; // per local m: offset (in doubles) of l = l0
   long long *tofs = nullptr; // per local m: first synthesis tile row (rows padded to a multiple of 8)
   long long trows = 0;       // total synthesis tile rows

@@ -115,6 +115,20 @@ def test_device_recurrence_math_spin0(emul):
                 assert np.max(np.abs(P - ref)) <= 2e-12 * max(np.max(np.abs(ref)), 1e-30) + 1e-19
 
 
+def test_device_recurrence_math_spin0_two_l_per_step(emul):
+    """The transform kernels' spin-0 form -- recurrence in x^2, two l per step, lambda of both parities rebuilt
+    from the mix rows (coef.cpp fill_spin0_x2, legendre_core.cuh step0x2; the scheme libsharp2 uses for scalar
+    transforms) -- against the reference's recurrence (math_tools.f90:926-1028).  Near the equator the even-l values
+    are differences of O(l) larger numbers, hence the looser relative bound than the one-step form."""
+    for nside, lmax in ((64, 200), (256, 700), (256, 701)):
+        for m in (0, 1, 2, 3, 17, 100, 199, lmax - 1, lmax):
+            for north in (1, 2, nside // 2, nside, nside + 1, 2 * nside - 1, 2 * nside):
+                cth, sth, *_ = D.healpix_ring(nside, north)
+                ref = D.comp_normalised_Plm(lmax, m, math.atan2(sth, cth))
+                P, _ = emul(-1, lmax, m, nside, north)
+                assert np.max(np.abs(P - ref)) <= 2e-11 * max(np.max(np.abs(ref)), 1e-30) + 1e-19, (nside, lmax, m, north)
+
+
 def test_device_recurrence_math_spin2(emul):
     import mpmath as mp
     mp.mp.dps = 400
