@@ -398,20 +398,7 @@ __device__ __forceinline__ void bfly_fixed(double *v, int bit) {
   for (int i = 0; i < H; ++i) v[i] = v[2 * i] + shfl_xor_d(v[2 * i + 1], bit);
 }
 
-// spin 0: acc[2 j + c], j = l in group (8), c = re/im as NAMED (lane bit 4 swaps the meaning).
-// On return the even lanes have stored the total of l = 4 b3 + 2 b2 + b1, part = b4.
-__device__ __forceinline__ int store_index_s0(int lane) {
-  return 2 * (((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1)) + ((lane >> 4) & 1);
-}
-__device__ __forceinline__ void reduce_store_s0(double (&v)[16], double *dst, int lane) {
-  bfly_fixed<8>(v, 16);          // v[j], j = 0..7
-  bfly_select<4>(v, lane, 8);    // j bit 2 <- lane bit 3
-  bfly_select<2>(v, lane, 4);
-  bfly_select<1>(v, lane, 2);
-  v[0] += shfl_xor_d(v[0], 1);
-  if (!(lane & 1)) dst[store_index_s0(lane)] = v[0];
-}
-// spin 2: acc[4 j + 2 s + c], j = l in group (4), s = S1/S2 as named (lane bit 3 swaps),
+// acc[4 j + 2 s + c], j = l (spin 0: row of two l) in group (4), s = S1/S2 (spin 0: T1/T2) as named (lane bit 3 swaps),
 // c = re/im as named (lane bit 4 swaps).  Even lanes store l = 2 b2 + b1, s = b3, part = b4.
 __device__ __forceinline__ int store_index_s2(int lane) {
   return 4 * (((lane >> 2) & 1) * 2 + ((lane >> 1) & 1)) + 2 * ((lane >> 3) & 1) + ((lane >> 4) & 1);
@@ -433,11 +420,13 @@ __device__ __forceinline__ void reduce_store_s2(double (&v)[16], double *dst, in
 // leave the FP64 pipe idle).  Same 15 live doubles as holding one extra group of sums.
 struct ReducePipe { double v1[8], v2[4], v3[2], v4; };
 
+// `sidx`: shared-memory byte address of this lane's slot in group 0 of the tile (16 doubles per group).  Both lanes of a
+// pair hold the same total after stage 5 and store it to the same address: no divergence, no predicate.
 template <bool SPIN2>
-__device__ __forceinline__ void pipe_tail(const ReducePipe &in, ReducePipe &out, double *dst, bool store, int lane) {
+__device__ __forceinline__ void pipe_tail(const ReducePipe &in, ReducePipe &out, unsigned sidx, int gstore, bool store, int lane) {
   {  // stage 5 -> shared memory (group g-4)
     double v5 = in.v4 + shfl_xor_d(in.v4, 1);
-    if (store && !(lane & 1)) dst[SPIN2 ? store_index_s2(lane) : store_index_s0(lane)] = v5;
+    if (store) asm volatile("st.shared.f64 [%0], %1;" ::"r"(sidx + 128u * (unsigned)gstore), "d"(v5) : "memory");
   }
   {  // stage 4 (group g-3)
     const bool hi = lane & 2;
@@ -506,8 +495,8 @@ __device__ __forceinline__ void anal0_fma(const TileA0 *tA, const double (&x2)[R
 template <int R, bool FMA>
 __device__ __forceinline__ void anal0_step(const TileA0 *tA, const double (&x2)[R], double (&cur)[R],
                                            double (&prev)[R], const double (&w)[R][4],
-                                           const ReducePipe &in, ReducePipe &out, double *dst, bool store, int lane) {
-  pipe_tail<true>(in, out, dst, store, lane);
+                                           const ReducePipe &in, ReducePipe &out, unsigned sidx, int gstore, bool store, int lane) {
+  pipe_tail<true>(in, out, sidx, gstore, store, lane);
   if (FMA) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -593,6 +582,8 @@ __global__ void __launch_bounds__(32, MINB) anal0_kernel(KParams p) {
   __syncwarp();
   int buf = 0;
   bool steady = false;
+  unsigned sidx = (unsigned)__cvta_generic_to_shared(red + 4 + store_index_s2(lane));
+  asm volatile("mov.u32 %0, %0;" : "+r"(sidx));   // opaque: kept in a register instead of being recomputed per group
   for (int jt = 0; jt < J; jt += TL, buf ^= 1) {
     if (jt + TL < J) issue_tile(buf ^ 1, jt + TL);
     const int ngroups = min(TL, J - jt + 3) / 4;
@@ -627,13 +618,13 @@ __global__ void __launch_bounds__(32, MINB) anal0_kernel(KParams p) {
 #pragma unroll 2
       for (; g < ngroups; ++g) {
         ReducePipe nx;
-        anal0_step<R, true>(T + 4 * g, x2, cur, prev, w, st, nx, dst + 16 * (g - 4), g - 4 >= gs, lane);
+        anal0_step<R, true>(T + 4 * g, x2, cur, prev, w, st, nx, sidx, g - 4, g - 4 >= gs, lane);
         st = nx;
       }
 #pragma unroll
       for (int d = 0; d < 4; ++d, ++g) {   // drain
         ReducePipe nx;
-        anal0_step<R, false>(T, x2, cur, prev, w, st, nx, dst + 16 * (g - 4), g - 4 >= gs, lane);
+        anal0_step<R, false>(T, x2, cur, prev, w, st, nx, sidx, g - 4, g - 4 >= gs, lane);
         st = nx;
       }
     }
@@ -641,7 +632,7 @@ __global__ void __launch_bounds__(32, MINB) anal0_kernel(KParams p) {
     __syncwarp();
     // flush the tile: four consecutive lanes = (re, im) of l_j and of l_j + 1 -> contiguous atomics
     double *a = p.alm0;
-#pragma unroll 1
+#pragma unroll 4
     for (int e = lane; e < 4 * TL; e += 32) {
       const int li = e >> 2, odd = (e >> 1) & 1, part = e & 1, j = jt + li, l = m + 2 * j + odd;
       if (l <= p.lmax && (m > 0 || part == 0)) {
@@ -720,8 +711,8 @@ template <int R, bool FMA>
 __device__ __forceinline__ void anal2_step(const TileA2 *t, const int csign, const double (&x)[R], double (&Pa)[R],
                                            double (&Pap)[R], double (&Pb)[R], double (&Pbp)[R],
                                            const double (&w)[R][8], const ReducePipe &in, ReducePipe &out,
-                                           double *dst, bool store, int lane) {
-  pipe_tail<true>(in, out, dst, store, lane);
+                                           unsigned sidx, int gstore, bool store, int lane) {
+  pipe_tail<true>(in, out, sidx, gstore, store, lane);
   if (FMA) {
     double s[4][4];
 #pragma unroll
@@ -820,6 +811,8 @@ __global__ void __launch_bounds__(32, MINB) anal2_kernel(KParams p) {
   __syncwarp();
   int buf = 0;
   bool steady = false;
+  unsigned sidx = (unsigned)__cvta_generic_to_shared(red + store_index_s2(lane));
+  asm volatile("mov.u32 %0, %0;" : "+r"(sidx));   // opaque: kept in a register instead of being recomputed per group
   for (int lt = l0; lt <= p.lmax; lt += TL, buf ^= 1) {
     if (lt + TL <= p.lmax) issue_tile(buf ^ 1, lt + TL);
     const int ngroups = min(TL, p.lmax - lt + 4) / 4;
@@ -854,13 +847,13 @@ __global__ void __launch_bounds__(32, MINB) anal2_kernel(KParams p) {
 #pragma unroll 2
       for (; g < ngroups; ++g) {
         ReducePipe nx;
-        anal2_step<R, true>(T + 4 * g, csign, x, Pa, Pap, Pb, Pbp, w, st, nx, dst + 16 * (g - 4), g - 4 >= gs, lane);
+        anal2_step<R, true>(T + 4 * g, csign, x, Pa, Pap, Pb, Pbp, w, st, nx, sidx, g - 4, g - 4 >= gs, lane);
         st = nx;
       }
 #pragma unroll
       for (int d = 0; d < 4; ++d, ++g) {   // drain
         ReducePipe nx;
-        anal2_step<R, false>(T, csign, x, Pa, Pap, Pb, Pbp, w, st, nx, dst + 16 * (g - 4), g - 4 >= gs, lane);
+        anal2_step<R, false>(T, csign, x, Pa, Pap, Pb, Pbp, w, st, nx, sidx, g - 4, g - 4 >= gs, lane);
         st = nx;
       }
     }
@@ -868,7 +861,7 @@ __global__ void __launch_bounds__(32, MINB) anal2_kernel(KParams p) {
     __syncwarp();
     // flush the tile: lane pair (2i, 2i+1) = (re, im) of one l -> contiguous atomics
     double *aE = p.alm0, *aB = p.alm1;
-#pragma unroll 1
+#pragma unroll 4
     for (int e = lane; e < 2 * TL; e += 32) {
       const int li = e >> 1, part = e & 1, l = lt + li;
       if (l <= p.lmax && (m > 0 || part == 0)) {
@@ -971,9 +964,11 @@ void launch_legendre_anal(int spin, const LegGeom &g, const LegAlm &a, double *c
   const int nmr = (a.im_end >= 0 ? a.im_end : a.nm) - a.im_begin;   // local m's of this launch
   if (nmr <= 0) return;
   KParams p = make_params(g, a, alm[0], spin ? alm[1] : nullptr, const_cast<double4 *>(ph));
-  static const int r0 = env_int("CMDR_SHT_R_A0", 4), r2 = env_int("CMDR_SHT_R_A2", 4);
+  // spin 0: 8 ring pairs per thread since the two-l-per-step kernels (fewer registers per ring pair; the butterfly and the
+  // per-tile flush are per warp, so their share halves): 8.71 -> 8.31 ms at nside 2048 / lmax 4000
+  static const int r0 = env_int("CMDR_SHT_R_A0", 8), r2 = env_int("CMDR_SHT_R_A2", 4);
   // resident warps per SM the register allocation is capped for (tuning: CMDR_SHT_MINB_A0 / _A2)
-  static const int b0 = env_int("CMDR_SHT_MINB_A0", 16), b2 = env_int("CMDR_SHT_MINB_A2", 12);
+  static const int b0 = env_int("CMDR_SHT_MINB_A0", 12), b2 = env_int("CMDR_SHT_MINB_A2", 12);
   if (spin == 0) {
     switch (r0 * 100 + b0) {
       case 416: launch_w<4>(anal0_kernel<4, 16>, p, nmr, st); break;
