@@ -63,4 +63,25 @@ BF_HD void rs_butterfly4(const double2 (&c)[4], double2 (&o)[4]) {
   o[3] = bf_sub(d02, d13);
 }
 
+// (3) One ring of even length n = 2 h through ONE complex transform of length h (ring_half_kernel).  The samples of
+//     a ring are real, so its spectrum X_b = sum_j x_j e^{-2 pi i j b / n} is Hermitian and half of a length-n complex
+//     transform is redundant; the whole-ring kernels use that redundancy to pack the north ring and its southern
+//     mirror into one complex transform (z = x_N + i x_S), at the price of a footprint of n complex numbers per
+//     CTA (1 CTA per SM for the belt at nside 2048).  Packing even and odd samples of ONE ring instead,
+//         y_p = x_{2p} + i x_{2p+1},   p < h,
+//     costs the same arithmetic per ring pair and halves the footprint, so that 3 CTAs share an SM:
+//         synthesis  Y_k = (X_k + X_{k+h}) + i w^k (X_k - X_{k+h}),  w = e^{2 pi i / n};   y = DFT+_h(Y)
+//         analysis   Y = DFT-_h(y);  X_b = E_k + e^{-2 pi i b / n} O_k,  k = b mod h,
+//                    E_k = (Y_k + conj Y_{h-k}) / 2,  O_k = (Y_k - conj Y_{h-k}) / (2 i)
+BF_HD double2 rh_pack(double2 Xk, double2 Xkh, double2 wk) {           // wk = e^{i pi k / h}
+  const double2 a = bf_add(Xk, Xkh), b = bf_mul_pi(bf_mul(bf_sub(Xk, Xkh), wk));
+  return bf_add(a, b);
+}
+BF_HD double2 rh_unpack(double2 Ya, double2 Yb, double2 wb) {          // Ya = Y_k, Yb = Y_{(h-k) mod h}, wb = e^{-2 pi i b / n}
+  double2 E, O;
+  E.x = 0.5 * (Ya.x + Yb.x); E.y = 0.5 * (Ya.y - Yb.y);               // (Ya + conj Yb) / 2
+  O.x = 0.5 * (Ya.y + Yb.y); O.y = -0.5 * (Ya.x - Yb.x);              // (Ya - conj Yb) / (2 i)
+  return bf_add(E, bf_mul(O, wb));
+}
+
 }  // namespace cmdr

@@ -638,6 +638,145 @@ __global__ void __launch_bounds__(NT) ring_pow2_kernel(FParams p, int first_pair
   }
 }
 
+// ---- rings of power-of-two length, ONE RING per CTA through a complex transform of half the ring length
+// (ring_split.cuh (3)): 64 KB + padding for the belt of nside 2048 instead of 128 KB per ring pair, so that three CTAs
+// share an SM and one CTA's DRAM phases (fold, scatter) run beside the FFT passes of the others.  grid.x = 2 pairs
+// (hemisphere = blockIdx.x & 1: the north and the south CTA of a pair read the two halves of the same 32-byte phase
+// elements back to back, the second one from L2).
+__device__ __forceinline__ double2 ph_half_load(const FParams &p, const PhaseLayout &L, int src, int c, int im, int pair, int hemi) {
+  return reinterpret_cast<const double2 *>(ph_at(p, L, src, c, im, pair))[hemi];
+}
+// folded spectrum bin b (0 <= b < n) of one ring without the phi0 factor e^{i pi b / n} (see fold_bin)
+__device__ __forceinline__ double2 fold_bin1(const FParams &p, const PhaseLayout &L, int c, int pair, int n, bool shifted, int b, int hemi) {
+  double2 acc = make_double2(0.0, 0.0);
+  double sg = 1.0;
+  for (int m = b; m <= L.mmax; m += n, sg = shifted ? -sg : sg) {            // m == b: p_m
+    const int src = L.m2src[m];
+    if (src < 0) continue;
+    const double2 q = ph_half_load(p, L, src, c, L.m2im[m], pair, hemi);
+    if (m == 0) acc.x += q.x; else { acc.x += sg * q.x; acc.y += sg * q.y; }
+  }
+  sg = shifted ? -1.0 : 1.0;
+  for (int m = n - b; m <= L.mmax; m += n, sg = shifted ? -sg : sg) {        // m == -b, m >= 1: conj p_m
+    const int src = L.m2src[m];
+    if (src < 0) continue;
+    const double2 q = ph_half_load(p, L, src, c, L.m2im[m], pair, hemi);
+    acc.x += sg * q.x; acc.y -= sg * q.y;
+  }
+  return acc;
+}
+
+template <int DIR, int NT>
+__global__ void __launch_bounds__(NT) ring_half_kernel(FParams p, int first_pair, int n, int bitsh, const double2 *__restrict__ tw) {
+  extern __shared__ double2 u_sm[];
+  const int pair = first_pair + (blockIdx.x >> 1), hemi = blockIdx.x & 1, c = blockIdx.y;
+  const int h = n >> 1;
+  const bool shifted = p.shifted[pair];
+  const PhaseLayout &L = p.L;
+  const long long o = hemi ? p.ofsS[pair] : p.ofsN[pair];
+  if (DIR == 0 && o < 0) return;                       // ring absent (equator mirror, ring subsets): nothing to write
+  double2 *work = u_sm, *T = work + bf_padded(h);
+  const int ntw = bf2_tw_total(h);
+  for (int k = threadIdx.x; k < ntw; k += NT) T[k] = tw[k];
+  const double w = p.weighted ? p.wgt[pair] : 1.0;
+  auto slot = [bitsh](int k) { return bf_pidx<true>((int)(__brev((unsigned)k) >> (32 - bitsh))); };
+  if (DIR == 0) {
+    // position k holds Y_k = e^{i pi k / n} [ (X_k + f X_{k+h}) + i w^k (X_k - f X_{k+h}) ], X without the phi0 factor,
+    // f = e^{i pi h / n} = i for shifted rings
+    if (L.mmax < h) {                                  // no aliasing: X_k = p_k, X_{k+h} = -+ conj p_{h-k}; loads in flight
+      constexpr int NB = 4;
+      const double sgc = shifted ? -1.0 : 1.0;
+      for (int t0 = threadIdx.x; t0 < h; t0 += NT * NB) {
+        double2 qd[NB], qc[NB];
+        bool hd[NB], hc[NB];
+#pragma unroll
+        for (int j = 0; j < NB; ++j) {
+          const int k = t0 + j * NT, m2 = h - k;
+          hd[j] = hc[j] = false;
+          if (k >= h) continue;
+          if (k <= L.mmax) {
+            const int src = L.m2src[k];
+            if (src >= 0) { hd[j] = true; qd[j] = ph_half_load(p, L, src, c, L.m2im[k], pair, hemi); }
+          }
+          if (m2 <= L.mmax) {                          // m2 >= 1 always
+            const int src = L.m2src[m2];
+            if (src >= 0) { hc[j] = true; qc[j] = ph_half_load(p, L, src, c, L.m2im[m2], pair, hemi); }
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < NB; ++j) {
+          const int k = t0 + j * NT;
+          if (k >= h) continue;
+          double2 Xk = make_double2(0.0, 0.0), Xh = make_double2(0.0, 0.0);
+          if (hd[j]) Xk = k == 0 ? make_double2(qd[j].x, 0.0) : qd[j];
+          if (hc[j]) { Xh = make_double2(sgc * qc[j].x, -sgc * qc[j].y); if (shifted) Xh = bf_mul_pi(Xh); }
+          double2 y = rh_pack(Xk, Xh, rs_expipi(k, h));
+          if (shifted) y = cmul(y, rs_expipi(k, n));
+          work[slot(k)] = y;
+        }
+      }
+    } else {
+      for (int k = threadIdx.x; k < h; k += NT) {
+        const double2 Xk = fold_bin1(p, L, c, pair, n, shifted, k, hemi);
+        double2 Xh = fold_bin1(p, L, c, pair, n, shifted, k + h, hemi);
+        if (shifted) Xh = bf_mul_pi(Xh);
+        double2 y = rh_pack(Xk, Xh, rs_expipi(k, h));
+        if (shifted) y = cmul(y, rs_expipi(k, n));
+        work[slot(k)] = y;
+      }
+    }
+    __syncthreads();
+    sm_fft_dit<NT>(work, h, T);
+    double *mp = map_ptr(p, c) + o;
+    const double *ps = ps_ptr(p, c);
+    if (ps) ps += o;
+    if ((reinterpret_cast<uintptr_t>(mp) & 15) == 0 && (!ps || (reinterpret_cast<uintptr_t>(ps) & 15) == 0)) {
+      double2 *mp2 = reinterpret_cast<double2 *>(mp);
+      const double2 *ps2 = reinterpret_cast<const double2 *>(ps);
+      for (int q = threadIdx.x; q < h; q += NT) {
+        const double2 z = work[bf_pidx<true>(q)];
+        double2 v = make_double2(w * z.x, w * z.y);
+        if (ps) { const double2 f = ps2[q]; v.x *= f.x; v.y *= f.y; }
+        if (p.add) { const double2 old = mp2[q]; v.x += old.x; v.y += old.y; }
+        mp2[q] = v;
+      }
+    } else {
+      for (int j = threadIdx.x; j < n; j += NT) {
+        const double2 z = work[bf_pidx<true>(j >> 1)];
+        double v = w * ((j & 1) ? z.y : z.x);
+        if (ps) v *= ps[j];
+        if (p.add) mp[j] += v; else mp[j] = v;
+      }
+    }
+  } else {
+    if (o < 0) {                                       // absent ring: its phases are zero
+      for (int e = threadIdx.x; e < L.nm_total; e += NT)
+        reinterpret_cast<double2 *>(ph_at(p, L, L.mlist_src[e], c, L.mlist_im[e], pair))[hemi] = make_double2(0.0, 0.0);
+      return;
+    }
+    const double *mp = map_ptr(p, c) + o;
+    if ((reinterpret_cast<uintptr_t>(mp) & 15) == 0) {
+      const double2 *mp2 = reinterpret_cast<const double2 *>(mp);
+      for (int q = threadIdx.x; q < h; q += NT) { const double2 z = mp2[q]; work[bf_pidx<true>(q)] = make_double2(w * z.x, w * z.y); }
+    } else {
+      for (int q = threadIdx.x; q < h; q += NT) work[bf_pidx<true>(q)] = make_double2(w * mp[2 * q], w * mp[2 * q + 1]);
+    }
+    __syncthreads();
+    sm_fft_dif<NT>(work, h, T);
+    for (int e = threadIdx.x; e < L.nm_total; e += NT) {
+      const int m = L.mlist[e], b = m % n, k = b & (h - 1), k2 = (h - k) & (h - 1);
+      double2 wb = rs_expipi(2LL * b, n);
+      wb.y = -wb.y;
+      double2 X = rh_unpack(work[slot(k)], work[slot(k2)], wb);
+      const double cm = m == 0 ? 1.0 : 2.0;
+      double2 f = make_double2(cm, 0.0);
+      if (shifted) { const double2 t = rs_expipi(m, n); f = make_double2(cm * t.x, -cm * t.y); }
+      X = cmul(X, f);
+      reinterpret_cast<double2 *>(ph_at(p, L, L.mlist_src[e], c, L.mlist_im[e], pair))[hemi] = X;
+    }
+  }
+}
+
 // twiddles of one fused pass with leading half-size h: T[j] = exp(-i pi j / h), j < h/2 (blue_fft.cuh)
 __global__ void twiddle_kernel(double2 *T, int h, int count) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
@@ -812,6 +951,28 @@ static void launch_region(sharp_geom_info *g, int ncomp, size_t r, RegionKind ki
     const int n = R.len;
     int bits = 0;
     while ((1 << bits) < n) ++bits;
+    // CMDR_SHT_BELT_HALF=1: one ring per CTA through a transform of half the length (three CTAs per SM at n = 8192).
+    // Measured at nside 2048: ring stage 6.48 ms per pair against 5.99 ms with the whole-pair kernel below (the
+    // 16-byte halves of the 32-byte phase elements cost twice the sector requests, two sincospi per bin), so it is
+    // off by default; kept as a second, independently written path for the tests.
+    static const bool half = env_or("CMDR_SHT_BELT_HALF", 0) != 0;
+    if (half && n >= 2048) {
+      static bool hattr = false;
+      if (!hattr) {
+        hattr = true;
+        const int smh = (int)(sizeof(double2) * (bf_padded(4096) + bf2_tw_total(4096)));
+        CMDR_CUDA_CHECK(cudaFuncSetAttribute(ring_half_kernel<DIR, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smh));
+        CMDR_CUDA_CHECK(cudaFuncSetAttribute(ring_half_kernel<DIR, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, smh));
+      }
+      const int h = n / 2;
+      const double2 *twh = twiddle_table2(h, cs);
+      const size_t smh = sizeof(double2) * (size_t)(bf_padded(h) + bf2_tw_total(h));
+      const dim3 gh(2 * R.np, ncomp);
+      if (h <= 2048) ring_half_kernel<DIR, 128><<<gh, 128, smh, cs>>>(p, R.first, n, bits - 1, twh);
+      else ring_half_kernel<DIR, 256><<<gh, 256, smh, cs>>>(p, R.first, n, bits - 1, twh);
+      count_launch();
+      return;
+    }
     const double2 *tw = twiddle_table2(n, cs);
     const size_t smem = sizeof(double2) * (size_t)(bf_padded(n) + bf2_tw_total(n));
     if (n <= 2048) ring_pow2_kernel<DIR, 128><<<grid, 128, smem, cs>>>(p, R.first, n, bits, tw);

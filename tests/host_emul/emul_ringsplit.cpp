@@ -117,3 +117,28 @@ extern "C" void emul_ring_pow2(const double *inv, double *outv, int n, int dir) 
     for (int k = 0; k < n; ++k) out[k] = work[bf_pidx<true>((int)bf_bitrev((unsigned)k, bits))];
   }
 }
+
+// one ring of length n = 2 h through one complex transform of length h (ring_half_kernel): dir 0 takes the Hermitian
+// spectrum X (n complex) and returns the n real samples, dir 1 takes n real samples and returns X_b, b < n
+extern "C" void emul_ring_half(const double *inv, double *outv, int n, int dir) {
+  const int h = n / 2;
+  int bits = 0;
+  while ((1 << bits) < h) ++bits;
+  std::vector<double2> tw = twiddles2(h), work(bf_padded(h));
+  if (dir == 0) {
+    const double2 *X = reinterpret_cast<const double2 *>(inv);
+    for (int k = 0; k < h; ++k)
+      work[bf_pidx<true>((int)bf_bitrev((unsigned)k, bits))] = rh_pack(X[k], X[k + h], rs_expipi(k, h));
+    fft_dit(work.data(), h, tw.data());
+    for (int p = 0; p < h; ++p) { outv[2 * p] = work[bf_pidx<true>(p)].x; outv[2 * p + 1] = work[bf_pidx<true>(p)].y; }
+  } else {
+    double2 *X = reinterpret_cast<double2 *>(outv);
+    for (int p = 0; p < h; ++p) { work[bf_pidx<true>(p)].x = inv[2 * p]; work[bf_pidx<true>(p)].y = inv[2 * p + 1]; }
+    fft_dif(work.data(), h, tw.data());
+    for (int b = 0; b < n; ++b) {
+      const int k = b & (h - 1), k2 = (h - k) & (h - 1);
+      double2 wb = rs_expipi(2LL * b, n); wb.y = -wb.y;
+      X[b] = rh_unpack(work[bf_pidx<true>((int)bf_bitrev((unsigned)k, bits))], work[bf_pidx<true>((int)bf_bitrev((unsigned)k2, bits))], wb);
+    }
+  }
+}

@@ -567,7 +567,8 @@ def test_ring_fft_paths_agree(shtlib, cpu_oracle):
     """The ring-FFT stage has several execution paths per ring class (commander_b200/csrc/ringfft.cu: region_kind): batched
     cuFFT with chirp-z through HBM (the reference path of this test: every switch off), the whole-ring fused chirp-z
     kernel (plain and register-blocked), the radix-4 split chirp-z kernel (default only for the classes of work length
-    16384; CMDR_SHT_SPLIT_MIN=1024 forces it for every cap ring here) and the whole-ring power-of-two kernel for the belt.
+    16384; CMDR_SHT_SPLIT_MIN=1024 forces it for every cap ring here) and the two power-of-two kernels for the belt (one ring
+    pair per CTA, the default, and one ring per CTA through a half-length transform).
     The switches are read once per process, hence the subprocesses.  Same maps and a_lm to rounding, and the all-cuFFT
     result against the oracle."""
     import os
@@ -598,7 +599,8 @@ np.savez(sys.argv[1], map=mp, alm=m.alm, a0=a0, x0=x0)
         "fused": dict(off, CMDR_SHT_FUSED_BLUE="1", CMDR_SHT_FFT_BLOCKED="0"),
         "blocked": dict(off, CMDR_SHT_FUSED_BLUE="1", CMDR_SHT_FFT_BLOCKED="1"),
         "split": dict(off, CMDR_SHT_RING_SPLIT="1", CMDR_SHT_SPLIT_MIN="1024"),
-        "belt": dict(off, CMDR_SHT_BELT_FUSED="1"),
+        "belt": dict(off, CMDR_SHT_BELT_FUSED="1"),                                  # whole ring pair per CTA
+        "belt_half": dict(off, CMDR_SHT_BELT_FUSED="1", CMDR_SHT_BELT_HALF="1"),     # one ring per CTA, half-length transform
         "default": {},
     }
     res = {}

@@ -344,6 +344,7 @@ def emul_ring():
     L = C.CDLL(so)
     L.emul_ring_split.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int]
     L.emul_ring_pow2.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+    L.emul_ring_half.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
     return L
 
 
@@ -376,3 +377,19 @@ def test_ring_pow2_transform_on_host(emul_ring, n):
     emul_ring.emul_ring_pow2(Z.ctypes.data, x.ctypes.data, n, 1)
     ref = np.fft.fft(Z)
     assert np.abs(x - ref).max() <= 1e-12 * np.abs(ref).max()
+
+
+@pytest.mark.parametrize("n", [2048, 4096, 8192, 16384])
+def test_ring_half_transform_on_host(emul_ring, n):
+    """One ring of n real samples through one complex transform of length n / 2 (ring_half_kernel: even / odd sample
+    packing, ring_split.cuh rh_pack / rh_unpack) against numpy's real FFTs, both directions."""
+    rng = np.random.default_rng(n)
+    x = rng.standard_normal(n)
+    X = np.fft.fft(x)                       # Hermitian spectrum, e^{-} convention
+    out = np.empty(n)
+    Xs = np.ascontiguousarray(X / 1.0)
+    emul_ring.emul_ring_half(Xs.ctypes.data, out.ctypes.data, n, 0)
+    assert np.abs(out - n * x).max() <= 1e-12 * n * np.abs(x).max()
+    F = np.empty(n, dtype=np.complex128)
+    emul_ring.emul_ring_half(x.ctypes.data, F.ctypes.data, n, 1)
+    assert np.abs(F - X).max() <= 1e-12 * np.abs(X).max()
