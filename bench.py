@@ -485,7 +485,7 @@ def run_ours(args):
     dom = max(((k, v) for k, v in avg.items() if k[0] == 2), key=lambda kv: kv[1], default=((2, 1), float("nan")))
     achieved = flops2 / (dom[1] * 1e-3) / 1e12
     exe = {0: executed_fraction(nside, lmax, 0, info.ms), 2: executed_fraction(nside, lmax, 2, info.ms)}
-    # FP64-pipe instructions the kernel really issues per visited triple: 4 (spin 0) / 12 (spin 2) DFMA
+    # FP64-pipe instructions the kernel really issues per visited triple: 3 (spin 0, two l per recurrence step) / 12 (spin 2) DFMA
     achieved_exec = 2.0 * 12.0 * ntriples(nside, lmax) * local_frac * exe[2] / (dom[1] * 1e-3) / 1e12
     kern = {f"spin{k[0]}_{'analysis' if k[1] else 'synthesis'}_ms": round(v, 4) for k, v in sorted(avg.items())}
     kern["legendre_share_of_step"] = round(share, 4)
@@ -493,7 +493,7 @@ def run_ours(args):
     for k, v in sorted(avg.items()):
         fl = (8.0 if k[0] == 0 else 28.0) * ntriples(nside, lmax) * local_frac
         kern[f"spin{k[0]}_{'analysis' if k[1] else 'synthesis'}_tflops_nominal"] = round(fl / (v * 1e-3) / 1e12, 3)
-        fe = 2.0 * (4.0 if k[0] == 0 else 12.0) * ntriples(nside, lmax) * local_frac * exe[k[0]]
+        fe = 2.0 * (3.0 if k[0] == 0 else 12.0) * ntriples(nside, lmax) * local_frac * exe[k[0]]
         kern[f"spin{k[0]}_{'analysis' if k[1] else 'synthesis'}_tflops_executed"] = round(fe / (v * 1e-3) / 1e12, 3)
     traffic = None
     try:   # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from the committed ncu --set full capture
@@ -513,7 +513,7 @@ def run_ours(args):
                 "flop_convention": "achieved = nominal 28 flops per (l,m,ring pair) for spin 2 (8 for spin 0; SURVEY 8d), no work "
                                    "subtracted for the m cut-off, divided by the kernel's mean launch time (CUDA events on its stream)",
                 "achieved_executed": round(achieved_exec, 3), "frac_executed": round(achieved_exec / fp64_peak, 4),
-                "executed_convention": "DFMA instructions really issued: 12 per visited (l,m,ring pair) for spin 2 (4 for spin 0) x 2 flops; "
+                "executed_convention": "DFMA instructions really issued: 12 per visited (l,m,ring pair) for spin 2 (3 for spin 0) x 2 flops; "
                                        f"visited = {exe[2]:.3f} of the nominal triples (rings beyond the per-ring m cut-off are skipped)",
                 "peak_3operand": round(fp64_3op, 3),
                 "peak_3operand_note": "DFMA with three distinct vector-register operands (no operand-reuse-cache hit): the register file "

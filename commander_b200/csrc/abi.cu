@@ -431,6 +431,12 @@ LegAlm make_legalm(sharp_alm_info *a, int spin, bool classic) {
   A.coef = a->coef[key].tab; A.coef2 = a->coef[key].tab2; A.cofs = a->coef[key].ofs;
   A.Kstart = ensure_start_norms(a, spin);
   A.tofs = a->coef[key].tofs; A.trows = a->coef[key].trows;
+  static const bool front_on = !(getenv("CMDR_SHT_FRONT") && atoi(getenv("CMDR_SHT_FRONT")) == 0);
+  if (spin == 2 && front_on) {   // scalar front phase of the spin-2 kernels (legendre.cu, spin2_front_phase)
+    ensure_coef(a, COEF_KEY_S0X2);
+    A.front_coef = a->coef[COEF_KEY_S0X2].tab; A.front_mix = a->coef[COEF_KEY_S0X2].tab2; A.front_cofs = a->coef[COEF_KEY_S0X2].ofs;
+    A.front_K0 = ensure_start_norms(a, 0);
+  }
   return A;
 }
 

@@ -47,6 +47,9 @@ struct LegAlm {
   const double *coef2 = nullptr;   // spin 0: mix rows {u_j, v_j, h_j, v_{j-1}}
   const long long *cofs = nullptr;
   const double *Kstart = nullptr;  // start-value normalisation of this spin, indexed by m
+  // spin 2: scalar (spin-0, two l per step) tables and start norms for the front phase of the kernels (nullptr: off)
+  const double *front_coef = nullptr, *front_mix = nullptr, *front_K0 = nullptr;
+  const long long *front_cofs = nullptr;
   const long long *tofs = nullptr; // first synthesis tile row of each local m (rows padded to 8 per m)
   long long trows = 0;             // total tile rows
   // optional factor per l for each component of this spin (device, lmax+1 entries; nullptr = 1): applied to the

@@ -45,6 +45,9 @@ struct KParams {
   const double *coef2;               // spin 0: mix rows {u_j, v_j, h_j, v_{j-1}} of the two-l-per-step scheme (coef.cpp)
   const long long *cofs;
   const double *Kstart;
+  // spin 2 only: scalar tables for the front phase (spin2_front_phase); fcoef == nullptr disables it
+  const double *fcoef, *fmix, *fK0;   // rec rows {a_j, b'_j}, mix rows {u, v, h, v_prev}, spin-0 start norms
+  const long long *fcofs;
   const long long *tofs;             // synthesis: first tile row of each local m (rows padded to 8 per m)
   double *trows;                     // synthesis: tile rows (TileS0 / TileS2), written by the prep kernels
   const double *trig;
@@ -222,6 +225,83 @@ __global__ void __launch_bounds__(32, MINB) synth0_kernel(KParams p) {
 }
 
 // ------------------------------------------------------------------------------------
+// Scalar front phase of the spin-2 kernels (legendre_core.cuh, "spin 2 seeded from the scalar recurrence").  While no
+// ring of the warp is within FRONT_MARGIN_BITS of the accumulation threshold the warp advances the scalar
+// two-l-per-step recurrence (1 FP64 op per l and ring pair) instead of the two spin-2 recurrences (4); the first ring
+// to get there switches the whole warp.  Used when every valid ring of the warp starts below the threshold and has
+// sin(theta) >= FRONT_MIN_STH (nearer to the poles the smaller of the two spin-2 functions would be seeded with too
+// few digits: tests/test_host.py test_spin2_scalar_front_on_host).
+// ------------------------------------------------------------------------------------
+constexpr double FRONT_MIN_STH = 0.15;
+constexpr int FRONT_TR = 8;          // rows (of two l) between the snapshots at which the front phase can hand over
+
+// Rows of two l are advanced GR at a time; the hand-over happens at a multiple of TR rows (= one shared-memory tile of
+// the caller's l loop, so that the caller simply starts its tile loop later and nothing else in it changes -- the
+// kernels sit at their register limit, and every extra value live across the steady-state loop costs spills there):
+// the state at the last tile boundary is kept and restored when a ring triggers inside the tile (those rows are then
+// redone by the spin-2 recurrences).  nu / nup: scalar state on entry (start_spin0) and exit; returns the rows done.
+template <int R, int GR, int TR>
+__device__ __forceinline__ int spin2_front_phase(const KParams &p, int im, int m, unsigned vmask, const double (&x)[R],
+                                                 const int (&mg)[R], double (&nu)[R], double (&nup)[R], int (&k)[R]) {
+  const double2 *rec = reinterpret_cast<const double2 *>(p.fcoef + p.fcofs[im]);
+  const int J = (p.lmax - m) / 2 + 1;
+  double x2[R], snu[R], snup[R];
+  int sk[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) x2[r] = x[r] * x[r];
+  int jb = 0;
+#pragma unroll 1
+  for (;;) {                                    // one tile of TR rows per iteration
+#pragma unroll
+    for (int r = 0; r < R; ++r) { snu[r] = nu[r]; snup[r] = nup[r]; sk[r] = k[r]; }
+    bool stop = jb + TR > J - 1;                // the hand-over row and the one after it must exist
+    double2 rc[GR];
+#pragma unroll
+    for (int q = 0; q < GR; ++q) rc[q] = rec[jb + q];          // (the table is zero padded past the last row)
+#pragma unroll 1
+    for (int j = jb; !stop && j < jb + TR; j += GR) {
+      bool sw = false;
+#pragma unroll
+      for (int r = 0; r < R; ++r) sw |= ((vmask >> r) & 1) && front_must_switch(nu[r], k[r], mg[r]);
+      if (__any_sync(FULL, sw)) { stop = true; break; }
+      double2 nx[GR];
+#pragma unroll
+      for (int q = 0; q < GR; ++q) nx[q] = rec[j + GR + q];
+#pragma unroll
+      for (int q = 0; q < GR; ++q)
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          const double nxt = step0x2(rc[q].x, rc[q].y, x2[r], nu[r], nup[r]);
+          nup[r] = nu[r]; nu[r] = nxt;
+        }
+#pragma unroll
+      for (int r = 0; r < R; ++r)
+        if (k[r] < 0 && needs_rescale(nu[r])) { nu[r] *= SCALE_DOWN; nup[r] *= SCALE_DOWN; ++k[r]; }
+#pragma unroll
+      for (int q = 0; q < GR; ++q) rc[q] = nx[q];
+    }
+    if (stop) {                                 // back to the tile boundary
+#pragma unroll
+      for (int r = 0; r < R; ++r) { nu[r] = snu[r]; nup[r] = snup[r]; k[r] = sk[r]; }
+      return jb;
+    }
+    jb += TR;
+  }
+}
+// conversion of one ring at row jb (l_b = m + 2 jb): spin-2 state in kernel normalisation
+__device__ __forceinline__ void spin2_front_finish(const KParams &p, int im, int m, int jb, double x, double sth, double nu, double nup,
+                                                   double &P, double &Pp, double &M, double &Mp) {
+  const double4 *mix = reinterpret_cast<const double4 *>(p.fmix + 2 * p.fcofs[im]);
+  const double4 mb = mix[jb];
+  const double mixb[4] = {mb.x, mb.y, mb.z, mb.w};
+  const double hprev = jb > 0 ? mix[jb - 1].z : 0.0;
+  const double *c0 = p.coef + p.cofs[im] + 4 * (size_t)(2 * jb);   // l0 = m (m >= 2): row l_b - l0 = 2 jb; the table is zero padded
+  const double4 r0 = reinterpret_cast<const double4 *>(c0)[0], r1 = reinterpret_cast<const double4 *>(c0)[1];
+  const double cc0[4] = {r0.x, r0.y, r0.z, r0.w}, cc1[4] = {r1.x, r1.y, r1.z, r1.w};
+  spin2_front_convert(m + 2 * jb, m, p.lmax, x, sth, nu, nup, mixb, hprev, cc0, cc1, P, Pp, M, Mp);
+}
+
+// ------------------------------------------------------------------------------------
 // spin-2 synthesis.  cp = -(E+iB) g, cm = -(E-iB) g;  P,M = mu of (+2)lambda, (-2)lambda.
 //   a1 = sum cp P, a2 = sum cm M (north);  a3 = sum sg cp M, a4 = sum sg cm P (south)
 //   Q = (a1+a2)/2, U = -i (a1-a2)/2
@@ -310,22 +390,52 @@ __global__ void __launch_bounds__(32, MINB) synth2_kernel(KParams p) {
   int k[R], slot[R];
   bool any = false;
   const double K = p.Kstart[m];
+  // scalar front phase (spin 2, m >= 4): eligible when every valid ring of the warp starts below the threshold and
+  // is not too close to a pole; P / Pp hold the scalar state until the conversion
+  unsigned vmask = 0;
+  int mg[R];
+  bool front = p.fcoef != nullptr && m >= 4 && l0 <= p.lmax, fok = true;
 #pragma unroll
   for (int r = 0; r < R; ++r) {
     slot[r] = chunk0 + lane * R + r;
     bool valid = slot[r] < p.nslots && m <= p.mlim[min(slot[r], p.nslots - 1)] && l0 <= p.lmax;
 #pragma unroll
     for (int q = 0; q < 8; ++q) a[r][q] = 0.0;
-    P[r] = M[r] = Pp[r] = Mp[r] = 0.0; k[r] = 0; x[r] = 0.0;
+    P[r] = M[r] = Pp[r] = Mp[r] = 0.0; k[r] = 0; x[r] = 0.0; mg[r] = 0;
     if (valid) {
       const double4 tg = reinterpret_cast<const double4 *>(p.trig)[slot[r]];
       RingTrig g{tg.x, tg.y, tg.z, tg.w};
       x[r] = g.cth;
-      if (p.spin == 2) start_spin2(m, K, g, P[r], M[r], k[r]); else start_spin_s(m, p.spin, K, g, P[r], M[r], k[r]);
+      vmask |= 1u << r;
+      mg[r] = front_margin_bits(g.sth);
+      if (front) { start_spin0(m, p.fK0[m], g, P[r], k[r]); fok &= k[r] < 0 && g.sth >= FRONT_MIN_STH; }
       any = true;
     }
   }
+  front = front && __all_sync(FULL, fok);
+  int lskip = 0;                        // l (counted from l0) the front phase has covered: whole tiles
   if (__any_sync(FULL, any)) {
+    if (front) {
+      const int jb = spin2_front_phase<R, 4, FRONT_TR>(p, im, m, vmask, x, mg, P, Pp, k);
+      lskip = 2 * jb;
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const double nu = P[r], nup = Pp[r];
+        P[r] = Pp[r] = 0.0;
+        if ((vmask >> r) & 1) {
+          const double sth = reinterpret_cast<const double4 *>(p.trig)[slot[r]].y;
+          spin2_front_finish(p, im, m, jb, x[r], sth, nu, nup, P[r], Pp[r], M[r], Mp[r]);
+        } else k[r] = 0;
+      }
+    } else {
+#pragma unroll
+      for (int r = 0; r < R; ++r)
+        if ((vmask >> r) & 1) {
+          const double4 tg = reinterpret_cast<const double4 *>(p.trig)[slot[r]];
+          RingTrig g{tg.x, tg.y, tg.z, tg.w};
+          if (p.spin == 2) start_spin2(m, K, g, P[r], M[r], k[r]); else start_spin_s(m, p.spin, K, g, P[r], M[r], k[r]);
+        }
+    }
     const TileS2 *rows = reinterpret_cast<const TileS2 *>(p.trows) + p.tofs[im];
     auto issue_tile = [&](int b, int lt) {     // rows past this m's padded range are never used
       const char *src = reinterpret_cast<const char *>(rows + (lt - l0));
@@ -334,11 +444,11 @@ __global__ void __launch_bounds__(32, MINB) synth2_kernel(KParams p) {
       for (int q = 0; q < (int)(TL * sizeof(TileS2)) / 512; ++q) cp_async16(dst + (q * 32 + lane) * 16, src + (q * 32 + lane) * 16);
       cp_async_commit();
     };
-    issue_tile(0, l0);
+    issue_tile(0, l0 + lskip);
     cp_async_wait_all();
     __syncwarp();
     int buf = 0;
-    for (int lt = l0; lt <= p.lmax; lt += TL, buf ^= 1) {
+    for (int lt = l0 + lskip; lt <= p.lmax; lt += TL, buf ^= 1) {
       if (lt + TL <= p.lmax) issue_tile(buf ^ 1, lt + TL);
       const int ngroups = min(TL, p.lmax - lt + 8) / 8;
 #pragma unroll 1
@@ -763,20 +873,61 @@ __global__ void __launch_bounds__(32, MINB) anal2_kernel(KParams p) {
   const double sg0 = ((l0 + m) & 1) ? -1.0 : 1.0;
   const bool swapRI = lane & 16, swapPM = lane & 8;
   const int csign = swapPM ? 0x80000000 : 0;   // sign-bit mask applied to C' (an integer op, not a DMUL)
+  // scalar front phase (see synth2_kernel): Pa / Pap hold the scalar state until the conversion
+  unsigned vmask = 0;
+  int mg[R];
+  bool front = p.fcoef != nullptr && m >= 4, fok = true;
 #pragma unroll
   for (int r = 0; r < R; ++r) {
     int slot = chunk0 + lane * R + r;
     bool valid = slot < p.nslots && m <= p.mlim[min(slot, p.nslots - 1)];
-    Pa[r] = Pb[r] = Pap[r] = Pbp[r] = x[r] = 0.0; k[r] = 0;
+    Pa[r] = Pb[r] = Pap[r] = Pbp[r] = x[r] = 0.0; k[r] = 0; mg[r] = 0;
 #pragma unroll
     for (int q = 0; q < 8; ++q) w[r][q] = 0.0;
     if (valid) {
       const double4 tg = reinterpret_cast<const double4 *>(p.trig)[slot];
       RingTrig g{tg.x, tg.y, tg.z, tg.w};
       x[r] = g.cth;
-      double P0, M0;
-      if (p.spin == 2) start_spin2(m, K, g, P0, M0, k[r]); else start_spin_s(m, p.spin, K, g, P0, M0, k[r]);
-      Pa[r] = swapPM ? M0 : P0; Pb[r] = swapPM ? P0 : M0;
+      vmask |= 1u << r;
+      mg[r] = front_margin_bits(g.sth);
+      if (front) { start_spin0(m, p.fK0[m], g, Pa[r], k[r]); fok &= k[r] < 0 && g.sth >= FRONT_MIN_STH; }
+      any = true;
+    }
+  }
+  if (!__any_sync(FULL, any)) return;
+  front = front && __all_sync(FULL, fok);
+  int lskip = 0;                        // l (counted from l0) the front phase has covered: whole tiles, which
+  if (front) {                          // contribute nothing to the a_lm
+    const int jb = spin2_front_phase<R, 2, FRONT_TR>(p, im, m, vmask, x, mg, Pa, Pap, k);
+    lskip = 2 * jb;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const double nu = Pa[r], nup = Pap[r];
+      Pa[r] = Pap[r] = 0.0;
+      if ((vmask >> r) & 1) {
+        const double sth = reinterpret_cast<const double4 *>(p.trig)[chunk0 + lane * R + r].y;
+        double P0, Pp0, M0, Mp0;
+        spin2_front_finish(p, im, m, jb, x[r], sth, nu, nup, P0, Pp0, M0, Mp0);
+        Pa[r] = swapPM ? M0 : P0; Pb[r] = swapPM ? P0 : M0;
+        Pap[r] = swapPM ? Mp0 : Pp0; Pbp[r] = swapPM ? Pp0 : Mp0;
+      } else k[r] = 0;
+    }
+  } else {
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+      if ((vmask >> r) & 1) {
+        const double4 tg = reinterpret_cast<const double4 *>(p.trig)[chunk0 + lane * R + r];
+        RingTrig g{tg.x, tg.y, tg.z, tg.w};
+        double P0, M0;
+        if (p.spin == 2) start_spin2(m, K, g, P0, M0, k[r]); else start_spin_s(m, p.spin, K, g, P0, M0, k[r]);
+        Pa[r] = swapPM ? M0 : P0; Pb[r] = swapPM ? P0 : M0;
+      }
+  }
+  // ring data (loaded after the front phase, which needs the registers)
+#pragma unroll
+  for (int r = 0; r < R; ++r)
+    if ((vmask >> r) & 1) {
+      const int slot = chunk0 + lane * R + r;
       double4 q = *ph_in(p, 0, im, slot), u = *ph_in(p, 1, im, slot);
       double z[8];
       z[0] = q.x - u.y; z[1] = q.y + u.x;            // zpN = qQ + i qU
@@ -789,10 +940,7 @@ __global__ void __launch_bounds__(32, MINB) anal2_kernel(KParams p) {
         double a0 = swapPM ? z[i ^ 2] : z[i], a1 = swapPM ? z[(i ^ 2) + 1] : z[i + 1];
         w[r][i] = swapRI ? a1 : a0; w[r][i + 1] = swapRI ? a0 : a1;
       }
-      any = true;
     }
-  }
-  if (!__any_sync(FULL, any)) return;
   const double *coef = p.coef + p.cofs[im];
   const long long mvs = p.mvstart[im];
   // real-packed: orthonormal real basis (sqrt2 both ways).  complex a_lm: the phases carry the
@@ -806,14 +954,14 @@ __global__ void __launch_bounds__(32, MINB) anal2_kernel(KParams p) {
     for (int q = 0; q < (int)(TL * sizeof(TileA2)) / 512; ++q) cp_async16(dst + (q * 32 + lane) * 16, src + (q * 32 + lane) * 16);
     cp_async_commit();
   };
-  issue_tile(0, l0);
+  issue_tile(0, l0 + lskip);
   cp_async_wait_all();
   __syncwarp();
   int buf = 0;
   bool steady = false;
   unsigned sidx = (unsigned)__cvta_generic_to_shared(red + store_index_s2(lane));
   asm volatile("mov.u32 %0, %0;" : "+r"(sidx));   // opaque: kept in a register instead of being recomputed per group
-  for (int lt = l0; lt <= p.lmax; lt += TL, buf ^= 1) {
+  for (int lt = l0 + lskip; lt <= p.lmax; lt += TL, buf ^= 1) {
     if (lt + TL <= p.lmax) issue_tile(buf ^ 1, lt + TL);
     const int ngroups = min(TL, p.lmax - lt + 4) / 4;
     const TileA2 *T = tile[buf];
@@ -898,6 +1046,7 @@ static KParams make_params(const LegGeom &g, const LegAlm &a, double *alm0, doub
   p.slot_begin = g.slot_begin; p.nslots = g.slot_end >= 0 ? g.slot_end : g.nslots; p.NPL = g.NPL; p.NML = g.NML; p.ncomp_tot = g.ncomp_tot; p.comp0 = g.comp0;
   p.ring_major = phase_ring_major() ? 1 : 0;
   p.mval = a.mval; p.mvstart = a.mvstart; p.coef = a.coef; p.coef2 = a.coef2; p.cofs = a.cofs; p.Kstart = a.Kstart;
+  p.fcoef = a.front_coef; p.fmix = a.front_mix; p.fcofs = a.front_cofs; p.fK0 = a.front_K0;
   p.tofs = nullptr; p.trows = nullptr;
   p.im0 = a.im_begin;
   p.trig = g.trig; p.mlim = g.mlim; p.wslot = g.wslot;

@@ -111,6 +111,57 @@ CMDR_HD void start_spin2(int m, double K2m, const RingTrig &g, double &P, double
   }
 }
 
+// ---- spin 2 seeded from the scalar recurrence ---------------------------------------------------------
+// While every ring of a warp is still far below the accumulation threshold, the spin-2 kernels run the SCALAR
+// two-l-per-step recurrence (1 FP64 op per l and ring pair instead of 4 for the two spin-2 recurrences) and convert at a
+// group boundary with the classical relations between spin-2 and scalar harmonics (W_lm, X_lm of the polarisation
+// literature; checked against the definitional Wigner-d sums in tests/test_host.py):
+//   (+2)lam_l = W - X,  (-2)lam_l = W + X,   N = 1 / sqrt((l-1) l (l+1) (l+2)),  c = sqrt((2l+1)/(2l-1) (l-m)/(l+m))
+//   W = 2N [ (-(l - m^2)/sin^2 - l(l-1)/2) lam_l + (l+m) (cos/sin^2) c lam_{l-1} ]
+//   X = 2N (m/sin^2) [ (l-1) cos lam_l - (l+m) c lam_{l-1} ]
+// Linear in the lambdas, so a common scale factor 2^(512 k) passes through.  The smaller of the two functions loses
+// log2(large/small) bits (<= 11 for the rings and m this path is used for, i.e. relative errors <= 1e-11 on a function
+// that is itself that much smaller than its partner).
+CMDR_HD void spin2_from_scalar(int l, int m, double x, double sth, double lam, double lam1, double &P, double &M) {
+  const double dl = l, dm = m;
+  const double N = 1.0 / sqrt((dl - 1.0) * dl * (dl + 1.0) * (dl + 2.0));
+  const double c = sqrt((2.0 * dl + 1.0) / (2.0 * dl - 1.0) * (dl - dm) / (dl + dm));
+  const double f = 2.0 * N / (sth * sth);
+  const double a = -(dl - dm * dm) - 0.5 * dl * (dl - 1.0) * sth * sth;
+  const double b = dm * (dl - 1.0) * x, e = (dl + dm) * c;
+  P = f * ((a - b) * lam + e * (x + dm) * lam1);
+  M = f * ((a + b) * lam + e * (x - dm) * lam1);
+}
+// switch from the scalar to the spin-2 recurrences once a ring's scalar value (stored as true * 2^(-512 k)) is within
+// `margin` bits of the accumulation threshold.  The spin-2 functions are larger than the scalar one by at most
+// ~2 / sin^2(theta) (the m^2 / sin^2 term of W with m <= l), and a few bits of growth until the next check are allowed for.
+CMDR_HD int front_margin_bits(double sth) {
+  const int e2 = ((hi_word(sth * sth) >> 20) & 0x7ff) - 1023;   // floor(log2 sin^2): <= 0
+  return 8 - e2;
+}
+CMDR_HD bool front_must_switch(double cur, int k, int margin) {
+  return k >= 0 || (k == -1 && ((hi_word(cur) >> 20) & 0x7ff) >= RESCALE_EXP - margin);
+}
+// State of the spin-2 recurrences at l_b = m + 2 jb (m >= 2) from the scalar state (nu_jb, nu_{jb-1}):
+//   mixb = mix row jb {u, v, h, v_{jb-1}}, hprev = h_{jb-1};  c0 / c1 = spin-2 coefficient rows {A', C', g, .} of l_b, l_b + 1.
+// Returns mu(l_b) in P / M and mu(l_b - 1) in Pp / Mp (kernel normalisation lam = g mu), same scale factor as nu.
+CMDR_HD void spin2_front_convert(int lb, int m, int lmax, double x, double sth, double nu, double nup, const double *mixb, double hprev,
+                                 const double *c0, const double *c1, double &P, double &Pp, double &M, double &Mp) {
+  const double lam_m1 = x * hprev * nup;                       // lam(l_b - 1)
+  const double lam_0 = mixb[0] * nu + mixb[3] * nup;           // lam(l_b)
+  const double lam_p1 = x * mixb[2] * nu;                      // lam(l_b + 1)
+  double P0, M0, P1 = 0.0, M1 = 0.0;
+  spin2_from_scalar(lb, m, x, sth, lam_0, lam_m1, P0, M0);
+  P = P0 / c0[2]; M = M0 / c0[2];
+  Pp = 0.0; Mp = 0.0;
+  if (lb + 1 <= lmax) {
+    spin2_from_scalar(lb + 1, m, x, sth, lam_p1, lam_0, P1, M1);
+    // mu_{l+1} = (A' x +- C') mu_l - mu_{l-1}  =>  mu_{l-1} = (A' x +- C') mu_l - mu_{l+1}
+    Pp = fma(fma(c0[0], x, c0[1]), P, -P1 / c1[2]);
+    Mp = fma(fma(c0[0], x, -c0[1]), M, -M1 / c1[2]);
+  }
+}
+
 // ---- arbitrary spin s >= 1 (conviqt: commander3/src/comm_conviqt_mod.f90:234-239) ---------------
 CMDR_HD double ipow(double b, int n) {      // b^n, n >= 0, by repeated squaring
   double r = 1.0;

@@ -93,11 +93,18 @@ def emul():
         subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-o", so, src, coef, "-lpthread"])
     L = C.CDLL(so)
     L.emul_lambda.argtypes = [C.c_int] * 5 + [C.c_void_p, C.c_void_p]
+    L.emul_lambda_front.argtypes = [C.c_int] * 5 + [C.c_void_p, C.c_void_p]
+
+    def front(lmax, m, nside, north, force_row):
+        P = np.zeros(lmax + 1); M = np.zeros(lmax + 1)
+        lb = L.emul_lambda_front(lmax, m, nside, north, force_row, P.ctypes.data, M.ctypes.data)
+        return lb, P, M
 
     def run(spin, lmax, m, nside, north):
         P = np.zeros(lmax + 1); M = np.zeros(lmax + 1)
         L.emul_lambda(spin, lmax, m, nside, north, P.ctypes.data, M.ctypes.data)
         return P, M
+    run.front = front
     return run
 
 
@@ -143,6 +150,39 @@ def test_device_recurrence_math_spin2(emul):
                 rp, rm = float(D.slam(l, m, 2, cth, sth)), float(D.slam(l, m, -2, cth, sth))
                 sc = max(abs(rp), abs(rm))
                 assert abs(P[l] - rp) <= 1e-11 * sc + 1e-19 and abs(M[l] - rm) <= 1e-11 * sc + 1e-19
+
+
+def test_spin2_scalar_front_on_host(emul):
+    """The scalar front phase of the spin-2 kernels (legendre_core.cuh spin2_from_scalar / spin2_front_convert,
+    legendre.cu spin2_front_phase): scalar two-l-per-step recurrence, conversion to the two spin-2 recurrences at a tile
+    boundary -- natural hand-over and forced early ones (another ring of the warp got there first) -- against the plain
+    spin-2 recurrence for rings with sin(theta) >= 0.15 (the kernels' FRONT_MIN_STH), and against the definitional
+    Wigner-d values."""
+    import mpmath as mp
+    mp.mp.dps = 60
+    nside, lmax = 512, 1000
+    used = 0
+    for m in (4, 7, 35, 120, 300, 600, 900):
+        for north in (100, 128, 200, 400, 512, 700, 1000):
+            cth, sth, *_ = D.healpix_ring(nside, north)
+            if sth < 0.15:
+                continue
+            P, M = emul(2, lmax, m, nside, north)
+            for force in (-1, 0, 8, 64, 200):
+                lb, Pf, Mf = emul.front(lmax, m, nside, north, force)
+                if lb < 0:          # ring starts above the threshold: the kernels take the plain path
+                    continue
+                both = (P != 0) & (Pf != 0)
+                if not both.any():
+                    continue
+                used += 1
+                sc = max(np.abs(P[both]).max(), np.abs(M[both]).max())
+                assert np.abs(P - Pf)[both].max() <= 2e-11 * sc and np.abs(M - Mf)[both].max() <= 2e-11 * sc, (m, north, force)
+                if force == -1 and north in (128, 512):
+                    l = int(np.nonzero(both)[0][0]) + 3
+                    rp, rm = float(D.slam(l, m, 2, cth, sth)), float(D.slam(l, m, -2, cth, sth))
+                    assert abs(Pf[l] - rp) <= 1e-10 * max(abs(rp), abs(rm)) and abs(Mf[l] - rm) <= 1e-10 * max(abs(rp), abs(rm))
+    assert used > 40
 
 
 @pytest.mark.parametrize("spin", [1, 3, 5])
