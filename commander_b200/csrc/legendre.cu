@@ -15,6 +15,8 @@
 // warp-uniform broadcasts from a shared-memory tile of TL consecutive l that the warp stages
 // itself with cp.async.  FP64-pipe cost per (l, m, ring pair):
 //   spin 0: 1 (recurrence) + 2 (accumulate) -- two l per step, recurrence in x^2 (coef.cpp) ; spin s: 4 + 8.
+// Spin 2 runs that scalar recurrence too while every ring of a warp is still far below the accumulation threshold
+// (1 instead of 4 per l and ring pair) and converts to the two spin-2 recurrences at the hand-over (spin2_front_phase).
 // Analysis reduces over the rings of the warp with a select-free, software-pipelined register
 // butterfly and adds the sums to the a_lm with coalesced atomics.
 #include <cstdio>
