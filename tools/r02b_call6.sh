@@ -1,5 +1,6 @@
 #!/bin/bash
-# round-2 (second session) check 6: rows per shared-memory tile of the analysis kernels
+# round-2 (second session) check 6: rows per shared-memory tile of the analysis kernels (the CMDR_SHT_TL_A* switches of that experiment were
+# removed again after the measurement: 192 rows -0.3 %, 256 rows slower; profiles/r02_legendre_session2.txt)
 cd "$GRAFT_REPO_ROOT" 2>/dev/null || cd /root/repo
 mkdir -p gpurun_out
 ( bash tools/quick.sh
