@@ -9,7 +9,7 @@
 // (commander3/src/comm_conviqt_mod.f90:234-239).
 //
 // Work decomposition: grid = (ring-pair chunks, local m), ONE WARP PER CTA, no block-level
-// synchronisation.  A thread owns R adjacent ring pairs (north ring + its southern mirror
+// synchronisation.  A thread owns R adjacent ring pairs (spin-2 analysis: 32 apart; north ring + its southern mirror
 // share one recurrence through the l+m parity), runs the recurrence in registers over l, and
 // reads per-l data (recurrence coefficients and, for synthesis, the pre-scaled a_lm) as
 // warp-uniform broadcasts from a shared-memory tile of TL consecutive l that the warp stages
@@ -84,6 +84,20 @@ __device__ __forceinline__ double4 *ph_out(const KParams &p, int comp, int im, i
   return p.peer[owner] + ph_index(blk, p.ncomp_tot, p.comp0 + comp, p.NML, p.NPL, im, local, p.ring_major);
 }
 
+// Spin-2 analysis only: ring pair r of lane `lane` is slot chunk0 + 32 r + lane, so that the 32 ring pairs with the same r
+// (a "slice") are neighbours in colatitude and cross the accumulation threshold together; in the transient phase (some
+// rings on, some not) the accumulate FMAs of a slice none of whose rings is on yet are skipped with a warp-uniform test:
+// bit r of the mask (anal2 28.31 -> 27.88 ms).  The other three kernels keep R adjacent ring pairs per thread and the
+// default mask: the same change cost them registers (synth2 162 -> 226) and made them slower.
+template <int R>
+__device__ __forceinline__ unsigned slices_on(const int (&k)[R]) {
+  unsigned m = 0;
+#pragma unroll
+  for (int r = 0; r < R; ++r)
+    if (__any_sync(FULL, k[r] == 0)) m |= 1u << r;
+  return m;
+}
+
 // 16-byte asynchronous global -> shared copies (LDGSTS): every kernel stages its per-l
 // tiles as raw rows of a global table (coefficient tables for analysis, the pre-scaled a_lm rows
 // written by the prep kernels for synthesis), so staging needs no registers and no barrier.
@@ -103,14 +117,14 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 template <int MODE, int R>
 __device__ __forceinline__ void synth0_group(const TileS0 *t, const double (&x2)[R], double (&cur)[R],
                                              double (&prev)[R], double (&per)[R], double (&pei)[R],
-                                             double (&por)[R], double (&poi)[R], int (&k)[R]) {
+                                             double (&por)[R], double (&poi)[R], int (&k)[R], unsigned ron = ~0u) {
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     const double A = t[j].A, B = t[j].B;
     const double c1r = t[j].c1r, c1i = t[j].c1i, c2r = t[j].c2r, c2i = t[j].c2i;
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-      if (MODE >= 1) {
+      if (MODE == 2 || (MODE == 1 && ((ron >> r) & 1))) {
         double v = (MODE == 2 || k[r] == 0) ? cur[r] : 0.0;
         per[r] = fma(v, c1r, per[r]); pei[r] = fma(v, c1i, pei[r]);
         por[r] = fma(v, c2r, por[r]); poi[r] = fma(v, c2i, poi[r]);
@@ -311,14 +325,14 @@ __device__ __forceinline__ void spin2_front_finish(const KParams &p, int im, int
 template <int MODE, int R>
 __device__ __forceinline__ void synth2_group(const TileS2 *t, const double (&x)[R], double (&P)[R],
                                              double (&Pp)[R], double (&M)[R], double (&Mp)[R],
-                                             double (&a)[R][8], int (&k)[R]) {
+                                             double (&a)[R][8], int (&k)[R], unsigned ron = ~0u) {
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const double A = t[j].A, C = t[j].C;
     const double cpr = t[j].cpr, cpi = t[j].cpi, cmr = t[j].cmr, cmi = t[j].cmi;
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-      if (MODE >= 1) {
+      if (MODE == 2 || (MODE == 1 && ((ron >> r) & 1))) {
         bool on = (MODE == 2 || k[r] == 0);
         double vp = on ? P[r] : 0.0, vm = on ? M[r] : 0.0;
         a[r][0] = fma(vp, cpr, a[r][0]); a[r][1] = fma(vp, cpi, a[r][1]);
@@ -579,14 +593,14 @@ __device__ __forceinline__ void pipe_tail(const ReducePipe &in, ReducePipe &out,
 template <int MODE, int R>
 __device__ __forceinline__ void anal0_fma(const TileA0 *tA, const double (&x2)[R], double (&cur)[R],
                                           double (&prev)[R], const double (&w)[R][4], int (&k)[R],
-                                          double (&acc)[16]) {
+                                          double (&acc)[16], unsigned ron = ~0u) {
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     const double A = tA[j].A, B = tA[j].B;
     double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-      if (MODE >= 1) {
+      if (MODE == 2 || (MODE == 1 && ((ron >> r) & 1))) {
         double v = (MODE == 2 || k[r] == 0) ? cur[r] : 0.0;
         s0 = fma(v, w[r][0], s0); s1 = fma(v, w[r][1], s1);
         s2 = fma(v, w[r][2], s2); s3 = fma(v, w[r][3], s3);
@@ -779,14 +793,14 @@ __device__ __forceinline__ double flip_sign(double v, int mask) {
 template <int MODE, int R>
 __device__ __forceinline__ void anal2_fma(const TileA2 *t, const int csign, const double (&x)[R], double (&Pa)[R],
                                           double (&Pap)[R], double (&Pb)[R], double (&Pbp)[R],
-                                          const double (&w)[R][8], int (&k)[R], double (&acc)[16]) {
+                                          const double (&w)[R][8], int (&k)[R], double (&acc)[16], unsigned ron = ~0u) {
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     const double A = t[j].A, C = flip_sign(t[j].C, csign);
     double s1r = 0.0, s1i = 0.0, s2r = 0.0, s2i = 0.0;
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-      if (MODE >= 1) {
+      if (MODE == 2 || (MODE == 1 && ((ron >> r) & 1))) {
         bool on = (MODE == 2 || k[r] == 0);
         double va = on ? Pa[r] : 0.0, vb = on ? Pb[r] : 0.0;
         // w: 0,1 zpN ; 2,3 zmN ; 4,5 zpS ; 6,7 zmS  (before the per-lane permutation)
@@ -881,7 +895,7 @@ __global__ void __launch_bounds__(32, MINB) anal2_kernel(KParams p) {
   bool front = p.fcoef != nullptr && m >= 4, fok = true;
 #pragma unroll
   for (int r = 0; r < R; ++r) {
-    int slot = chunk0 + lane * R + r;
+    int slot = chunk0 + r * 32 + lane;
     bool valid = slot < p.nslots && m <= p.mlim[min(slot, p.nslots - 1)];
     Pa[r] = Pb[r] = Pap[r] = Pbp[r] = x[r] = 0.0; k[r] = 0; mg[r] = 0;
 #pragma unroll
@@ -907,7 +921,7 @@ __global__ void __launch_bounds__(32, MINB) anal2_kernel(KParams p) {
       const double nu = Pa[r], nup = Pap[r];
       Pa[r] = Pap[r] = 0.0;
       if ((vmask >> r) & 1) {
-        const double sth = reinterpret_cast<const double4 *>(p.trig)[chunk0 + lane * R + r].y;
+        const double sth = reinterpret_cast<const double4 *>(p.trig)[chunk0 + r * 32 + lane].y;
         double P0, Pp0, M0, Mp0;
         spin2_front_finish(p, im, m, jb, x[r], sth, nu, nup, P0, Pp0, M0, Mp0);
         Pa[r] = swapPM ? M0 : P0; Pb[r] = swapPM ? P0 : M0;
@@ -918,7 +932,7 @@ __global__ void __launch_bounds__(32, MINB) anal2_kernel(KParams p) {
 #pragma unroll
     for (int r = 0; r < R; ++r)
       if ((vmask >> r) & 1) {
-        const double4 tg = reinterpret_cast<const double4 *>(p.trig)[chunk0 + lane * R + r];
+        const double4 tg = reinterpret_cast<const double4 *>(p.trig)[chunk0 + r * 32 + lane];
         RingTrig g{tg.x, tg.y, tg.z, tg.w};
         double P0, M0;
         if (p.spin == 2) start_spin2(m, K, g, P0, M0, k[r]); else start_spin_s(m, p.spin, K, g, P0, M0, k[r]);
@@ -929,7 +943,7 @@ __global__ void __launch_bounds__(32, MINB) anal2_kernel(KParams p) {
 #pragma unroll
   for (int r = 0; r < R; ++r)
     if ((vmask >> r) & 1) {
-      const int slot = chunk0 + lane * R + r;
+      const int slot = chunk0 + r * 32 + lane;
       double4 q = *ph_in(p, 0, im, slot), u = *ph_in(p, 1, im, slot);
       double z[8];
       z[0] = q.x - u.y; z[1] = q.y + u.x;            // zpN = qQ + i qU
@@ -981,7 +995,7 @@ __global__ void __launch_bounds__(32, MINB) anal2_kernel(KParams p) {
           anal2_fma<0, R>(T + 4 * g, csign, x, Pa, Pap, Pb, Pbp, w, k, acc);
           if (!(lane & 1)) dst[16 * g + (lane >> 1)] = 0.0;
         } else {
-          anal2_fma<1, R>(T + 4 * g, csign, x, Pa, Pap, Pb, Pbp, w, k, acc);
+          anal2_fma<1, R>(T + 4 * g, csign, x, Pa, Pap, Pb, Pbp, w, k, acc, slices_on(k));
           reduce_store_s2(acc, dst + 16 * g, lane);
         }
       }
