@@ -185,6 +185,45 @@ def test_spin2_scalar_front_on_host(emul):
     assert used > 40
 
 
+def test_recurrence_variants_random_sweep(emul):
+    """Random (nside, lmax, m, ring) up to nside 2048 / lmax 4000: the two-l-per-step spin-0 form against the one-step
+    form (which the tests above pin to the reference's recurrence), and the scalar front phase of the spin-2 kernels
+    against the plain spin-2 recurrence, natural and forced hand-over points.  Absolute floor 3e-15: a ring joins the
+    accumulation at a group boundary (8 l), and near l = m the functions grow by up to 2^20 per group, so both forms
+    drop values of that size around the joining point -- each in its own way."""
+    rng = np.random.default_rng(20261018)
+    n0 = n2 = 0
+    for _ in range(500):
+        nside = int(rng.choice([16, 64, 256, 1024, 2048]))
+        lmax = min(4000, int(rng.integers(4, 3 * nside + 1)))
+        m = int(rng.integers(0, lmax + 1))
+        north = int(rng.integers(1, 2 * nside + 1)) if rng.random() < 0.8 else int(2 * nside - rng.integers(0, 4))
+        P, _ = emul(0, lmax, m, nside, north)
+        Q, _ = emul(-1, lmax, m, nside, north)
+        assert np.isfinite(Q).all()
+        both = (P != 0) & (Q != 0)
+        if both.any():
+            n0 += 1
+            assert np.abs(P - Q)[both].max() <= 2e-11 * np.abs(P[both]).max() + 3e-15, (nside, lmax, m, north)
+        cth, sth, *_ = D.healpix_ring(nside, north)
+        if m < 4 or sth < 0.15:
+            continue
+        P, M = emul(2, lmax, m, nside, north)
+        force = int(rng.choice([-1, -1, 0, 2, 8, int(rng.integers(0, (lmax - m) // 2 + 1))]))
+        lb, Pf, Mf = emul.front(lmax, m, nside, north, force)
+        if lb < 0:
+            continue
+        assert np.isfinite(Pf).all() and np.isfinite(Mf).all()
+        both = (P != 0) & (Pf != 0)
+        if both.any():
+            n2 += 1
+            sc = max(np.abs(P[both]).max(), np.abs(M[both]).max())
+            assert max(np.abs(P - Pf)[both].max(), np.abs(M - Mf)[both].max()) <= 2e-11 * sc + 3e-15, (nside, lmax, m, north, force)
+            if force == -1:     # the seeded path must not join later than the plain one by more than a group
+                assert np.nonzero(Pf)[0][0] <= np.nonzero(P)[0][0] + 8
+    assert n0 > 300 and n2 > 40
+
+
 @pytest.mark.parametrize("spin", [1, 3, 5])
 def test_device_recurrence_math_arbitrary_spin(emul, spin):
     """start_spin_s + the spin-s coefficient tables (conviqt, commander3/src/comm_conviqt_mod.f90:234-239)
