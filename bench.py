@@ -73,8 +73,14 @@ def workload(args):
             "ring_fft": "one shared-memory kernel per ring class, no cuFFT at this size: whole-ring chirp-z (work length <= 8192), "
                         "radix-4 split chirp-z (4 x work length 4096) for the cap rings longer than 4096, whole-ring FFT for the belt"
                         + "".join(f"; {k}={os.environ[k]}" for k in ("CMDR_SHT_FUSED_BLUE", "CMDR_SHT_RING_SPLIT", "CMDR_SHT_BELT_FUSED",
-                                                                    "CMDR_SHT_FFT_BLOCKED", "CMDR_SHT_SPLIT_MIN", "CMDR_SHT_PH_LAYOUT")
-                                  if k in os.environ)}
+                                                                    "CMDR_SHT_FFT_BLOCKED", "CMDR_SHT_SPLIT_MIN", "CMDR_SHT_PH_LAYOUT",
+                                                                    "CMDR_SHT_BELT_HALF")
+                                  if k in os.environ),
+            "legendre": "FP64 recurrence kernels, one warp per CTA: spin 0 two l per recurrence step (3 DFMA per (l,m,ring pair)), spin 2 "
+                        "two coupled recurrences (12 DFMA) with a scalar front phase while all rings of a warp are below the threshold"
+                        + "".join(f"; {k}={os.environ[k]}" for k in ("CMDR_SHT_FRONT", "CMDR_SHT_R_S0", "CMDR_SHT_R_S2", "CMDR_SHT_R_A0",
+                                                                    "CMDR_SHT_R_A2", "CMDR_SHT_MINB_S0", "CMDR_SHT_MINB_S2",
+                                                                    "CMDR_SHT_MINB_A0", "CMDR_SHT_MINB_A2") if k in os.environ)}
 
 
 # ------------------------------------------------------------------ CPU baseline / reference arm
@@ -514,7 +520,8 @@ def run_ours(args):
                                    "subtracted for the m cut-off, divided by the kernel's mean launch time (CUDA events on its stream)",
                 "achieved_executed": round(achieved_exec, 3), "frac_executed": round(achieved_exec / fp64_peak, 4),
                 "executed_convention": "DFMA instructions really issued: 12 per visited (l,m,ring pair) for spin 2 (3 for spin 0) x 2 flops; "
-                                       f"visited = {exe[2]:.3f} of the nominal triples (rings beyond the per-ring m cut-off are skipped)",
+                                       f"visited = {exe[2]:.3f} of the nominal triples (rings beyond the per-ring m cut-off are skipped); an upper bound since the "
+                                       "scalar front phase of the spin-2 kernels issues 1 instead of 4 recurrence DFMAs for the triples it covers",
                 "peak_3operand": round(fp64_3op, 3),
                 "peak_3operand_note": "DFMA with three distinct vector-register operands (no operand-reuse-cache hit): the register file "
                                       "feeds one 64-bit operand per cycle per scheduler, so such a DFMA issues every 3 cycles instead of 2",
